@@ -1,0 +1,121 @@
+/* wsae.h — C ABI of libwsae_sm100.so: the B200 (sm_100a) TopK-SAE train-step kernels.
+ *
+ * The reference (omarkhursheed/whisper-sae) is pure PyTorch and has no FFI; each entry point
+ * below cites the reference lines (under /root/reference/src/whisper_sae/) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors); the library never
+ *     allocates, frees or retains them past the call;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 ok; <0 argument/shape error (WSAE_E_*); >0 a cudaError_t; >=1000 is
+ *     1000 + CUresult from the tensor-map encoder;
+ *   - no global mutable state besides per-device function attributes; safe to call from
+ *     different host threads on different streams/devices.
+ */
+#ifndef WSAE_H_
+#define WSAE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSAE_OK 0
+#define WSAE_E_BADARG (-1)
+#define WSAE_E_UNSUPPORTED (-2)
+#define WSAE_E_NODRIVER (-3)
+
+typedef void* wsae_stream_t; /* cudaStream_t */
+
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 100). */
+int wsae_abi_version(void);
+
+/* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
+ * Packed row layout: `terms` blocks of dp = round_up(d, 8) bf16 columns (split-bf16 pieces), then
+ * a 16-column bias block, zero-padded to Kp = round_up(terms*dp + 16, 64).  terms: 1 = bf16,
+ * 3 = ~2^-16, 6 = fp32-grade.  Rows >= B (resp. F) up to Bp (Fp) are written as zeros.
+ * Bp must be a multiple of 128 and Fp a multiple of 256 for wsae_encode_topk. */
+int wsae_packed_k(int d, int terms, int* dp_out, int* used_cols_out, int* kp_out);
+int wsae_pack_activations(const float* x, const float* b_pre /*nullable*/, int B, int Bp, int d,
+                          int terms, void* a_packed /*bf16 [Bp,Kp]*/, wsae_stream_t stream);
+int wsae_pack_encoder(const float* w_enc /*[F,d]*/, const float* b_enc /*[F] nullable*/, int F,
+                      int Fp, int d, int terms, void* w_packed /*bf16 [Fp,Kp]*/,
+                      wsae_stream_t stream);
+
+/* ---- K1: encoder GEMM + fused per-row TopK (sae/model.py:111 Linear, :114 torch.topk) ---------
+ * pre = A' . W'^T on tcgen05 tensor cores (fp32 accumulate in TMEM); the [B,F] pre-activations
+ * are never written.  Emits, per row, the k largest pre-activations (signed, pre-ReLU) and their
+ * feature indices, unordered.  Ties at the k-th value resolve to the lowest feature index.
+ * nsplit > 1 splits F across CTAs (latency at small B); part_* are [B, nsplit_eff*k] scratch
+ * (nsplit_eff from wsae_encode_effective_splits) and may be NULL when nsplit == 1.  k <= 64. */
+int wsae_encode_effective_splits(int F, int nsplit);
+int wsae_encode_topk(const void* a_packed, const void* w_packed, int B, int Bp, int F, int Fp,
+                     int Kp, int k_used_cols, int k, int nsplit, float* part_val,
+                     int32_t* part_idx, float* out_val /*[B,k]*/, int32_t* out_idx /*[B,k]*/,
+                     wsae_stream_t stream);
+
+/* ---- K2: k-sparse decode + MSE + L0 + fired stamps (sae/model.py:116,129,145,148,174-181) -----
+ * recon = sum_j relu(val_j) * W_decT[idx_j,:] + b_dec (+ b_pre);  resid = recon - target.
+ * stats (16 bytes, caller-zeroed): { double sse; uint64 l0_count }.
+ * If last_activated/step_count are non-NULL (training mode), last_activated[f] = *step_count + 1
+ * for every feature with a selected value > 0 (the +1 on step_count itself is
+ * wsae_counters_update).  w_decT is [F,d] fp32 (w_is_bf16 = 0) or bf16 (1). */
+int wsae_decode_mse(const float* target, const void* w_decT, int w_is_bf16, const float* b_dec,
+                    const float* b_pre /*nullable*/, const int32_t* idx, const float* val, int B,
+                    int d, int F, int k, float* resid /*nullable [B,d]*/,
+                    float* recon /*nullable [B,d]*/, void* stats /*nullable*/,
+                    long long* last_activated /*nullable [F]*/,
+                    const long long* step_count /*nullable*/, wsae_stream_t stream);
+
+/* ---- K3: sparse backward (autograd of sae/model.py:108-145, run at sae/training.py:184) -------
+ * s = coef * (*grad_out) with coef = 2 / (B_total * d).  Accumulates (+=) into the caller-zeroed
+ * gradient buffers; any of d_w_enc / d_w_decT / d_b_enc / d_b_dec / dpre_val may be NULL to skip
+ * that output.  dpre_val[b,j] = [val>0] * s * (resid_b . W_decT[idx,:]).  d % 4 == 0. */
+int wsae_backward_sparse(const float* resid, const float* x /*nullable if !d_w_enc*/,
+                         const float* b_pre /*nullable*/, const void* w_decT, int w_is_bf16,
+                         const int32_t* idx, const float* val, const float* grad_out /*nullable*/,
+                         float coef, int B, int d, int F, int k, float* d_w_enc /*[F,d]*/,
+                         float* d_w_decT /*[F,d]*/, float* d_b_enc /*[F]*/, float* d_b_dec /*[d]*/,
+                         float* dpre_val /*[B,k]*/, wsae_stream_t stream);
+/* db_pre = db_dec - db_enc . W_enc  (overwrites d_b_pre). */
+int wsae_bpre_grad(const float* d_b_dec, const float* d_b_enc, const float* w_enc, int F, int d,
+                   float* d_b_pre, wsae_stream_t stream);
+/* dx = dpre . W_enc (- g if subtract_g): only needed when the input requires grad. */
+int wsae_input_grad(const float* resid, const float* w_enc, const int32_t* idx,
+                    const float* dpre_val, const float* grad_out, float coef, int B, int d, int F,
+                    int k, int subtract_g, float* dx, wsae_stream_t stream);
+
+/* ---- K4: tensor-core weight gradients (autograd `mm`s of sae/model.py:111,129) ----------------
+ * dW[F,d] += P^T . R, with P the k-sparse [B,F] matrix given as (idx, pval)[B,k] and R a dense
+ * bf16 [B,d] matrix; tcgen05 GEMM with the sparse operand expanded to dense bf16 tiles in shared
+ * memory.  Used for dW_enc (pval = dpre_val, R = bf16(x - b_pre)) and dW_decT (pval = relu(val),
+ * R = bf16(s * resid)).  Requires the bucket arrays from wsae_bucket_by_tile. (see wsae_wgrad_gemm.cu) */
+
+/* ---- K5: elementwise / reductions ------------------------------------------------------------
+ * renorm: rows of W_decT /= max(||row||, eps)  (sae/model.py:91-96, F.normalize(dim=0), eps 1e-12);
+ *         optionally refreshes the bf16 shadow in the same pass.
+ * counters: if bump, *step_count += 1 (model.py:174); *dead_count = #{f: step - last[f] > thr}
+ *         (model.py:183-195). */
+int wsae_renorm_decoder(float* w_decT, int F, int d, float eps, void* bf16_shadow /*nullable*/,
+                        wsae_stream_t stream);
+int wsae_counters_update(const long long* last_activated, long long* step_count, int F,
+                         long long threshold, int bump, long long* dead_count /*nullable*/,
+                         wsae_stream_t stream);
+/* hidden[B,F] = scatter(relu(val)) (sae/model.py:115-116) for API callers that need it dense. */
+int wsae_densify_hidden(const int32_t* idx, const float* val, int B, int F, int k, float* hidden,
+                        wsae_stream_t stream);
+int wsae_cast_bf16(const float* src, void* dst_bf16, long long n, wsae_stream_t stream);
+/* *out += sum(g^2) (double): building block of clip_grad_norm_ (sae/training.py:188-191). */
+int wsae_sumsq(const float* g, long long n, double* out, wsae_stream_t stream);
+/* Clip scale + AdamW in one pass (sae/training.py:187-194, torch.optim.AdamW semantics).
+ * hyper (device, 8 floats) = {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t),
+ * max_norm}; grad_sumsq (device double, nullable) = total squared grad norm over all params. */
+int wsae_fused_adamw(float* p, const float* grad, float* m, float* v, long long n,
+                     const float* hyper, const double* grad_sumsq, wsae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSAE_H_ */

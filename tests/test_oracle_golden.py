@@ -1,0 +1,113 @@
+"""Pin the CPU oracle against golden vectors produced by the live reference
+(oracle/make_golden.py).  CPU-only; runs in the build container and on the GPU box."""
+
+import pytest
+import torch
+
+from oracle import topk_sae_oracle as O
+from tests.conftest import load_golden
+
+CASES = ["small_64x256", "tiny_test_384x3072", "mid_128x1024_k32"]
+
+
+def _check_digest(t: torch.Tensor, dg: dict, rtol: float, atol: float = 1e-7):
+    assert tuple(t.shape) == tuple(dg["shape"])
+    td = t.double().reshape(-1)
+    scale = max(dg["abs_sum"], 1e-30)
+    assert abs(td.sum().item() - dg["sum"]) <= rtol * scale + atol
+    assert abs(td.abs().sum().item() - dg["abs_sum"]) <= rtol * scale + atol
+    sample = t.reshape(-1)[:: dg["sample_stride"]]
+    torch.testing.assert_close(sample, dg["sample"], rtol=rtol * 50, atol=rtol * dg["abs_sum"] / td.numel())
+
+
+def _run_oracle(fx):
+    r = fx["recipe"]
+    torch.manual_seed(r["model_seed"])
+    state = O.init_state(r["d"], r["F"])
+    opt = O.AdamWState()
+    x_all = O.synthetic_activations(r["B"] * r["steps"], r["d"], r["data_seed"])
+    lrs = O.lr_sequence(r["lr"], r["total_steps"], r["warmup"])
+    results = []
+    for s in range(r["steps"]):
+        xb = x_all[s * r["B"]:(s + 1) * r["B"]]
+        results.append(O.train_step(state, opt, xb, r["k"], lrs[s], gradient_clip=r["gradient_clip"],
+                                    weight_decay=r["weight_decay"], dead_threshold=r["dead_threshold"]))
+    return state, results, lrs
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_init_matches_reference_rng(name):
+    fx = load_golden(name)
+    r = fx["recipe"]
+    torch.manual_seed(r["model_seed"])
+    state = O.init_state(r["d"], r["F"])
+    for n, dg in fx["init_digest"].items():
+        _check_digest(state[n], dg, rtol=1e-7)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_steps_match_reference(name):
+    fx = load_golden(name)
+    state, results, lrs = _run_oracle(fx)
+    for s, (res, ref) in enumerate(zip(results, fx["per_step"])):
+        assert res.loss == pytest.approx(ref["loss"], rel=2e-6), f"step {s}"
+        assert res.l0 == pytest.approx(ref["l0"], rel=1e-6)
+        assert res.dead_feature_ratio == pytest.approx(ref["dead_feature_ratio"], abs=1e-7)
+        assert lrs[s] == pytest.approx(ref["lr_used"], rel=1e-9)
+    # integer state is bit-exact
+    assert torch.equal(state["feature_last_activated"], fx["final_counters"]["feature_last_activated"])
+    assert int(state["step_count"]) == int(fx["final_counters"]["step_count"])
+    for n in O.PARAM_ORDER:
+        ref = fx["final_params"][n]
+        if isinstance(ref, dict):
+            _check_digest(state[n], ref, rtol=2e-6)
+        else:
+            torch.testing.assert_close(state[n], ref, rtol=2e-5, atol=2e-7)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_first_step_topk_and_grads(name):
+    fx = load_golden(name)
+    r = fx["recipe"]
+    torch.manual_seed(r["model_seed"])
+    state = O.init_state(r["d"], r["F"])
+    xb = O.synthetic_activations(r["B"] * r["steps"], r["d"], r["data_seed"])[: r["B"]]
+    fwd = O.forward(state, xb, r["k"], training=True)
+    first = fx["first_step"]
+    assert torch.equal(torch.sort(fwd.idx, -1).values.to(torch.int32), first["topk_idx_sorted"])
+    assert fwd.loss.item() == pytest.approx(first["loss"], rel=2e-6)
+    assert fwd.l0.item() == pytest.approx(first["l0"], rel=1e-6)
+    grads = O.backward(state, xb, fwd)
+    for n in O.PARAM_ORDER:
+        ref = first["grads"][n]
+        if isinstance(ref, dict):
+            _check_digest(grads[n], ref, rtol=1e-5)
+        else:
+            torch.testing.assert_close(grads[n], ref, rtol=1e-4, atol=1e-9)
+
+
+def test_dead_feature_counters_fixed_row():
+    """The reference's exactly-4-alive scenario (tests/test_sae_model.py:251-294)."""
+    fx = load_golden("dead_fixed_row")
+    r = fx["recipe"]
+    torch.manual_seed(r["model_seed"])
+    state = O.init_state(r["d"], r["F"])
+    x = torch.randn(1, r["d"], generator=torch.Generator().manual_seed(r["x_seed"]))
+    for _ in range(r["steps"]):
+        O.forward(state, x, r["k"], training=True)
+    assert int(state["step_count"]) == fx["step_count"]
+    assert torch.equal(state["feature_last_activated"], fx["feature_last_activated"])
+    dead = O.dead_features(state, r["thr"])
+    assert torch.equal(dead, fx["dead_mask"])
+    assert int((~dead).sum()) == fx["num_alive"] == 4
+
+
+def test_dense_hidden_has_exactly_k_nonzeros():
+    torch.manual_seed(0)
+    state = O.init_state(64, 256)
+    x = torch.randn(100, 64)
+    fwd = O.forward(state, x, 8, training=False)
+    hidden = O.dense_hidden(fwd, 256)
+    assert ((hidden != 0).sum(-1) <= 8).all()
+    assert (hidden >= 0).all()
+    assert int(state["step_count"]) == 0  # eval mode leaves counters alone (model.py:174)

@@ -1,0 +1,266 @@
+// wsae_backward.cu — K3: sparse backward of the TopK-SAE loss (what autograd derives from
+// /root/reference/src/whisper_sae/sae/model.py:108-145 and runs at sae/training.py:184).
+//
+// With  r = recon - target,  s = grad_out * 2 / (B_total * d),  g = s * r,  h_j = relu(v_j):
+//   db_dec            = sum_b g                                   (mse_loss_backward + Linear bias)
+//   dW_decT[i_j, :]  += h_j * g                                   (decoder Linear weight grad, sparse)
+//   dv_j              = [v_j > 0] * (g . W_decT[i_j, :])          (scatter/relu/topk backward)
+//   dW_enc[i_j, :]   += dv_j * xc,   xc = x - b_pre               (encoder Linear weight grad, sparse)
+//   db_enc[i_j]      += dv_j
+//   db_pre            = db_dec - db_enc . W_enc                   (wsae_bpre_grad below)
+//   dx                = dpre . W_enc - g                          (wsae_input_grad, only if x needs grad)
+// Nothing of shape [B, F] is ever materialised.  This file is the fp32 "scatter" implementation
+// (red.global.add); the bf16 production path replaces the two weight-gradient scatters by the
+// tensor-core kernel in wsae_wgrad_gemm.cu and keeps only the dv / bias parts from here.
+#include "wsae_common.cuh"
+
+namespace wsae {
+
+template <typename WT>
+__device__ __forceinline__ float4 bw_load_w4(const WT* p);
+template <>
+__device__ __forceinline__ float4 bw_load_w4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+__device__ __forceinline__ float4 bw_load_w4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return bf16x4_to_float4(__ldg(reinterpret_cast<const uint2*>(p)));
+}
+
+// One warp per activation row.  scatter_w: 1 = also scatter-add dW_enc / dW_decT (fp32 path).
+template <typename WT, int NV>
+__global__ void __launch_bounds__(256)
+backward_sparse_kernel(const float* __restrict__ resid, const float* __restrict__ x,
+                       const float* __restrict__ b_pre, const WT* __restrict__ w_decT,
+                       const int32_t* __restrict__ idx, const float* __restrict__ val,
+                       const float* __restrict__ grad_out, float coef, int B, int d, int F, int k,
+                       float* __restrict__ d_w_enc, float* __restrict__ d_w_decT,
+                       float* __restrict__ d_b_enc, float* __restrict__ d_b_dec,
+                       float* __restrict__ dpre_val) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int warp_stride = gridDim.x * warps_per_block;
+  const float s = coef * (grad_out != nullptr ? *grad_out : 1.f);
+
+  float4 bp[NV];
+  float4 gsum[NV];
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int col = c * 128 + lane * 4;
+    bp[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < d && b_pre != nullptr) bp[c] = *reinterpret_cast<const float4*>(b_pre + col);
+  }
+
+  for (int row = warp_global; row < B; row += warp_stride) {
+    float4 g[NV], xc[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int col = c * 128 + lane * 4;
+      g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xc[c] = g[c];
+      if (col < d) {
+        const float4 r = *reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * d + col);
+        g[c] = make_float4(s * r.x, s * r.y, s * r.z, s * r.w);
+        gsum[c].x += g[c].x; gsum[c].y += g[c].y; gsum[c].z += g[c].z; gsum[c].w += g[c].w;
+        if (d_w_enc != nullptr) {
+          const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d + col);
+          xc[c] = make_float4(xv.x - bp[c].x, xv.y - bp[c].y, xv.z - bp[c].z, xv.w - bp[c].w);
+        }
+      }
+    }
+    const int32_t* irow = idx + static_cast<size_t>(row) * k;
+    const float* vrow = val + static_cast<size_t>(row) * k;
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int jj = j0 + lane;
+      int32_t my_i = -1;
+      float my_v = 0.f;
+      if (jj < k) {
+        my_i = irow[jj];
+        my_v = vrow[jj];
+      }
+      const bool fired = (my_i >= 0) && (my_i < F) && (my_v > 0.f);
+      float my_dv = 0.f;
+      uint32_t m = __ballot_sync(0xffffffffu, fired);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int32_t f = __shfl_sync(0xffffffffu, my_i, src);
+        const float h = __shfl_sync(0xffffffffu, my_v, src);
+        const WT* wrow = w_decT + static_cast<size_t>(f) * d;
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+          const int col = c * 128 + lane * 4;
+          if (col < d) {
+            const float4 w = bw_load_w4<WT>(wrow + col);
+            dot = fmaf(g[c].x, w.x, dot);
+            dot = fmaf(g[c].y, w.y, dot);
+            dot = fmaf(g[c].z, w.z, dot);
+            dot = fmaf(g[c].w, w.w, dot);
+          }
+        }
+        dot = warp_sum(dot);  // dv for feature f of this row (v > 0 already known)
+        if (lane == src) my_dv = dot;
+        if (d_w_decT != nullptr) {
+          float* drow = d_w_decT + static_cast<size_t>(f) * d;
+#pragma unroll
+          for (int c = 0; c < NV; ++c) {
+            const int col = c * 128 + lane * 4;
+            if (col < d) red_add_f32x4(drow + col, h * g[c].x, h * g[c].y, h * g[c].z, h * g[c].w);
+          }
+        }
+        if (d_w_enc != nullptr) {
+          float* erow = d_w_enc + static_cast<size_t>(f) * d;
+#pragma unroll
+          for (int c = 0; c < NV; ++c) {
+            const int col = c * 128 + lane * 4;
+            if (col < d)
+              red_add_f32x4(erow + col, dot * xc[c].x, dot * xc[c].y, dot * xc[c].z, dot * xc[c].w);
+          }
+        }
+      }
+      if (jj < k) {
+        if (dpre_val != nullptr) dpre_val[static_cast<size_t>(row) * k + jj] = my_dv;
+        if (fired && d_b_enc != nullptr) atomicAdd(d_b_enc + my_i, my_dv);
+      }
+    }
+  }
+
+  // db_dec: per-block shared reduction, then one atomic per column per block
+  extern __shared__ float s_g[];  // [d]
+  for (int i = threadIdx.x; i < d; i += blockDim.x) s_g[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int col = c * 128 + lane * 4;
+    if (col < d) {
+      atomicAdd(&s_g[col + 0], gsum[c].x);
+      atomicAdd(&s_g[col + 1], gsum[c].y);
+      atomicAdd(&s_g[col + 2], gsum[c].z);
+      atomicAdd(&s_g[col + 3], gsum[c].w);
+    }
+  }
+  __syncthreads();
+  if (d_b_dec != nullptr)
+    for (int i = threadIdx.x; i < d; i += blockDim.x) atomicAdd(d_b_dec + i, s_g[i]);
+}
+
+// db_pre[c] = db_dec[c] - sum_f db_enc[f] * W_enc[f, c].   grid.x tiles columns, grid.y splits F.
+__global__ void __launch_bounds__(256)
+bpre_grad_kernel(const float* __restrict__ d_b_dec, const float* __restrict__ d_b_enc,
+                 const float* __restrict__ w_enc, int F, int d, int f_per_block,
+                 float* __restrict__ d_b_pre) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f0 = blockIdx.y * f_per_block;
+  const int f1 = min(F, f0 + f_per_block);
+  if (col >= d) return;
+  float acc = 0.f;
+  for (int f = f0; f < f1; ++f) acc = fmaf(d_b_enc[f], w_enc[static_cast<size_t>(f) * d + col], acc);
+  float out = -acc;
+  if (blockIdx.y == 0) out += d_b_dec[col];
+  atomicAdd(d_b_pre + col, out);
+}
+
+// dx[b, :] = sum_j dv_j * W_enc[i_j, :] - g[b, :]    (only when the input itself requires grad)
+__global__ void __launch_bounds__(256)
+input_grad_kernel(const float* __restrict__ resid, const float* __restrict__ w_enc,
+                  const int32_t* __restrict__ idx, const float* __restrict__ dpre_val,
+                  const float* __restrict__ grad_out, float coef, int B, int d, int F, int k,
+                  int subtract_g, float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float s = coef * (grad_out != nullptr ? *grad_out : 1.f);
+  for (int col = lane; col < d; col += 32) {
+    float acc = subtract_g ? -s * resid[static_cast<size_t>(row) * d + col] : 0.f;
+    for (int j = 0; j < k; ++j) {
+      const int32_t f = idx[static_cast<size_t>(row) * k + j];
+      const float dv = dpre_val[static_cast<size_t>(row) * k + j];
+      if (f >= 0 && f < F && dv != 0.f) acc = fmaf(dv, w_enc[static_cast<size_t>(f) * d + col], acc);
+    }
+    dx[static_cast<size_t>(row) * d + col] = acc;
+  }
+}
+
+template <typename WT>
+static int launch_backward(const float* resid, const float* x, const float* b_pre, const void* w,
+                           const int32_t* idx, const float* val, const float* grad_out, float coef,
+                           int B, int d, int F, int k, float* d_w_enc, float* d_w_decT,
+                           float* d_b_enc, float* d_b_dec, float* dpre_val, cudaStream_t stream) {
+  if (d % 4 != 0 || d > 128 * 16) return kUnsupported;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int threads = 256, wpb = threads / 32;
+  int blocks = ceil_div(B, wpb);
+  const int cap = sms * 4;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = static_cast<size_t>(d) * sizeof(float);
+  const WT* wt = static_cast<const WT*>(w);
+#define WSAE_BWD_CASE(NVV)                                                                       \
+  backward_sparse_kernel<WT, NVV><<<blocks, threads, smem, stream>>>(                            \
+      resid, x, b_pre, wt, idx, val, grad_out, coef, B, d, F, k, d_w_enc, d_w_decT, d_b_enc,      \
+      d_b_dec, dpre_val)
+  const int nv = ceil_div(d, 128);
+  if (nv <= 1) WSAE_BWD_CASE(1);
+  else if (nv <= 2) WSAE_BWD_CASE(2);
+  else if (nv <= 3) WSAE_BWD_CASE(3);
+  else if (nv <= 4) WSAE_BWD_CASE(4);
+  else if (nv <= 6) WSAE_BWD_CASE(6);
+  else if (nv <= 8) WSAE_BWD_CASE(8);
+  else if (nv <= 10) WSAE_BWD_CASE(10);
+  else if (nv <= 12) WSAE_BWD_CASE(12);
+  else WSAE_BWD_CASE(16);
+#undef WSAE_BWD_CASE
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace wsae
+
+using namespace wsae;
+
+extern "C" int wsae_backward_sparse(const float* resid, const float* x, const float* b_pre,
+                                    const void* w_decT, int w_is_bf16, const int32_t* idx,
+                                    const float* val, const float* grad_out, float coef, int B,
+                                    int d, int F, int k, float* d_w_enc, float* d_w_decT,
+                                    float* d_b_enc, float* d_b_dec, float* dpre_val,
+                                    cudaStream_t stream) {
+  if (!resid || !w_decT || !idx || !val) return kBadArg;
+  if (d_w_enc != nullptr && x == nullptr) return kBadArg;
+  if (B <= 0 || d <= 0 || F <= 0 || k <= 0) return kBadArg;
+  if (w_is_bf16)
+    return launch_backward<__nv_bfloat16>(resid, x, b_pre, w_decT, idx, val, grad_out, coef, B, d,
+                                          F, k, d_w_enc, d_w_decT, d_b_enc, d_b_dec, dpre_val,
+                                          stream);
+  return launch_backward<float>(resid, x, b_pre, w_decT, idx, val, grad_out, coef, B, d, F, k,
+                                d_w_enc, d_w_decT, d_b_enc, d_b_dec, dpre_val, stream);
+}
+
+extern "C" int wsae_bpre_grad(const float* d_b_dec, const float* d_b_enc, const float* w_enc,
+                              int F, int d, float* d_b_pre, cudaStream_t stream) {
+  if (!d_b_dec || !d_b_enc || !w_enc || !d_b_pre || F <= 0 || d <= 0) return kBadArg;
+  cudaError_t e = cudaMemsetAsync(d_b_pre, 0, static_cast<size_t>(d) * sizeof(float), stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int threads = 128;
+  int fsplit = F / 256;
+  if (fsplit < 1) fsplit = 1;
+  if (fsplit > 512) fsplit = 512;
+  const int fpb = ceil_div(F, fsplit);
+  dim3 grid(ceil_div(d, threads), ceil_div(F, fpb));
+  bpre_grad_kernel<<<grid, threads, 0, stream>>>(d_b_dec, d_b_enc, w_enc, F, d, fpb, d_b_pre);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int wsae_input_grad(const float* resid, const float* w_enc, const int32_t* idx,
+                               const float* dpre_val, const float* grad_out, float coef, int B,
+                               int d, int F, int k, int subtract_g, float* dx,
+                               cudaStream_t stream) {
+  if (!resid || !w_enc || !idx || !dpre_val || !dx) return kBadArg;
+  const int warps = 8;
+  input_grad_kernel<<<ceil_div(B, warps), warps * 32, 0, stream>>>(
+      resid, w_enc, idx, dpre_val, grad_out, coef, B, d, F, k, subtract_g, dx);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,217 @@
+// wsae_elementwise.cu — K5 and friends: HBM-bound fused elementwise / reduction kernels.
+//
+//   wsae_renorm_decoder      model.py:91-96   W_dec <- F.normalize(W_dec, dim=0)   (rows of W_decT)
+//   wsae_counters_update     model.py:174,183-195   step_count += 1 ; dead = (step - last) > thr
+//   wsae_densify_hidden      model.py:115-116 zeros_like + scatter_(relu(topk_values))
+//   wsae_cast_bf16           bf16 shadow of the decoder for the gather kernels
+//   wsae_fused_adamw         training.py:187-198   clip (global-norm scale) + AdamW (+ renorm input)
+//   wsae_sumsq               training.py:188-191   squared L2 norm of a gradient tensor (clip_grad_norm_)
+#include "wsae_common.cuh"
+
+namespace wsae {
+
+// One warp per feature row of W_decT[F, d]: row /= max(||row||_2, eps).  Optionally also emits the
+// bf16 shadow row so the refresh costs no extra pass.
+__global__ void __launch_bounds__(256)
+renorm_rows_kernel(float* __restrict__ w, int F, int d, float eps,
+                   __nv_bfloat16* __restrict__ shadow) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= F) return;
+  float* p = w + static_cast<size_t>(row) * d;
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = p[c];
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float denom = fmaxf(sqrtf(ss), eps);
+  for (int c = lane; c < d; c += 32) {
+    const float v = p[c] / denom;
+    p[c] = v;
+    if (shadow != nullptr) shadow[static_cast<size_t>(row) * d + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// Single block: optional step_count bump, then count dead features against the *new* step.
+__global__ void __launch_bounds__(1024)
+counters_update_kernel(const long long* __restrict__ last_activated, long long* step_count, int F,
+                       long long threshold, int bump, long long* __restrict__ dead_count) {
+  __shared__ long long s_step;
+  __shared__ int s_part[32];
+  if (threadIdx.x == 0) {
+    long long sc = *step_count + (bump ? 1 : 0);
+    if (bump) *step_count = sc;
+    s_step = sc;
+  }
+  __syncthreads();
+  const long long sc = s_step;
+  int c = 0;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) c += ((sc - last_activated[f]) > threshold) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0 && dead_count != nullptr) {
+    long long t = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += s_part[w];
+    *dead_count = t;
+  }
+}
+
+// hidden[B, F] = 0 ; hidden[b, idx[b, j]] = relu(val[b, j]).  One block per row.
+__global__ void __launch_bounds__(256)
+densify_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, int B, int F, int k,
+               float* __restrict__ hidden) {
+  const int row = blockIdx.x;
+  float* h = hidden + static_cast<size_t>(row) * F;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) h[c] = 0.f;
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const int32_t f = idx[static_cast<size_t>(row) * k + j];
+    const float v = val[static_cast<size_t>(row) * k + j];
+    if (f >= 0 && f < F) h[f] = fmaxf(v, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  } else {
+    for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+  }
+}
+
+// out[0] += sum(g^2)  (double accumulator; caller zeroes it).  Grid-stride, float4.
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ out) {
+  float acc = 0.f;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
+  size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  for (; i + 3 < n; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(g + i);
+    acc = fmaf(v.x, v.x, acc);
+    acc = fmaf(v.y, v.y, acc);
+    acc = fmaf(v.z, v.z, acc);
+    acc = fmaf(v.w, v.w, acc);
+  }
+  if (i < n && i + 3 >= n)
+    for (size_t j = i; j < n; ++j) acc = fmaf(g[j], g[j], acc);
+  __shared__ float s[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += static_cast<double>(s[w]);
+    atomicAdd(out, t);
+  }
+}
+
+// AdamW with the clip_grad_norm_ scale folded in (torch.optim.AdamW semantics, amsgrad=False):
+//   g   = grad * min(1, max_norm / (sqrt(sumsq) + 1e-6))
+//   p  *= 1 - lr * wd ; m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g
+//   p  -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// hyper[] lives in device memory so a captured CUDA graph can be replayed with new lr / step:
+//   hyper = {lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2_sqrt, max_norm}
+__global__ void __launch_bounds__(256)
+fused_adamw_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m,
+                   float* __restrict__ v, size_t n, const float* __restrict__ hyper,
+                   const double* __restrict__ grad_sumsq) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const float bc1 = hyper[5], bc2s = hyper[6], max_norm = hyper[7];
+  float clip = 1.f;
+  if (grad_sumsq != nullptr && max_norm > 0.f) {
+    const float total = static_cast<float>(sqrt(*grad_sumsq));
+    const float c = max_norm / (total + 1e-6f);
+    clip = c < 1.f ? c : 1.f;
+  }
+  const float step_size = lr / bc1;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float g = grad[i] * clip;
+    float pv = p[i];
+    pv *= 1.f - lr * wd;
+    const float mv = m[i] + (g - m[i]) * (1.f - b1);          // lerp form, as torch does
+    const float vv = b2 * v[i] + (1.f - b2) * g * g;
+    const float denom = sqrtf(vv) / bc2s + eps;
+    pv -= step_size * (mv / denom);
+    p[i] = pv;
+    m[i] = mv;
+    v[i] = vv;
+  }
+}
+
+}  // namespace wsae
+
+using namespace wsae;
+
+extern "C" int wsae_renorm_decoder(float* w_decT, int F, int d, float eps, void* bf16_shadow,
+                                   cudaStream_t stream) {
+  if (!w_decT || F <= 0 || d <= 0) return kBadArg;
+  const int warps = 8;
+  renorm_rows_kernel<<<ceil_div(F, warps), warps * 32, 0, stream>>>(
+      w_decT, F, d, eps, static_cast<__nv_bfloat16*>(bf16_shadow));
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int wsae_counters_update(const long long* last_activated, long long* step_count, int F,
+                                    long long threshold, int bump, long long* dead_count,
+                                    cudaStream_t stream) {
+  if (!last_activated || !step_count || F <= 0) return kBadArg;
+  counters_update_kernel<<<1, 1024, 0, stream>>>(last_activated, step_count, F, threshold, bump,
+                                                 dead_count);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int wsae_densify_hidden(const int32_t* idx, const float* val, int B, int F, int k,
+                                   float* hidden, cudaStream_t stream) {
+  if (!idx || !val || !hidden || B <= 0 || F <= 0 || k <= 0) return kBadArg;
+  densify_kernel<<<B, 256, 0, stream>>>(idx, val, B, F, k, hidden);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int wsae_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
+  if (!src || !dst || n <= 0) return kBadArg;
+  const size_t groups = (static_cast<size_t>(n) + 3) / 4;
+  const unsigned blocks = static_cast<unsigned>((groups + 255) / 256);
+  cast_bf16_kernel<<<blocks, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst),
+                                               static_cast<size_t>(n));
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int wsae_sumsq(const float* g, long long n, double* out, cudaStream_t stream) {
+  if (!g || !out || n <= 0) return kBadArg;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t want = (static_cast<size_t>(n) / 4 + 255) / 256;
+  if (want < 1) want = 1;
+  const size_t cap = static_cast<size_t>(sms) * 8;
+  const unsigned blocks = static_cast<unsigned>(want < cap ? want : cap);
+  sumsq_kernel<<<blocks, 256, 0, stream>>>(g, static_cast<size_t>(n), out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int wsae_fused_adamw(float* p, const float* grad, float* m, float* v, long long n,
+                                const float* hyper, const double* grad_sumsq,
+                                cudaStream_t stream) {
+  if (!p || !grad || !m || !v || !hyper || n <= 0) return kBadArg;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t want = (static_cast<size_t>(n) + 255) / 256;
+  const size_t cap = static_cast<size_t>(sms) * 16;
+  const unsigned blocks = static_cast<unsigned>(want < cap ? want : cap);
+  fused_adamw_kernel<<<blocks, 256, 0, stream>>>(p, grad, m, v, static_cast<size_t>(n), hyper,
+                                                 grad_sumsq);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,527 @@
+// wsae_encode_topk.cu — K1: dense encoder GEMM on tcgen05/TMEM with the per-row TopK fused
+// into the epilogue, so the [B, F] pre-activation tensor never reaches HBM.
+//
+// Replaces (reference, /root/reference/src/whisper_sae/sae/model.py):
+//   :108  x_centered = x - b_pre            (done by the pack kernel, wsae_pack.cu)
+//   :111  pre = encoder(x_centered)         (this GEMM; the bias rides in 16 extra K columns)
+//   :114  torch.topk(pre, k, dim=-1)        (epilogue below; values kept in fp32)
+//
+// Operands are *packed* bf16 matrices produced by wsae_pack.cu:
+//   A' [Bp, Kp]  rows = activations, K-major, Kp = T*dp + 16 (+ zero pad to a multiple of 64)
+//   W' [Fp, Kp]  rows = features,    K-major
+// T = 1 is plain bf16; T = 3 / 6 concatenates split-bf16 pieces along K so the same kernel
+// produces fp32-grade results (the "fp32 verification mode").
+//
+// Kernel shape: one CTA per SM, persistent over (row-block, F-split) work items.
+//   warp 0      TMA producer   (A' 128x64 + W' 256x64 bf16 tiles, SWIZZLE_128B, 3-stage ring)
+//   warp 1      MMA issuer     (tcgen05.mma 128x256x16, fp32 accumulators double-buffered in TMEM)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       (tcgen05.ld 32x32b: one thread owns one activation row)
+//
+// Epilogue TopK: each thread streams its row's accumulator columns, appends values above a
+// running threshold tau to a thread-private candidate list in shared memory and, whenever a
+// list in the warp is nearly full, raises tau by a bisection select over the list (in
+// registers).  The final select per work item is exact (ties broken towards the lower index).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "wsae_common.cuh"
+
+namespace wsae {
+
+constexpr int kBM = 128;   // rows per CTA tile  (= TMEM lanes)
+constexpr int kBN = 256;   // features per MMA tile (= TMEM columns per accumulator stage)
+constexpr int kBK = 64;    // bf16 K elements per pipeline stage (= one 128-byte swizzle row)
+constexpr int kAStage = kBM * kBK * 2;
+constexpr int kBStage = kBN * kBK * 2;
+constexpr int kChunk = 16;  // accumulator columns per tcgen05.ld
+constexpr int kSlack = 8;   // intermediate selects may keep up to k + kSlack candidates
+
+template <int CAP, int STAGES>
+struct EncodeSmem {
+  static constexpr int kPipeBytes = STAGES * (kAStage + kBStage);
+  static constexpr int kCandBytes = CAP * kBM * 8;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kPipeBytes + kCandBytes + kBarBytes + 1024;  // +1024 align slack
+};
+
+// Wait for the tcgen05.ld that filled r[]; the "+r" operands pin the uses after the wait.
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]),
+                 "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
+                 "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+// Thread-private candidate list: slot s of row r lives at base[s * 128 + r].
+// Raise tau so that at most k + slack candidates (exactly k when slack == 0) survive, and
+// compact the list in place.  Warp-synchronous: every lane of the warp must call it.
+template <int CAP>
+__device__ __forceinline__ void topk_compact(float* cv, uint32_t* ci, int& cnt, float& tau, int k,
+                                             int slack) {
+  uint32_t key[CAP];
+  uint32_t hi = 0;
+#pragma unroll
+  for (int s = 0; s < CAP; ++s) {
+    key[s] = (s < cnt) ? f2key(cv[s * kBM]) : 0u;
+    hi = max(hi, key[s]);
+  }
+  uint32_t lo = f2key(tau);  // invariant: count(key > lo) >= min(cnt, k); count(key > hi) < k
+  int c_lo = cnt;
+  bool done = (c_lo <= k + slack);
+  while (true) {
+    const bool active = !done && (hi - lo > 1u);
+    if (!__any_sync(0xffffffffu, active)) break;
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+#pragma unroll
+    for (int s = 0; s < CAP; ++s) c += (key[s] > mid) ? 1 : 0;
+    if (active) {
+      if (c >= k) {
+        lo = mid;
+        c_lo = c;
+        done = (c <= k + slack);
+      } else {
+        hi = mid;
+      }
+    }
+  }
+  // done: keep key > lo.  otherwise hi == lo + 1 and the values equal to hi are tied across the
+  // k-th position: keep everything above hi plus the first (k - m) ties (lowest index first).
+  uint32_t thr = lo, tie_key = 0xFFFFFFFFu;
+  int tie_left = 0;
+  if (!done) {
+    int m = 0;
+#pragma unroll
+    for (int s = 0; s < CAP; ++s) m += (key[s] > hi) ? 1 : 0;
+    thr = hi;
+    tie_key = hi;
+    tie_left = k - m;
+  }
+  int w = 0;
+#pragma unroll
+  for (int s = 0; s < CAP; ++s) {
+    const uint32_t kk = key[s];
+    bool keep = kk > thr;
+    if (!keep && kk == tie_key && tie_left > 0) {
+      keep = true;
+      --tie_left;
+    }
+    if (keep) {
+      const uint32_t id = ci[s * kBM];
+      cv[w * kBM] = key2f(kk);
+      ci[w * kBM] = id;
+      ++w;
+    }
+  }
+  cnt = w;
+  if (c_lo >= k) tau = key2f(thr);
+}
+
+template <int CAP, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                   const __grid_constant__ CUtensorMap tmap_w, int B, int F, int k, int ksteps,
+                   int num_m_blocks, int num_n_tiles, int nsplit, int tiles_per_split,
+                   float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* pipe = smem;
+  float* cand_val = reinterpret_cast<float*>(smem + EncodeSmem<CAP, STAGES>::kPipeBytes);
+  uint32_t* cand_idx = reinterpret_cast<uint32_t*>(cand_val + CAP * kBM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EncodeSmem<CAP, STAGES>::kPipeBytes +
+                                               EncodeSmem<CAP, STAGES>::kCandBytes);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = ceil_div(ksteps, kBK / 16);
+  const int total_items = num_m_blocks * nsplit;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kBM);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int m_blk = item / nsplit;
+        const int sp = item - m_blk * nsplit;
+        const int t0 = sp * tiles_per_split;
+        const int t1 = min(t0 + tiles_per_split, num_n_tiles);
+        for (int nt = t0; nt < t1; ++nt) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], kAStage + kBStage);
+            uint8_t* sa = pipe + stage * (kAStage + kBStage);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+            tma_load_2d(sa + kAStage, &tmap_w, &full_bar[stage], kb * kBK, nt * kBN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t tile = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int m_blk = item / nsplit;
+      const int sp = item - m_blk * nsplit;
+      const int t0 = sp * tiles_per_split;
+      const int t1 = min(t0 + tiles_per_split, num_n_tiles);
+      for (int nt = t0; nt < t1; ++nt, ++tile) {
+        const uint32_t as = tile & 1u;
+        const uint32_t aphase = (tile >> 1) & 1u;
+        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(pipe + stage * (kAStage + kBStage));
+            const uint64_t da = umma_desc_sw128_kmajor(sa);
+            const uint64_t db = umma_desc_sw128_kmajor(sa + kAStage);
+            const int nks = min(kBK / 16, ksteps - kb * (kBK / 16));
+            for (int ks = 0; ks < nks; ++ks) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+              umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * ks), db + static_cast<uint64_t>(2 * ks),
+                        idesc, (kb | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: streaming TopK =====================
+    const int q = warp - 4;               // TMEM lane quarter this warp may read
+    const int row_in_blk = q * 32 + lane;
+    float* cv = cand_val + row_in_blk;
+    uint32_t* ci = cand_idx + row_in_blk;
+    const float neg_inf = __uint_as_float(0xff800000u);
+    uint32_t tile = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int m_blk = item / nsplit;
+      const int sp = item - m_blk * nsplit;
+      const int t0 = sp * tiles_per_split;
+      const int t1 = min(t0 + tiles_per_split, num_n_tiles);
+      int cnt = 0;
+      float tau = neg_inf;
+      for (int nt = t0; nt < t1; ++nt, ++tile) {
+        const uint32_t as = tile & 1u;
+        const uint32_t aphase = (tile >> 1) & 1u;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const int col0 = nt * kBN;
+        const int ncols = min(kBN, F - col0);
+        const int nchunks = ceil_div(ncols, kChunk);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBN;
+
+        auto process = [&](uint32_t (&r)[16], int cbase) {
+          const int lim = F - cbase;  // columns >= F are zero padding of W'
+          if (lim >= kChunk) {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+              const float v = __uint_as_float(r[j]);
+              if (v > tau) {
+                cv[cnt * kBM] = v;
+                ci[cnt * kBM] = static_cast<uint32_t>(cbase + j);
+                ++cnt;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+              const float v = __uint_as_float(r[j]);
+              if (j < lim && v > tau) {
+                cv[cnt * kBM] = v;
+                ci[cnt * kBM] = static_cast<uint32_t>(cbase + j);
+                ++cnt;
+              }
+            }
+          }
+          if (__any_sync(0xffffffffu, cnt > CAP - kChunk)) {
+            topk_compact<CAP>(cv, ci, cnt, tau, k, kSlack);
+          }
+        };
+
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr, ra);
+        for (int c = 0; c < nchunks; c += 2) {
+          tmem_ld_wait16(ra);
+          if (c + 1 < nchunks) tmem_ld16(taddr + (c + 1) * kChunk, rb);
+          process(ra, col0 + c * kChunk);
+          if (c + 1 < nchunks) {
+            tmem_ld_wait16(rb);
+            if (c + 2 < nchunks) tmem_ld16(taddr + (c + 2) * kChunk, ra);
+            process(rb, col0 + (c + 1) * kChunk);
+          }
+        }
+        // accumulator stage fully read: hand it back to the MMA warp
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+      }
+      // ---- end of work item: exact select, write k (val, idx) pairs for this row/split ----
+      topk_compact<CAP>(cv, ci, cnt, tau, k, 0);
+      const int row = m_blk * kBM + row_in_blk;
+      if (row < B) {
+        const size_t base = (static_cast<size_t>(row) * nsplit + sp) * k;
+        for (int s = 0; s < k; ++s) {
+          if (s < cnt) {
+            out_val[base + s] = cv[s * kBM];
+            out_idx[base + s] = static_cast<int32_t>(ci[s * kBM]);
+          } else {  // split narrower than k columns: pad with never-selected entries
+            out_val[base + s] = neg_inf;
+            out_idx[base + s] = -1;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Merge of per-split partial top-k lists: part_[B, nsplit*k] -> out_[B, k].  One warp per row.
+// Candidate order (split, slot) is ascending feature index, so "first tie wins" = lowest index.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMergeMaxPerLane = 64;
+
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict__ part_idx, int B,
+                  int n, int k, float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* pv = part_val + static_cast<size_t>(row) * n;
+  const int32_t* pi = part_idx + static_cast<size_t>(row) * n;
+  const int per = ceil_div(n, 32);  // <= kMergeMaxPerLane (checked on the host)
+  uint32_t key[kMergeMaxPerLane];
+  uint32_t hi = 0;
+#pragma unroll 4
+  for (int t = 0; t < kMergeMaxPerLane; ++t) {
+    const int p = t * 32 + lane;
+    uint32_t kk = 0;
+    if (t < per && p < n && pi[p] >= 0) kk = f2key(pv[p]);
+    key[t] = kk;
+    hi = max(hi, kk);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  uint32_t lo = 1u;  // below every valid key (key(-inf) = 0x007fffff), above the empty marker 0
+  bool exact = false;
+  while (hi - lo > 1u) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+#pragma unroll 4
+    for (int t = 0; t < kMergeMaxPerLane; ++t) c += (key[t] > mid) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (c >= k) {
+      lo = mid;
+      if (c == k) {
+        exact = true;
+        break;
+      }
+    } else {
+      hi = mid;
+    }
+  }
+  uint32_t thr = lo, tie_key = 0xFFFFFFFFu;
+  int tie_left = 0;
+  if (!exact) {
+    int m = 0;
+#pragma unroll 4
+    for (int t = 0; t < kMergeMaxPerLane; ++t) m += (key[t] > hi) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    thr = hi;
+    tie_key = hi;
+    tie_left = k - m;
+  }
+  int base = 0;
+  const uint32_t below = (1u << lane) - 1u;
+  for (int t = 0; t < per; ++t) {
+    const uint32_t kk = key[t];
+    const bool gt = kk > thr;
+    const bool tie = (kk == tie_key);
+    const uint32_t tie_mask = __ballot_sync(0xffffffffu, tie);
+    const bool keep = gt || (tie && (__popc(tie_mask & below) < tie_left));
+    tie_left -= __popc(tie_mask);
+    const uint32_t keep_mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int slot = base + __popc(keep_mask & below);
+      if (slot < k) {
+        const int p = t * 32 + lane;
+        out_val[static_cast<size_t>(row) * k + slot] = pv[p];
+        out_idx[static_cast<size_t>(row) * k + slot] = pi[p];
+      }
+    }
+    base += __popc(keep_mask);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess)
+      return static_cast<PFN_cuTensorMapEncodeTiled_v12000>(nullptr);
+    if (q != cudaDriverEntryPointSuccess) return static_cast<PFN_cuTensorMapEncodeTiled_v12000>(nullptr);
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+// [rows, cols] bf16 row-major (row pitch = cols * 2 bytes), box = box_rows x 64, 128B swizzle.
+static int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
+                          uint32_t box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return kNoDriver;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? kOk : static_cast<int>(1000 + r);
+}
+
+template <int CAP, int STAGES>
+static int launch_encode(const CUtensorMap& ta, const CUtensorMap& tw, int B, int F, int k,
+                         int ksteps, int num_m_blocks, int num_n_tiles, int nsplit,
+                         int tiles_per_split, float* out_val, int32_t* out_idx, int num_sms,
+                         cudaStream_t stream) {
+  auto kern = encode_topk_kernel<CAP, STAGES>;
+  constexpr int smem = EncodeSmem<CAP, STAGES>::kTotal;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set[dev] = true;
+  }
+  const int total = num_m_blocks * nsplit;
+  const int grid = total < num_sms ? total : num_sms;
+  kern<<<grid, 256, smem, stream>>>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
+                                    tiles_per_split, out_val, out_idx);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace wsae
+
+using namespace wsae;
+
+// See include/wsae.h for the contract.
+extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int B, int Bp, int F,
+                                int Fp, int Kp, int k_used_cols, int k, int nsplit,
+                                float* part_val, int32_t* part_idx, float* out_val,
+                                int32_t* out_idx, cudaStream_t stream) {
+  if (!a_packed || !w_packed || !out_val || !out_idx) return kBadArg;
+  if (B <= 0 || F <= 0 || k <= 0 || k > F) return kBadArg;
+  if (Bp % kBM != 0 || Fp % kBN != 0 || Kp % kBK != 0 || Bp < B || Fp < F) return kBadArg;
+  if (k_used_cols <= 0 || k_used_cols % 16 != 0 || k_used_cols > Kp) return kBadArg;
+  if (k > 64) return kUnsupported;
+  if (nsplit < 1) return kBadArg;
+  const int num_m_blocks = Bp / kBM;
+  const int num_n_tiles = ceil_div(F, kBN);
+  if (nsplit > num_n_tiles) nsplit = num_n_tiles;
+  int tiles_per_split = ceil_div(num_n_tiles, nsplit);
+  nsplit = ceil_div(num_n_tiles, tiles_per_split);
+  if (nsplit > 1 && (!part_val || !part_idx)) return kBadArg;
+  if (nsplit > 1 && ceil_div(nsplit * k, 32) > kMergeMaxPerLane) return kUnsupported;
+
+  CUtensorMap ta, tw;
+  int rc = make_tmap_bf16(&ta, a_packed, static_cast<uint64_t>(Bp), static_cast<uint64_t>(Kp), kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tw, w_packed, static_cast<uint64_t>(Fp), static_cast<uint64_t>(Kp), kBN);
+  if (rc) return rc;
+
+  int dev = 0, num_sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  float* kv = nsplit > 1 ? part_val : out_val;
+  int32_t* ki = nsplit > 1 ? part_idx : out_idx;
+  const int ksteps = k_used_cols / 16;
+  if (k <= 32)
+    rc = launch_encode<80, 3>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
+                              tiles_per_split, kv, ki, num_sms, stream);
+  else
+    rc = launch_encode<128, 2>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
+                               tiles_per_split, kv, ki, num_sms, stream);
+  if (rc) return rc;
+  if (nsplit > 1) {
+    const int warps = 8;
+    topk_merge_kernel<<<ceil_div(B, warps), warps * 32, 0, stream>>>(part_val, part_idx, B,
+                                                                    nsplit * k, k, out_val, out_idx);
+    rc = static_cast<int>(cudaGetLastError());
+  }
+  return rc;
+}
+
+// Number of F-splits wsae_encode_topk will actually use for a requested nsplit (so callers can
+// size part_val / part_idx = B * nsplit_eff * k entries).
+extern "C" int wsae_encode_effective_splits(int F, int nsplit) {
+  const int num_n_tiles = ceil_div(F, kBN);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > num_n_tiles) nsplit = num_n_tiles;
+  const int tps = ceil_div(num_n_tiles, nsplit);
+  return ceil_div(num_n_tiles, tps);
+}

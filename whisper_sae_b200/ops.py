@@ -1,0 +1,295 @@
+"""Tensor-level wrappers over the C ABI (``include/wsae.h``).
+
+PyTorch is used only for device memory and streams: every function here checks dtypes/layouts,
+passes raw device pointers + the current CUDA stream into ``libwsae_sm100.so`` and returns torch
+tensors.  CPU tensors are rejected — there is deliberately no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+GPU_LAUNCHES = 0  # kernels launched through this module (bench.py reports it)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors: Tensor | None) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "whisper_sae_b200 kernels run on CUDA (sm_100a) tensors only; there is no CPU "
+                "fallback (got a tensor on %s)" % t.device
+            )
+
+
+def _f32c(t: Tensor | None, name: str) -> None:
+    if t is None:
+        return
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous float32 tensor")
+
+
+def _count(n: int = 1) -> None:
+    global GPU_LAUNCHES
+    GPU_LAUNCHES += n
+
+
+@dataclass(frozen=True)
+class PackedShape:
+    d: int
+    terms: int
+    dp: int
+    used_cols: int
+    kp: int
+
+
+def packed_shape(d: int, terms: int) -> PackedShape:
+    lib = _lib.load()
+    dp, used, kp = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.wsae_packed_k(d, terms, ctypes.byref(dp), ctypes.byref(used), ctypes.byref(kp)),
+               "wsae_packed_k")
+    return PackedShape(d, terms, dp.value, used.value, kp.value)
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def pack_activations(x: Tensor, b_pre: Tensor | None, terms: int, out: Tensor | None = None) -> Tensor:
+    _need_cuda(x, b_pre)
+    _f32c(x, "x")
+    _f32c(b_pre, "b_pre")
+    B, d = x.shape
+    ps = packed_shape(d, terms)
+    Bp = _round_up(B, 128)
+    if out is None or out.shape != (Bp, ps.kp):
+        out = torch.empty((Bp, ps.kp), dtype=torch.bfloat16, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.wsae_pack_activations(_ptr(x), _ptr(b_pre), B, Bp, d, terms, _ptr(out), _stream()),
+               "wsae_pack_activations")
+    _count()
+    return out
+
+
+def pack_encoder(w_enc: Tensor, b_enc: Tensor | None, terms: int, out: Tensor | None = None) -> Tensor:
+    _need_cuda(w_enc, b_enc)
+    _f32c(w_enc, "encoder.weight")
+    _f32c(b_enc, "encoder.bias")
+    F, d = w_enc.shape
+    ps = packed_shape(d, terms)
+    Fp = _round_up(F, 256)
+    if out is None or out.shape != (Fp, ps.kp):
+        out = torch.empty((Fp, ps.kp), dtype=torch.bfloat16, device=w_enc.device)
+    lib = _lib.load()
+    _lib.check(lib.wsae_pack_encoder(_ptr(w_enc), _ptr(b_enc), F, Fp, d, terms, _ptr(out), _stream()),
+               "wsae_pack_encoder")
+    _count()
+    return out
+
+
+_SM_COUNT: dict[int, int] = {}
+
+
+def sm_count(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+def choose_nsplit(B: int, F: int, k: int, num_sms: int) -> int:
+    """Pick the F-split count that minimises (waves x tiles per split) for the persistent grid."""
+    m_blocks = (B + 127) // 128
+    n_tiles = (F + 255) // 256
+    best, best_cost = 1, None
+    for ns in range(1, n_tiles + 1):
+        tps = (n_tiles + ns - 1) // ns
+        ns_eff = (n_tiles + tps - 1) // tps
+        if ns_eff != ns:
+            continue
+        if ns > 1 and (ns * k + 31) // 32 > 64:
+            break
+        waves = (m_blocks * ns + num_sms - 1) // num_sms
+        cost = waves * tps + (0.15 * ns if ns > 1 else 0.0)  # small penalty for the merge pass
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = ns, cost
+    return best
+
+
+def encode_topk(a_packed: Tensor, w_packed: Tensor, B: int, F: int, d: int, terms: int, k: int,
+                nsplit: int | None = None) -> tuple[Tensor, Tensor]:
+    """K1. Returns (idx int32 [B,k], val float32 [B,k]) — signed pre-activations, unordered."""
+    _need_cuda(a_packed, w_packed)
+    if k > F:
+        raise RuntimeError(f"selected index k out of range (k={k} > hidden_dim={F})")
+    ps = packed_shape(d, terms)
+    Bp, Fp = a_packed.shape[0], w_packed.shape[0]
+    lib = _lib.load()
+    dev = a_packed.device
+    if nsplit is None:
+        nsplit = choose_nsplit(B, F, k, sm_count(dev))
+    nsplit = lib.wsae_encode_effective_splits(F, nsplit)
+    idx = torch.empty((B, k), dtype=torch.int32, device=dev)
+    val = torch.empty((B, k), dtype=torch.float32, device=dev)
+    pv = pi = None
+    if nsplit > 1:
+        pv = torch.empty((B, nsplit * k), dtype=torch.float32, device=dev)
+        pi = torch.empty((B, nsplit * k), dtype=torch.int32, device=dev)
+    _lib.check(
+        lib.wsae_encode_topk(_ptr(a_packed), _ptr(w_packed), B, Bp, F, Fp, ps.kp, ps.used_cols, k,
+                             nsplit, _ptr(pv), _ptr(pi), _ptr(val), _ptr(idx), _stream()),
+        "wsae_encode_topk",
+    )
+    _count(2 if nsplit > 1 else 1)
+    return idx, val
+
+
+def decode_mse(target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: Tensor | None, idx: Tensor,
+               val: Tensor, *, want_resid: bool = True, want_recon: bool = False,
+               stats: Tensor | None = None, last_activated: Tensor | None = None,
+               step_count: Tensor | None = None) -> tuple[Tensor | None, Tensor | None]:
+    """K2. ``stats`` is an int64[>=2] tensor: [0] holds a float64 SSE (bit pattern), [1] the L0 count."""
+    _need_cuda(target, w_decT, b_dec, b_pre, idx, val, stats, last_activated, step_count)
+    _f32c(target, "target")
+    _f32c(b_dec, "decoder.bias")
+    _f32c(b_pre, "b_pre")
+    F, d = w_decT.shape
+    B, k = idx.shape
+    if not w_decT.is_contiguous() or w_decT.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("w_decT must be contiguous [F, d] float32 or bfloat16")
+    resid = torch.empty_like(target) if want_resid else None
+    recon = torch.empty_like(target) if want_recon else None
+    lib = _lib.load()
+    _lib.check(
+        lib.wsae_decode_mse(_ptr(target), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16),
+                            _ptr(b_dec), _ptr(b_pre), _ptr(idx), _ptr(val), B, d, F, k,
+                            _ptr(resid), _ptr(recon), _ptr(stats), _ptr(last_activated),
+                            _ptr(step_count), _stream()),
+        "wsae_decode_mse",
+    )
+    _count()
+    return resid, recon
+
+
+def backward_sparse(resid: Tensor, x: Tensor | None, b_pre: Tensor | None, w_decT: Tensor,
+                    idx: Tensor, val: Tensor, grad_out: Tensor | None, coef: float, *,
+                    d_w_enc: Tensor | None, d_w_decT: Tensor | None, d_b_enc: Tensor | None,
+                    d_b_dec: Tensor | None, dpre_val: Tensor | None) -> None:
+    """K3 (scatter form). Accumulates into the provided (pre-zeroed) gradient buffers."""
+    _need_cuda(resid, x, w_decT, idx, val, grad_out)
+    F, d = w_decT.shape
+    B, k = idx.shape
+    if d % 4 != 0:
+        raise RuntimeError("input_dim must be a multiple of 4 for the sparse backward kernels")
+    lib = _lib.load()
+    _lib.check(
+        lib.wsae_backward_sparse(_ptr(resid), _ptr(x), _ptr(b_pre), _ptr(w_decT),
+                                 int(w_decT.dtype == torch.bfloat16), _ptr(idx), _ptr(val),
+                                 _ptr(grad_out), float(coef), B, d, F, k, _ptr(d_w_enc),
+                                 _ptr(d_w_decT), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val),
+                                 _stream()),
+        "wsae_backward_sparse",
+    )
+    _count()
+
+
+def bpre_grad(d_b_dec: Tensor, d_b_enc: Tensor, w_enc: Tensor) -> Tensor:
+    F, d = w_enc.shape
+    out = torch.empty(d, dtype=torch.float32, device=w_enc.device)
+    lib = _lib.load()
+    _lib.check(lib.wsae_bpre_grad(_ptr(d_b_dec), _ptr(d_b_enc), _ptr(w_enc), F, d, _ptr(out), _stream()),
+               "wsae_bpre_grad")
+    _count()
+    return out
+
+
+def input_grad(resid: Tensor, w_enc: Tensor, idx: Tensor, dpre_val: Tensor,
+               grad_out: Tensor | None, coef: float, subtract_g: bool) -> Tensor:
+    F, d = w_enc.shape
+    B, k = idx.shape
+    dx = torch.empty((B, d), dtype=torch.float32, device=resid.device)
+    lib = _lib.load()
+    _lib.check(
+        lib.wsae_input_grad(_ptr(resid), _ptr(w_enc), _ptr(idx), _ptr(dpre_val), _ptr(grad_out),
+                            float(coef), B, d, F, k, int(subtract_g), _ptr(dx), _stream()),
+        "wsae_input_grad",
+    )
+    _count()
+    return dx
+
+
+def renorm_decoder_(w_decT: Tensor, eps: float = 1e-12, shadow: Tensor | None = None) -> None:
+    _need_cuda(w_decT, shadow)
+    _f32c(w_decT, "w_decT")
+    F, d = w_decT.shape
+    lib = _lib.load()
+    _lib.check(lib.wsae_renorm_decoder(_ptr(w_decT), F, d, eps, _ptr(shadow), _stream()),
+               "wsae_renorm_decoder")
+    _count()
+
+
+def counters_update(last_activated: Tensor, step_count: Tensor, threshold: int, bump: bool,
+                    dead_count: Tensor | None) -> None:
+    _need_cuda(last_activated, step_count, dead_count)
+    if last_activated.dtype != torch.int64 or step_count.dtype != torch.int64:
+        raise RuntimeError("dead-feature counters must be int64")
+    lib = _lib.load()
+    _lib.check(
+        lib.wsae_counters_update(_ptr(last_activated), _ptr(step_count), last_activated.numel(),
+                                 int(threshold), int(bump), _ptr(dead_count), _stream()),
+        "wsae_counters_update",
+    )
+    _count()
+
+
+def densify_hidden(idx: Tensor, val: Tensor, F: int) -> Tensor:
+    _need_cuda(idx, val)
+    B, k = idx.shape
+    hidden = torch.empty((B, F), dtype=torch.float32, device=idx.device)
+    lib = _lib.load()
+    _lib.check(lib.wsae_densify_hidden(_ptr(idx), _ptr(val), B, F, k, _ptr(hidden), _stream()),
+               "wsae_densify_hidden")
+    _count()
+    return hidden
+
+
+def cast_bf16(src: Tensor, out: Tensor | None = None) -> Tensor:
+    _need_cuda(src)
+    _f32c(src, "src")
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    lib = _lib.load()
+    _lib.check(lib.wsae_cast_bf16(_ptr(src), _ptr(out), src.numel(), _stream()), "wsae_cast_bf16")
+    _count()
+    return out
+
+
+def sumsq_(g: Tensor, out: Tensor) -> None:
+    """out (float64[1]) += sum(g**2)."""
+    lib = _lib.load()
+    _lib.check(lib.wsae_sumsq(_ptr(g), g.numel(), _ptr(out), _stream()), "wsae_sumsq")
+    _count()
+
+
+def fused_adamw_(p: Tensor, grad: Tensor, m: Tensor, v: Tensor, hyper: Tensor,
+                 grad_sumsq: Tensor | None) -> None:
+    lib = _lib.load()
+    _lib.check(
+        lib.wsae_fused_adamw(_ptr(p), _ptr(grad), _ptr(m), _ptr(v), p.numel(), _ptr(hyper),
+                             _ptr(grad_sumsq), _stream()),
+        "wsae_fused_adamw",
+    )
+    _count()
