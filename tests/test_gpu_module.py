@@ -1,0 +1,268 @@
+"""Drop-in behaviour of TopKSAE / SAETrainer on the GPU: API conformance (mirrors the
+reference's tests/test_sae_model.py and tests/test_training.py) and numeric parity with the
+golden vectors produced by the live reference."""
+
+import pytest
+import torch
+
+from oracle import topk_sae_oracle as O
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from whisper_sae_b200.config import SAEConfig, TrainingConfig
+    from whisper_sae_b200.sae import SAEOutput, SAETrainer, TopKSAE, create_sae
+    return SAEConfig, TrainingConfig, SAEOutput, SAETrainer, TopKSAE, create_sae
+
+
+def test_forward_contract_and_sparsity():
+    _, _, SAEOutput, _, TopKSAE, _ = _mods()
+    sae = TopKSAE(384, 3072, k=32).cuda()
+    x = torch.randn(100, 384, device="cuda")
+    out = sae(x)
+    assert isinstance(out, SAEOutput)
+    assert out.reconstructed.shape == x.shape and out.hidden.shape == (100, 3072)
+    for t in (out.loss, out.reconstruction_loss, out.sparsity_loss, out.l0):
+        assert t.dim() == 0
+    assert out.loss is out.reconstruction_loss and out.sparsity_loss.item() == 0.0
+    nz = (out.hidden != 0).sum(-1)
+    assert (nz <= 32).all() and (out.hidden >= 0).all()
+    assert out.l0.item() == pytest.approx(nz.float().mean().item())
+    assert out.reconstruction_loss.item() == pytest.approx(
+        torch.nn.functional.mse_loss(out.reconstructed, x).item(), rel=1e-5)
+    recon, hidden, loss, *_ = out          # tuple protocol
+    assert recon.shape == x.shape and hidden.shape[1] == 3072 and loss.dim() == 0
+    # encode()/decode() agree with forward()
+    torch.testing.assert_close(sae.encode(x), out.hidden)
+    torch.testing.assert_close(sae.decode(out.hidden), out.reconstructed, rtol=1e-4, atol=1e-5)
+
+
+def test_topk_set_matches_torch_topk():
+    """tests/test_sae_model.py:110-130: selected index set == torch.topk set."""
+    _, _, _, _, TopKSAE, _ = _mods()
+    sae = TopKSAE(64, 256, k=8).cuda().eval()
+    x = torch.randn(10, 64, device="cuda")
+    hidden = sae.encode(x)
+    pre = torch.nn.functional.linear(x - sae.b_pre, sae.encoder.weight, sae.encoder.bias)
+    _, ref_idx = torch.topk(pre, 8, dim=-1)
+    for b in range(10):
+        got = set(hidden[b].nonzero().flatten().tolist())
+        want = {i for i in ref_idx[b].tolist() if pre[b, i] > 0}
+        assert got == want
+
+
+def test_dead_feature_tracking_exactly_k_alive():
+    """tests/test_sae_model.py:251-294 against the golden trace of the reference."""
+    fx = load_golden("dead_fixed_row")
+    r = fx["recipe"]
+    _, _, _, _, TopKSAE, _ = _mods()
+    torch.manual_seed(r["model_seed"])
+    sae = TopKSAE(r["d"], r["F"], k=r["k"], dead_feature_threshold=r["thr"]).cuda()
+    assert sae.feature_last_activated.dtype == torch.int64 and int(sae.step_count) == 0
+    x = torch.randn(1, r["d"], generator=torch.Generator().manual_seed(r["x_seed"])).cuda()
+    sae.eval()
+    sae(x)
+    assert int(sae.step_count) == 0                       # eval leaves the counters alone
+    sae.train()
+    with torch.no_grad():
+        for _ in range(r["steps"]):
+            sae(x)
+    assert int(sae.step_count) == fx["step_count"]
+    assert torch.equal(sae.feature_last_activated.cpu(), fx["feature_last_activated"])   # bit-exact
+    assert torch.equal(sae.get_dead_features().cpu(), fx["dead_mask"])
+    assert int((~sae.get_dead_features()).sum()) == 4
+    assert sae.get_dead_feature_ratio() == pytest.approx(124 / 128)
+
+
+def test_gradients_flow_and_match_oracle():
+    _, _, _, _, TopKSAE, _ = _mods()
+    torch.manual_seed(11)
+    sae = TopKSAE(64, 256, k=8).cuda()
+    with torch.no_grad():
+        sae.b_pre.normal_(0, 0.05)
+    x = O.synthetic_activations(48, 64, seed=3)
+    xg = x.cuda().requires_grad_(True)
+    out = sae(xg)
+    (out.loss * 4.0).backward()                           # arbitrary upstream scale (GradScaler-like)
+    state = {n: v.detach().cpu().contiguous() for n, v in sae.state_dict().items()}
+    state["step_count"] = state["step_count"] - 1
+    fwd = O.forward(state, x, 8, training=False)
+    ref = O.backward(state, x, fwd, grad_out=4.0)
+    assert out.loss.item() == pytest.approx(fwd.loss.item(), rel=1e-5)
+    named = dict(sae.named_parameters())
+    for n in O.PARAM_ORDER:
+        g = named[n].grad
+        assert g is not None and g.abs().sum() > 0
+        scale = ref[n].abs().max().item()
+        torch.testing.assert_close(g.cpu(), ref[n], rtol=2e-5, atol=2e-6 * scale)
+    torch.testing.assert_close(xg.grad.cpu(), ref["dx"], rtol=2e-5, atol=2e-6 * ref["dx"].abs().max().item())
+
+
+def test_state_dict_layout_roundtrip(tmp_path):
+    _, _, _, _, TopKSAE, _ = _mods()
+    sae = TopKSAE(64, 128, k=8).cuda()
+    keys = list(sae.state_dict().keys())
+    assert keys == ["b_pre", "feature_last_activated", "step_count", "encoder.weight", "encoder.bias",
+                    "decoder.weight", "decoder.bias"]
+    assert sae.decoder.weight.shape == (64, 128) and sae.encoder.weight.shape == (128, 64)
+    torch.save(sae.state_dict(), tmp_path / "sae_final.pt")
+    other = TopKSAE(64, 128, k=8).cuda()
+    other.load_state_dict(torch.load(tmp_path / "sae_final.pt"))
+    x = torch.randn(16, 64, device="cuda")
+    sae.eval(), other.eval()
+    assert sae(x).loss.item() == other(x).loss.item()
+    # callers may replace .data with a plain contiguous [d, F] tensor (tests/test_sae_model.py:525-530)
+    with torch.no_grad():
+        other.decoder.weight.data = sae.decoder.weight.data.contiguous()
+    assert other(x).loss.item() == sae(x).loss.item()
+
+
+def test_identity_weights_reconstruct():
+    _, _, _, _, TopKSAE, _ = _mods()
+    sae = TopKSAE(32, 32, k=32).cuda()
+    with torch.no_grad():
+        sae.encoder.weight.data = torch.eye(32, device="cuda")
+        sae.encoder.bias.data.zero_()
+        sae.decoder.weight.data = torch.eye(32, device="cuda")
+        sae.decoder.bias.data.zero_()
+        sae.b_pre.data.zero_()
+    out = sae(torch.rand(10, 32, device="cuda"))
+    assert out.reconstruction_loss.item() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["small_64x256", "tiny_test_384x3072", "mid_128x1024_k32"])
+@pytest.mark.parametrize("fused_opt", [True, False])
+def test_trainer_fp32_matches_reference_golden(name, fused_opt, tmp_path):
+    """fp32-grade mode: losses / weights within 1e-5 relative of the reference trace, TopK sets
+    identical (no near-ties occur in these traces at tau = 1e-5 * max|pre|), counters bit-exact."""
+    _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
+    fx = load_golden(name)
+    r = fx["recipe"]
+    torch.manual_seed(r["model_seed"])
+    sae = TopKSAE(r["d"], r["F"], k=r["k"], dead_feature_threshold=r["dead_threshold"])
+    cfg = TrainingConfig(batch_size=r["B"], learning_rate=r["lr"], warmup_steps=r["warmup"], epochs=1,
+                         use_amp=False, num_workers=0)
+    tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path, fused_optimizer=fused_opt)
+    tr.setup_scheduler(r["total_steps"])
+    x_all = O.synthetic_activations(r["B"] * r["steps"], r["d"], r["data_seed"])
+    for s in range(r["steps"]):
+        xb = x_all[s * r["B"]:(s + 1) * r["B"]]
+        if s == 0:
+            idx, _ = sae._sparse_encode(xb.cuda())
+            got = torch.sort(idx.cpu(), -1).values
+            want = fx["first_step"]["topk_idx_sorted"]
+            bad = (got != want).any(-1)
+            ties = fx["first_step"]["kth_gap"].abs() <= 1e-5 * fx["first_step"]["pre_absmax"]
+            assert not (bad & ~ties).any()
+        m = tr.train_step(xb)
+        ref = fx["per_step"][s]
+        assert m.loss == pytest.approx(ref["loss"], rel=1e-5), f"step {s}"
+        assert m.l0 == pytest.approx(ref["l0"], rel=1e-6)
+        assert m.dead_feature_ratio == pytest.approx(ref["dead_feature_ratio"], abs=1e-7)
+        assert m.learning_rate == pytest.approx(ref["lr_reported"], rel=1e-9)
+        assert m.step == ref["step"]
+    assert torch.equal(sae.feature_last_activated.cpu(), fx["final_counters"]["feature_last_activated"])
+    assert int(sae.step_count) == int(fx["final_counters"]["step_count"])
+    sd = sae.state_dict()
+    for n in O.PARAM_ORDER:
+        ref = fx["final_params"][n]
+        t = sd[n].cpu()
+        if isinstance(ref, dict):
+            sample = t.contiguous().reshape(-1)[:: ref["sample_stride"]]
+            torch.testing.assert_close(sample, ref["sample"], rtol=1e-5, atol=1e-5 * ref["abs_sum"] / t.numel())
+            assert t.double().abs().sum().item() == pytest.approx(ref["abs_sum"], rel=1e-5)
+        else:
+            torch.testing.assert_close(t, ref, rtol=1e-5, atol=1e-5 * ref.abs().mean().item())
+    # decoder columns are unit norm after a step (tests/test_training.py:314-326)
+    torch.testing.assert_close(sae.decoder.weight.norm(dim=0).cpu(), torch.ones(r["F"]), atol=1e-5, rtol=0)
+
+
+def test_trainer_bf16_within_tolerance(tmp_path):
+    """bf16 (use_amp) mode vs the fp32 reference trace: 2e-2 relative on losses (north_star)."""
+    _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
+    fx = load_golden("tiny_test_384x3072")
+    r = fx["recipe"]
+    torch.manual_seed(r["model_seed"])
+    sae = TopKSAE(r["d"], r["F"], k=r["k"], dead_feature_threshold=r["dead_threshold"])
+    cfg = TrainingConfig(batch_size=r["B"], learning_rate=r["lr"], warmup_steps=r["warmup"], epochs=1,
+                         use_amp=True, num_workers=0)
+    tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path)
+    assert tr.use_amp
+    tr.setup_scheduler(r["total_steps"])
+    x_all = O.synthetic_activations(r["B"] * r["steps"], r["d"], r["data_seed"])
+    for s in range(r["steps"]):
+        m = tr.train_step([x_all[s * r["B"]:(s + 1) * r["B"]]])   # list batch, as a DataLoader yields
+        assert m.loss == pytest.approx(fx["per_step"][s]["loss"], rel=2e-2)
+        assert m.l0 == pytest.approx(fx["per_step"][s]["l0"], rel=2e-2)
+    for n in O.PARAM_ORDER:
+        ref = fx["final_params"][n]
+        t = sae.state_dict()[n].cpu()
+        assert t.double().abs().sum().item() == pytest.approx(ref["abs_sum"], rel=2e-2)
+
+
+def test_trainer_bookkeeping_and_checkpoint(tmp_path):
+    _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
+    cfg = TrainingConfig(batch_size=16, epochs=2, use_amp=False, num_workers=0, checkpoint_every=1)
+    sae = TopKSAE(64, 128, k=8)
+    tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path / "run")
+    data = torch.randn(64, 64)
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(data), batch_size=16)
+    tr.train(loader, epochs=2)
+    assert tr.global_step == 8 and tr.epoch == 2 and len(tr.metrics_history) == 8
+    assert tr.metrics_history[0].l0 == 8.0 and tr.metrics_history[0].step == 1
+    for f in ("checkpoint_epoch1.pt", "checkpoint_epoch2.pt", "final.pt"):
+        assert (tmp_path / "run" / f).exists()
+    ck = torch.load(tmp_path / "run" / "final.pt", weights_only=False)
+    assert set(ck) == {"model_state_dict", "optimizer_state_dict", "scheduler_state_dict",
+                       "global_step", "epoch", "config"}
+    tr2 = SAETrainer(TopKSAE(64, 128, k=8), cfg, device="cuda", run_dir=tmp_path / "run2")
+    tr2.load_checkpoint(tmp_path / "run" / "final.pt")
+    assert tr2.global_step == 8 and tr2.epoch == 2
+    p = tr.save_metrics()
+    import json
+    rows = json.loads(p.read_text())
+    assert len(rows) == 8 and set(rows[0]) == {"step", "loss", "reconstruction_loss", "sparsity_loss",
+                                                "l0", "dead_feature_ratio", "learning_rate"}
+    # loss decreases over a few epochs (tests/test_training.py:214-240)
+    first = sum(m.loss for m in tr.metrics_history[:4]) / 4
+    tr.train(loader, epochs=5)
+    last = sum(m.loss for m in tr.metrics_history[-4:]) / 4
+    assert last < first
+
+
+def test_resample_dead_features_on_device():
+    _, _, _, _, TopKSAE, _ = _mods()
+    torch.manual_seed(0)
+    sae = TopKSAE(64, 128, k=8, dead_feature_threshold=5).cuda().train()
+    x = torch.randn(1, 64, device="cuda")
+    with torch.no_grad():
+        for _ in range(10):
+            sae(x)
+    dead_before = sae.get_dead_features()
+    n_dead = int(dead_before.sum())
+    assert n_dead == 120
+    inputs = torch.randn(256, 64, device="cuda")
+    n = sae.resample_dead_features(inputs, num_resample=10)
+    assert n == 10
+    idx = torch.where(dead_before)[0][:10]
+    torch.testing.assert_close(sae.encoder.weight[idx].norm(dim=1), torch.ones(10, device="cuda"))
+    torch.testing.assert_close(sae.decoder.weight[:, idx].t(), sae.encoder.weight[idx])
+    assert (sae.encoder.bias[idx] == 0).all()
+    assert (sae.feature_last_activated[idx] == sae.step_count).all()
+
+
+def test_enabled_grad_scaler_path(tmp_path):
+    """An enabled GradScaler (the reference's CUDA default) still trains: scaled grad_output is honoured."""
+    _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
+    cfg = TrainingConfig(batch_size=32, use_amp=True, num_workers=0)
+    torch.manual_seed(1)
+    a = SAETrainer(TopKSAE(64, 256, k=8), cfg, device="cuda", run_dir=tmp_path, grad_scaler=True)
+    torch.manual_seed(1)
+    b = SAETrainer(TopKSAE(64, 256, k=8), cfg, device="cuda", run_dir=tmp_path, grad_scaler=False)
+    assert a.scaler.is_enabled() and not b.scaler.is_enabled()
+    x = torch.randn(32, 64)
+    for _ in range(3):
+        ma, mb = a.train_step(x), b.train_step(x)
+        assert ma.loss == pytest.approx(mb.loss, rel=1e-4)

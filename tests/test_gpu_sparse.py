@@ -1,0 +1,181 @@
+"""K2 / K3 / K5 parity through the C ABI against the CPU oracle."""
+
+import math
+
+import pytest
+import torch
+
+from oracle import topk_sae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from whisper_sae_b200 import ops
+    return ops
+
+
+def _case(B, d, F, k, seed=0, b_pre_scale=0.05):
+    torch.manual_seed(seed)
+    state = O.init_state(d, F)
+    state["b_pre"] = torch.randn(d) * b_pre_scale
+    state["decoder.bias"] = torch.randn(d) * 0.02
+    x = O.synthetic_activations(B, d, seed=seed + 100)
+    fwd = O.forward(state, x, k, training=False)
+    return state, x, fwd
+
+
+def _dev(t):
+    return t.cuda().contiguous()
+
+
+SHAPES = [(1, 32, 128, 4), (33, 64, 256, 8), (64, 384, 3072, 32), (257, 768, 1024, 32),
+          (40, 1280, 2048, 32), (16, 64, 128, 64)]
+
+
+@pytest.mark.parametrize("B,d,F,k", SHAPES)
+@pytest.mark.parametrize("wdtype", ["fp32", "bf16"])
+def test_decode_mse(B, d, F, k, wdtype):
+    ops = _ops()
+    state, x, fwd = _case(B, d, F, k, seed=B + d)
+    quant = "bf16" if wdtype == "bf16" else None
+    # oracle decode with the same decoder precision (encoder side identical: same idx/val fed in)
+    state_q = dict(state)
+    ref = O.forward(state_q, x, k, training=False)
+    w_decT = state["decoder.weight"].t().contiguous()
+    if quant:
+        w_used = w_decT.to(torch.bfloat16)
+        rows = w_used.float()[ref.idx]
+    else:
+        w_used = w_decT
+        rows = w_decT[ref.idx]
+    recon = (torch.relu(ref.val).unsqueeze(-1) * rows).sum(1) + state["decoder.bias"] + state["b_pre"]
+    resid_ref = recon - x
+    stats = torch.zeros(3, dtype=torch.int64, device="cuda")
+    last = torch.zeros(F, dtype=torch.int64, device="cuda")
+    step = torch.tensor(6, dtype=torch.int64, device="cuda")
+    resid, rec = ops.decode_mse(_dev(x), _dev(w_used), _dev(state["decoder.bias"]), _dev(state["b_pre"]),
+                                _dev(ref.idx.to(torch.int32)), _dev(ref.val), want_resid=True,
+                                want_recon=True, stats=stats, last_activated=last, step_count=step)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(resid.cpu(), resid_ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rec.cpu(), recon, rtol=1e-5, atol=1e-6)
+    raw = stats.cpu()
+    sse = raw[:1].view(torch.float64).item()
+    assert sse == pytest.approx((resid_ref.double() ** 2).sum().item(), rel=1e-6)
+    assert raw[1].item() == int((ref.val > 0).sum())            # L0 numerator: exact integer
+    want_last = torch.zeros(F, dtype=torch.int64)
+    want_last[ref.idx[ref.val > 0]] = 7                          # stamp = step_count + 1
+    assert torch.equal(last.cpu(), want_last)                    # bit-exact
+    assert step.item() == 6                                      # K2 itself does not bump
+
+
+@pytest.mark.parametrize("B,d,F,k", SHAPES)
+def test_backward_sparse_fp32(B, d, F, k):
+    ops = _ops()
+    state, x, fwd = _case(B, d, F, k, seed=2 * B + d)
+    grad_out = 3.0
+    ref = O.backward(state, x, fwd, grad_out=grad_out)
+    dev = "cuda"
+    w_decT = _dev(state["decoder.weight"].t())
+    dWe = torch.zeros(F, d, device=dev)
+    dWd = torch.zeros(F, d, device=dev)
+    dbe = torch.zeros(F, device=dev)
+    dbd = torch.zeros(d, device=dev)
+    dpre = torch.empty(B, k, device=dev)
+    go = torch.tensor(grad_out, device=dev)
+    coef = 2.0 / (B * d)
+    idx = _dev(fwd.idx.to(torch.int32))
+    ops.backward_sparse(_dev(fwd.resid), _dev(x), _dev(state["b_pre"]), w_decT, idx, _dev(fwd.val), go,
+                        coef, d_w_enc=dWe, d_w_decT=dWd, d_b_enc=dbe, d_b_dec=dbd, dpre_val=dpre)
+    dbp = ops.bpre_grad(dbd, dbe, _dev(state["encoder.weight"]))
+    dx = ops.input_grad(_dev(fwd.resid), _dev(state["encoder.weight"]), idx, dpre, go, coef, True)
+    torch.cuda.synchronize()
+
+    def close(a, b, name):
+        scale = b.abs().max().item() + 1e-30
+        torch.testing.assert_close(a.cpu(), b, rtol=2e-5, atol=2e-6 * scale, msg=lambda m: f"{name}: {m}")
+
+    close(dpre, ref["dpre_val"], "dpre")
+    close(dWe, ref["encoder.weight"], "dW_enc")
+    close(dWd.t(), ref["decoder.weight"], "dW_dec")
+    close(dbe, ref["encoder.bias"], "db_enc")
+    close(dbd, ref["decoder.bias"], "db_dec")
+    close(dbp, ref["b_pre"], "db_pre")
+    close(dx, ref["dx"], "dx")
+
+
+def test_renorm_and_shadow():
+    ops = _ops()
+    torch.manual_seed(0)
+    F, d = 1000, 384
+    w = torch.randn(F, d) * torch.rand(F, 1) * 3
+    w[5] = 0.0                      # zero row hits the 1e-12 clamp (SkipTranscoder case, §8 a15)
+    ref = torch.nn.functional.normalize(w.t(), dim=0).t()
+    wg = w.cuda()
+    shadow = torch.empty(F, d, dtype=torch.bfloat16, device="cuda")
+    ops.renorm_decoder_(wg, 1e-12, shadow)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(wg.cpu(), ref, rtol=1e-6, atol=1e-7)
+    assert (wg[5] == 0).all()
+    assert torch.equal(shadow.cpu(), wg.cpu().to(torch.bfloat16))
+    torch.testing.assert_close(wg.norm(dim=1).cpu()[torch.arange(F) != 5], torch.ones(F - 1), atol=1e-5, rtol=0)
+
+
+def test_counters_bit_exact():
+    ops = _ops()
+    F = 40960
+    g = torch.Generator().manual_seed(1)
+    last = torch.randint(0, 5000, (F,), generator=g, dtype=torch.int64)
+    step = torch.tensor(5200, dtype=torch.int64)
+    for thr in (0, 1000, 10_000):
+        lg, sg = last.cuda(), step.clone().cuda()
+        dead = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ops.counters_update(lg, sg, thr, True, dead)
+        torch.cuda.synchronize()
+        assert sg.item() == 5201
+        assert dead.item() == int(((5201 - last) > thr).sum())
+        ops.counters_update(lg, sg, thr, False, dead)
+        assert sg.item() == 5201 and dead.item() == int(((5201 - last) > thr).sum())
+
+
+def test_densify_cast_sumsq():
+    ops = _ops()
+    state, x, fwd = _case(50, 64, 256, 8, seed=4)
+    h = ops.densify_hidden(fwd.idx.to(torch.int32).cuda(), fwd.val.cuda(), 256)
+    assert torch.equal(h.cpu(), O.dense_hidden(fwd, 256))
+    t = torch.randn(1001, 37).cuda()
+    assert torch.equal(ops.cast_bf16(t).cpu(), t.cpu().to(torch.bfloat16))
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ops.sumsq_(t, acc)
+    assert acc.item() == pytest.approx((t.double() ** 2).sum().item(), rel=1e-6)
+
+
+def test_fused_adamw_matches_torch():
+    ops = _ops()
+    torch.manual_seed(0)
+    shapes = [(384,), (3072, 384), (3072,), (3072, 384), (384,)]
+    ps = [torch.randn(s) for s in shapes]
+    ref_p = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.AdamW(ref_p, lr=1e-3, weight_decay=0.01)
+    gp = [p.clone().cuda() for p in ps]
+    m = [torch.zeros_like(p) for p in gp]
+    v = [torch.zeros_like(p) for p in gp]
+    hyper = torch.empty(8, device="cuda")
+    for step in range(1, 4):
+        grads = [torch.randn(s) * (10.0 if step == 2 else 0.01) for s in shapes]
+        for p, g in zip(ref_p, grads):
+            p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(ref_p, 1.0)
+        opt.step()
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        gg = [g.cuda() for g in grads]
+        for g in gg:
+            ops.sumsq_(g, ss)
+        hyper.copy_(torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.01, 1 - 0.9 ** step,
+                                  math.sqrt(1 - 0.999 ** step), 1.0]))
+        for p, g, mm, vv in zip(gp, gg, m, v):
+            ops.fused_adamw_(p, g, mm, vv, hyper, ss)
+        torch.cuda.synchronize()
+        for p, r in zip(gp, ref_p):
+            torch.testing.assert_close(p.cpu(), r.detach(), rtol=2e-6, atol=1e-7)

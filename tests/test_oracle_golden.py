@@ -111,3 +111,26 @@ def test_dense_hidden_has_exactly_k_nonzeros():
     assert ((hidden != 0).sum(-1) <= 8).all()
     assert (hidden >= 0).all()
     assert int(state["step_count"]) == 0  # eval mode leaves counters alone (model.py:174)
+
+
+def test_backward_matches_reference_autograd_formula():
+    """Oracle backward itself vs torch autograd on the reference's forward graph (sanity of the
+    hand-derived gradient)."""
+    torch.manual_seed(3)
+    state = O.init_state(32, 64)
+    state['b_pre'] = torch.randn(32) * 0.05
+    x = O.synthetic_activations(20, 32, seed=103)
+    fwd = O.forward(state, x, 4, training=False)
+    p = {n: state[n].clone().requires_grad_(True) for n in O.PARAM_ORDER}
+    xr = x.clone().requires_grad_(True)
+    pre = (xr - p["b_pre"]) @ p["encoder.weight"].t() + p["encoder.bias"]
+    v, i = torch.topk(pre, 4, dim=-1)
+    hidden = torch.zeros_like(pre).scatter(-1, i, torch.relu(v))
+    recon = hidden @ p["decoder.weight"].t() + p["decoder.bias"] + p["b_pre"]
+    torch.nn.functional.mse_loss(recon, xr).backward()
+    g = O.backward(state, x, fwd)
+    for n in O.PARAM_ORDER:
+        torch.testing.assert_close(g[n], p[n].grad, rtol=1e-4, atol=1e-8)
+    torch.testing.assert_close(g["dx"], xr.grad, rtol=1e-4, atol=1e-8)
+
+
