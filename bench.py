@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — activation rows/s of the TopK-SAE train step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 50 --warmup 10
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # CPU arm: the oracle port on the host cores
+
+Workload (BASELINE.json configs[1]): whisper-tiny TopKSAE 384 -> 3072, k = 32, hyper-parameters of
+configs/tiny_default.yaml (lr 1e-4, warm-up 1000, clip 1.0, AMP on => bf16 path), synthetic
+row-standardised Gaussian activations.  One "step" = one `SAETrainer.train_step`
+(pack, tcgen05 GEMM + fused TopK, sparse decode + MSE, sparse backward, clip + AdamW, decoder
+renorm, counters, stats readback).  The YAML batch (128) is launch-latency bound by construction,
+so the headline batch is `--batch` (default 16384, config-legal: TrainingConfig.batch_size >= 1);
+the YAML-batch number is reported next to it as `yaml_batch`.
+
+N > 1: one process per GPU, each training an independent layer's SAE (4 encoder + 4 decoder
+layers of whisper-tiny; no data-path collective), value = sum of rows/s, weak scaling.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+D_MODEL, EXPANSION, TOPK = 384, 8, 32
+HIDDEN = D_MODEL * EXPANSION
+METRIC = "sae_train_step_activation_rows_per_sec"
+UNIT = "rows/s"
+
+
+def load_peaks() -> tuple[dict, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._pump, daemon=True)
+            self._t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_trainer(batch: int, device: str, layer_seed: int, use_amp: bool = True):
+    from whisper_sae_b200.config import ExperimentConfig
+    from whisper_sae_b200.sae import SAETrainer, create_sae
+
+    cfg = ExperimentConfig.from_yaml(ROOT / "configs" / "tiny_default.yaml")
+    cfg.training.batch_size = batch
+    cfg.training.use_amp = use_amp
+    torch.manual_seed(cfg.training.seed + layer_seed)
+    sae = create_sae(cfg.sae, cfg.whisper.hidden_dim)
+    run_dir = Path(tempfile.mkdtemp(prefix="wsae_bench_"))
+    tr = SAETrainer(sae, cfg.training, device=device, run_dir=run_dir)
+    tr.setup_scheduler(100_000)
+    return tr, cfg
+
+
+def synth(n_rows: int, d: int, seed: int, device=None, pin: bool = False) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n_rows, d, generator=g)
+    x = (x - x.mean(1, keepdim=True)) / x.std(1, unbiased=False, keepdim=True)
+    if device is not None:
+        return x.to(device)
+    return x.pin_memory() if pin else x
+
+
+def time_steps(tr, batches, steps: int, warmup: int, dist_on: bool) -> tuple[float, int]:
+    """(seconds, own kernel launches) for exactly `steps` train steps: CUDA events on the launching
+    stream, barrier + synchronize on both sides, max over ranks."""
+    from whisper_sae_b200 import ops
+
+    n = len(batches)
+    for i in range(warmup):
+        tr.train_step(batches[i % n])
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ops.GPU_LAUNCHES
+    start.record()
+    for i in range(steps):
+        tr.train_step(batches[(warmup + i) % n])
+    end.record()
+    torch.cuda.synchronize()
+    launches = ops.GPU_LAUNCHES - launches0
+    if dist_on:
+        torch.distributed.barrier()
+    sec = start.elapsed_time(end) / 1e3
+    if dist_on:
+        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        sec = t.item()
+    return sec, launches
+
+
+def kernel_profile(tr, batches, steps: int) -> dict:
+    from whisper_sae_b200 import ops
+
+    ops.PROFILE = ops.KernelProfile()
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        tr.train_step(batches[i % len(batches)])
+    t1.record()
+    summ = ops.PROFILE.summary()
+    ops.PROFILE = None
+    total_ms = t0.elapsed_time(t1)
+    for v in summ.values():
+        v["share_of_step"] = v["total_ms"] / total_ms
+        v["per_step"] = v["launches"] / steps
+    summ["_step_ms"] = total_ms / steps
+    return summ
+
+
+def roofline(prof: dict, batch: int, d: int, F: int, k: int, peaks: dict, bf16_dec: bool) -> dict:
+    """Roofline of the dominant kernel (largest share of the step), DESIGN.md §kernels:
+    encode_topk: tensor bound, 2*B*d*F algorithmic FLOPs per launch;
+    decode: HBM bound, B*(k*d*w + 2*d*4 + k*8) bytes; backward: B*(k*d*w + 2*2*k*d*4 + d*4 + k*12)."""
+    kern = {n: v for n, v in prof.items() if not n.startswith("_")}
+    top = max(kern, key=lambda n: kern[n]["total_ms"])
+    per_launch_s = kern[top]["avg_ms"] / 1e3
+    w = 2 if bf16_dec else 4
+    if top == "wsae_encode_topk":
+        work = 2.0 * batch * d * F
+        peak = peaks["bf16_tflops_sustained"]
+        return {"kernel": top, "bound": "tensor", "achieved": work / per_launch_s / 1e12, "peak": peak,
+                "unit": "TFLOP/s", "frac": work / per_launch_s / 1e12 / peak, "traffic": None}
+    if top == "wsae_decode_mse":
+        nbytes = batch * (k * d * w + 2 * d * 4 + k * 8)
+    elif top == "wsae_backward_sparse":
+        nbytes = batch * (k * d * w + 2 * 2 * k * d * 4 + 2 * d * 4 + k * 12)
+    elif top == "wsae_fused_adamw":
+        nbytes = 28 * (kern[top]["launches"] and (2 * d * F + F + 2 * d)) / 5  # avg per launch (5 tensors)
+    else:
+        nbytes = 0
+    peak = peaks["hbm_gbs"]
+    ach = nbytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    return {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None}
+
+
+def cpu_oracle_rate(batch: int, seconds_budget: float, threads: int) -> dict:
+    """rows/s of the CPU oracle port (reference algorithm, torch CPU fp32, all host threads)."""
+    from oracle import topk_sae_oracle as O
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    state = O.init_state(D_MODEL, HIDDEN)
+    opt = O.AdamWState()
+    lrs = O.lr_sequence(1e-4, 100_000, 1000)
+    x = O.synthetic_activations(batch * 2, D_MODEL, seed=1234)
+    O.train_step(state, opt, x[:batch], TOPK, lrs[0])          # warm-up (thread pools, page faults)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        O.train_step(state, opt, x[(n % 2) * batch:(n % 2 + 1) * batch], TOPK, lrs[n + 1])
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds_budget or n >= 200:
+            break
+    return {"value": batch * n / el, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} train steps of B={batch} rows ({el:.1f} s), oracle/topk_sae_oracle.py, "
+                      f"torch {torch.__version__} CPU fp32"}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    from oracle import topk_sae_oracle as O
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    state = O.init_state(D_MODEL, HIDDEN)
+    opt = O.AdamWState()
+    lrs = O.lr_sequence(1e-4, 100_000, 1000)
+    batch = args.batch
+    x = O.synthetic_activations(batch * 2, D_MODEL, seed=1234)
+    # bounded: at most ~120 s of CPU work in total
+    probe0 = time.perf_counter()
+    O.train_step(state, opt, x[:batch], TOPK, lrs[0])
+    per = time.perf_counter() - probe0
+    max_steps = max(1, int(120.0 / max(per, 1e-3)))
+    warm = min(warm, max(0, max_steps // 4))
+    steps = min(steps, max(1, max_steps - warm))
+    for i in range(warm):
+        O.train_step(state, opt, x[(i % 2) * batch:(i % 2 + 1) * batch], TOPK, lrs[i + 1])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        O.train_step(state, opt, x[(i % 2) * batch:(i % 2 + 1) * batch], TOPK, lrs[warm + i + 1])
+    el = time.perf_counter() - t0
+    value = batch * steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{steps} timed train steps of B={batch} rows on the host CPU "
+                                   f"(oracle port of sae/model.py + sae/training.py, torch CPU fp32)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus: int) -> dict:
+    return {
+        "workload": f"whisper-tiny TopKSAE {D_MODEL}->{HIDDEN} k={TOPK} train step "
+                    f"(configs/tiny_default.yaml hyper-parameters; BASELINE.json configs[1])",
+        "batch_rows_per_gpu": args.batch,
+        "global_batch_rows": args.batch * n_gpus,
+        "parallelism": "1 SAE (layer) per GPU, no data-path collective" if n_gpus > 1 else "single GPU",
+        "precision_mode": args.precision,
+        "l2_policy": f"{args.resident_batches} distinct resident batches cycled "
+                     f"({args.resident_batches * args.batch * D_MODEL * 4 / 2**20:.0f} MiB > 126 MiB L2)",
+    }
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--resident-batches", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-only", action="store_true",
+                    help="only the HBM-resident timed leg (used under ncu; prints a reduced line)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = f"cuda:{local_rank}"
+
+    from whisper_sae_b200 import ops
+
+    peaks, peak_src = load_peaks()
+    tr, cfg = make_trainer(args.batch, dev, layer_seed=rank, use_amp=(args.precision == "bf16"))
+    nb = max(2, args.resident_batches)
+    rows = synth(nb * args.batch, D_MODEL, seed=1234 + rank)
+    dev_batches = [rows[i * args.batch:(i + 1) * args.batch].to(dev) for i in range(nb)]
+    host_batches = [rows[i * args.batch:(i + 1) * args.batch].pin_memory() for i in range(nb)]
+
+    # ---- value: inputs resident in HBM ----
+    with ClockSampler(local_rank) as clocks:
+        sec, launches = time_steps(tr, dev_batches, args.steps, args.warmup, dist_on)
+    value = args.batch * args.steps * world / sec
+
+    if args.value_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                              "steps": args.steps, "warmup": args.warmup,
+                              "ms_per_step": 1e3 * sec / args.steps, "gpu_launches": launches,
+                              "note": "value-only leg (not a bench line)"}))
+        if dist_on:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- e2e: pinned host batches through SAETrainer.train_step (H2D + stats D2H inside) ----
+    sec_e2e, _ = time_steps(tr, host_batches, args.steps, args.warmup, dist_on)
+    e2e = args.batch * args.steps * world / sec_e2e
+
+    line = None
+    if rank == 0:
+        prof = kernel_profile(tr, dev_batches, min(args.steps, 20))
+        roof = roofline(prof, args.batch, D_MODEL, HIDDEN, TOPK, peaks, args.precision == "bf16")
+        roof["peak_source"] = f"{peak_src} (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"
+        shares = {n: round(v["share_of_step"], 4) for n, v in prof.items() if not n.startswith("_")}
+        # the launch-bound YAML batch, for the record
+        cfg_batch = 128
+        tr_small, _ = make_trainer(cfg_batch, dev, layer_seed=rank, use_amp=(args.precision == "bf16"))
+        small = [dev_batches[0][i * cfg_batch:(i + 1) * cfg_batch].contiguous() for i in range(16)]
+        sec_small, _ = time_steps(tr_small, small, 100, 10, False)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": args.batch * D_MODEL * 4,
+                    "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * sec_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": roof,
+            "kernel_shares": shares,
+            "kernel_avg_ms": {n: round(v["avg_ms"], 4) for n, v in prof.items() if not n.startswith("_")},
+            "yaml_batch": {"batch_rows": cfg_batch, "value": cfg_batch * 100 / sec_small, "unit": UNIT,
+                           "ms_per_step": 1e3 * sec_small / 100},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_oracle_rate(args.batch, args.cpu_seconds, os.cpu_count() or 1)
+    if dist_on:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -82,9 +82,14 @@ def run_case(name: str, d: int, F: int, k: int, B: int, steps: int, total_steps:
                                   else digest(dict(probe.named_parameters())[n].grad))
                               for n in PARAM_ORDER},
                 }
+            with torch.no_grad():   # k-th / (k+1)-th gap of this step's pre-activations (near-tie rule)
+                pre_s = model.encoder(xb - model.b_pre)
+                top = torch.topk(pre_s, min(k + 1, F), dim=-1).values
+                min_gap_rel = ((top[:, k - 1] - top[:, -1]).min() / pre_s.abs().max()).item()
             m = trainer.train_step(xb)
             per_step.append({"loss": m.loss, "l0": m.l0, "dead_feature_ratio": m.dead_feature_ratio,
-                             "lr_used": lr_used, "lr_reported": m.learning_rate, "step": m.step})
+                             "lr_used": lr_used, "lr_reported": m.learning_rate, "step": m.step,
+                             "min_gap_rel": min_gap_rel})
         final = model.state_dict()
         fixture = {
             "recipe": dict(name=name, d=d, F=F, k=k, B=B, steps=steps, total_steps=total_steps, lr=lr,

@@ -10,7 +10,7 @@
 
 #ifndef WSAE_SPIN_LIMIT
 // Bounded spin on mbarrier waits: a broken pipeline traps (CUDA error) instead of hanging the GPU.
-#define WSAE_SPIN_LIMIT (1u << 28)
+#define WSAE_SPIN_LIMIT (1u << 22)
 #endif
 
 namespace wsae {

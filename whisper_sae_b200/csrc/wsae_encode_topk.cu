@@ -71,7 +71,9 @@ __device__ __forceinline__ void topk_compact(float* cv, uint32_t* ci, int& cnt, 
     key[s] = (s < cnt) ? f2key(cv[s * kBM]) : 0u;
     hi = max(hi, key[s]);
   }
-  uint32_t lo = f2key(tau);  // invariant: count(key > lo) >= min(cnt, k); count(key > hi) < k
+  // Stored keys are > key(tau), or == key(tau) when tau came from a tie break (then exactly k are
+  // stored).  Starting one below key(tau) covers both: count(key > lo) == cnt.
+  uint32_t lo = f2key(tau) - 1u;  // invariant: count(key > lo) >= min(cnt, k); count(key > hi) < k
   int c_lo = cnt;
   bool done = (c_lo <= k + slack);
   while (true) {

@@ -47,6 +47,38 @@ def _count(n: int = 1) -> None:
     GPU_LAUNCHES += n
 
 
+class KernelProfile:
+    """Per-kernel CUDA-event timing on the launching stream (enabled by bench.py for one pass)."""
+
+    def __init__(self) -> None:
+        self.spans: dict[str, list[tuple[torch.cuda.Event, torch.cuda.Event]]] = {}
+
+    def summary(self) -> dict[str, dict[str, float]]:
+        torch.cuda.synchronize()
+        out = {}
+        for name, spans in self.spans.items():
+            ms = [a.elapsed_time(b) for a, b in spans]
+            out[name] = {"launches": len(ms), "total_ms": sum(ms), "avg_ms": sum(ms) / max(1, len(ms))}
+        return out
+
+
+PROFILE: KernelProfile | None = None
+
+
+def _run(name: str, fn, *args, launches: int = 1) -> None:
+    """Call one C-ABI entry point, raise on a non-zero status, count (and optionally time) it."""
+    prof = PROFILE
+    if prof is None:
+        _lib.check(fn(*args), name)
+    else:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(fn(*args), name)
+        b.record()
+        prof.spans.setdefault(name, []).append((a, b))
+    _count(launches)
+
+
 @dataclass(frozen=True)
 class PackedShape:
     d: int
@@ -78,9 +110,7 @@ def pack_activations(x: Tensor, b_pre: Tensor | None, terms: int, out: Tensor | 
     if out is None or out.shape != (Bp, ps.kp):
         out = torch.empty((Bp, ps.kp), dtype=torch.bfloat16, device=x.device)
     lib = _lib.load()
-    _lib.check(lib.wsae_pack_activations(_ptr(x), _ptr(b_pre), B, Bp, d, terms, _ptr(out), _stream()),
-               "wsae_pack_activations")
-    _count()
+    _run("wsae_pack_activations", lib.wsae_pack_activations, _ptr(x), _ptr(b_pre), B, Bp, d, terms, _ptr(out), _stream())
     return out
 
 
@@ -94,9 +124,7 @@ def pack_encoder(w_enc: Tensor, b_enc: Tensor | None, terms: int, out: Tensor | 
     if out is None or out.shape != (Fp, ps.kp):
         out = torch.empty((Fp, ps.kp), dtype=torch.bfloat16, device=w_enc.device)
     lib = _lib.load()
-    _lib.check(lib.wsae_pack_encoder(_ptr(w_enc), _ptr(b_enc), F, Fp, d, terms, _ptr(out), _stream()),
-               "wsae_pack_encoder")
-    _count()
+    _run("wsae_pack_encoder", lib.wsae_pack_encoder, _ptr(w_enc), _ptr(b_enc), F, Fp, d, terms, _ptr(out), _stream())
     return out
 
 
@@ -148,12 +176,7 @@ def encode_topk(a_packed: Tensor, w_packed: Tensor, B: int, F: int, d: int, term
     if nsplit > 1:
         pv = torch.empty((B, nsplit * k), dtype=torch.float32, device=dev)
         pi = torch.empty((B, nsplit * k), dtype=torch.int32, device=dev)
-    _lib.check(
-        lib.wsae_encode_topk(_ptr(a_packed), _ptr(w_packed), B, Bp, F, Fp, ps.kp, ps.used_cols, k,
-                             nsplit, _ptr(pv), _ptr(pi), _ptr(val), _ptr(idx), _stream()),
-        "wsae_encode_topk",
-    )
-    _count(2 if nsplit > 1 else 1)
+    _run("wsae_encode_topk", lib.wsae_encode_topk, _ptr(a_packed), _ptr(w_packed), B, Bp, F, Fp, ps.kp, ps.used_cols, k, nsplit, _ptr(pv), _ptr(pi), _ptr(val), _ptr(idx), _stream(), launches=2 if nsplit > 1 else 1)
     return idx, val
 
 
@@ -173,14 +196,7 @@ def decode_mse(target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: Tensor | No
     resid = torch.empty_like(target) if want_resid else None
     recon = torch.empty_like(target) if want_recon else None
     lib = _lib.load()
-    _lib.check(
-        lib.wsae_decode_mse(_ptr(target), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16),
-                            _ptr(b_dec), _ptr(b_pre), _ptr(idx), _ptr(val), B, d, F, k,
-                            _ptr(resid), _ptr(recon), _ptr(stats), _ptr(last_activated),
-                            _ptr(step_count), _stream()),
-        "wsae_decode_mse",
-    )
-    _count()
+    _run("wsae_decode_mse", lib.wsae_decode_mse, _ptr(target), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16), _ptr(b_dec), _ptr(b_pre), _ptr(idx), _ptr(val), B, d, F, k, _ptr(resid), _ptr(recon), _ptr(stats), _ptr(last_activated), _ptr(step_count), _stream())
     return resid, recon
 
 
@@ -195,24 +211,14 @@ def backward_sparse(resid: Tensor, x: Tensor | None, b_pre: Tensor | None, w_dec
     if d % 4 != 0:
         raise RuntimeError("input_dim must be a multiple of 4 for the sparse backward kernels")
     lib = _lib.load()
-    _lib.check(
-        lib.wsae_backward_sparse(_ptr(resid), _ptr(x), _ptr(b_pre), _ptr(w_decT),
-                                 int(w_decT.dtype == torch.bfloat16), _ptr(idx), _ptr(val),
-                                 _ptr(grad_out), float(coef), B, d, F, k, _ptr(d_w_enc),
-                                 _ptr(d_w_decT), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val),
-                                 _stream()),
-        "wsae_backward_sparse",
-    )
-    _count()
+    _run("wsae_backward_sparse", lib.wsae_backward_sparse, _ptr(resid), _ptr(x), _ptr(b_pre), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(d_w_enc), _ptr(d_w_decT), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _stream())
 
 
 def bpre_grad(d_b_dec: Tensor, d_b_enc: Tensor, w_enc: Tensor) -> Tensor:
     F, d = w_enc.shape
     out = torch.empty(d, dtype=torch.float32, device=w_enc.device)
     lib = _lib.load()
-    _lib.check(lib.wsae_bpre_grad(_ptr(d_b_dec), _ptr(d_b_enc), _ptr(w_enc), F, d, _ptr(out), _stream()),
-               "wsae_bpre_grad")
-    _count()
+    _run("wsae_bpre_grad", lib.wsae_bpre_grad, _ptr(d_b_dec), _ptr(d_b_enc), _ptr(w_enc), F, d, _ptr(out), _stream())
     return out
 
 
@@ -222,12 +228,7 @@ def input_grad(resid: Tensor, w_enc: Tensor, idx: Tensor, dpre_val: Tensor,
     B, k = idx.shape
     dx = torch.empty((B, d), dtype=torch.float32, device=resid.device)
     lib = _lib.load()
-    _lib.check(
-        lib.wsae_input_grad(_ptr(resid), _ptr(w_enc), _ptr(idx), _ptr(dpre_val), _ptr(grad_out),
-                            float(coef), B, d, F, k, int(subtract_g), _ptr(dx), _stream()),
-        "wsae_input_grad",
-    )
-    _count()
+    _run("wsae_input_grad", lib.wsae_input_grad, _ptr(resid), _ptr(w_enc), _ptr(idx), _ptr(dpre_val), _ptr(grad_out), float(coef), B, d, F, k, int(subtract_g), _ptr(dx), _stream())
     return dx
 
 
@@ -236,9 +237,7 @@ def renorm_decoder_(w_decT: Tensor, eps: float = 1e-12, shadow: Tensor | None = 
     _f32c(w_decT, "w_decT")
     F, d = w_decT.shape
     lib = _lib.load()
-    _lib.check(lib.wsae_renorm_decoder(_ptr(w_decT), F, d, eps, _ptr(shadow), _stream()),
-               "wsae_renorm_decoder")
-    _count()
+    _run("wsae_renorm_decoder", lib.wsae_renorm_decoder, _ptr(w_decT), F, d, eps, _ptr(shadow), _stream())
 
 
 def counters_update(last_activated: Tensor, step_count: Tensor, threshold: int, bump: bool,
@@ -247,12 +246,7 @@ def counters_update(last_activated: Tensor, step_count: Tensor, threshold: int, 
     if last_activated.dtype != torch.int64 or step_count.dtype != torch.int64:
         raise RuntimeError("dead-feature counters must be int64")
     lib = _lib.load()
-    _lib.check(
-        lib.wsae_counters_update(_ptr(last_activated), _ptr(step_count), last_activated.numel(),
-                                 int(threshold), int(bump), _ptr(dead_count), _stream()),
-        "wsae_counters_update",
-    )
-    _count()
+    _run("wsae_counters_update", lib.wsae_counters_update, _ptr(last_activated), _ptr(step_count), last_activated.numel(), int(threshold), int(bump), _ptr(dead_count), _stream())
 
 
 def densify_hidden(idx: Tensor, val: Tensor, F: int) -> Tensor:
@@ -260,9 +254,7 @@ def densify_hidden(idx: Tensor, val: Tensor, F: int) -> Tensor:
     B, k = idx.shape
     hidden = torch.empty((B, F), dtype=torch.float32, device=idx.device)
     lib = _lib.load()
-    _lib.check(lib.wsae_densify_hidden(_ptr(idx), _ptr(val), B, F, k, _ptr(hidden), _stream()),
-               "wsae_densify_hidden")
-    _count()
+    _run("wsae_densify_hidden", lib.wsae_densify_hidden, _ptr(idx), _ptr(val), B, F, k, _ptr(hidden), _stream())
     return hidden
 
 
@@ -272,24 +264,17 @@ def cast_bf16(src: Tensor, out: Tensor | None = None) -> Tensor:
     if out is None:
         out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
     lib = _lib.load()
-    _lib.check(lib.wsae_cast_bf16(_ptr(src), _ptr(out), src.numel(), _stream()), "wsae_cast_bf16")
-    _count()
+    _run("wsae_cast_bf16", lib.wsae_cast_bf16, _ptr(src), _ptr(out), src.numel(), _stream())
     return out
 
 
 def sumsq_(g: Tensor, out: Tensor) -> None:
     """out (float64[1]) += sum(g**2)."""
     lib = _lib.load()
-    _lib.check(lib.wsae_sumsq(_ptr(g), g.numel(), _ptr(out), _stream()), "wsae_sumsq")
-    _count()
+    _run("wsae_sumsq", lib.wsae_sumsq, _ptr(g), g.numel(), _ptr(out), _stream())
 
 
 def fused_adamw_(p: Tensor, grad: Tensor, m: Tensor, v: Tensor, hyper: Tensor,
                  grad_sumsq: Tensor | None) -> None:
     lib = _lib.load()
-    _lib.check(
-        lib.wsae_fused_adamw(_ptr(p), _ptr(grad), _ptr(m), _ptr(v), p.numel(), _ptr(hyper),
-                             _ptr(grad_sumsq), _stream()),
-        "wsae_fused_adamw",
-    )
-    _count()
+    _run("wsae_fused_adamw", lib.wsae_fused_adamw, _ptr(p), _ptr(grad), _ptr(m), _ptr(v), p.numel(), _ptr(hyper), _ptr(grad_sumsq), _stream())
