@@ -133,8 +133,8 @@ def test_identity_weights_reconstruct():
 
 
 @pytest.mark.parametrize("name", ["small_64x256", "tiny_test_384x3072", "mid_128x1024_k32"])
-@pytest.mark.parametrize("fused_opt", [True, False])
-def test_trainer_fp32_matches_reference_golden(name, fused_opt, tmp_path):
+@pytest.mark.parametrize("mode", ["graph", "fused", "torch"])
+def test_trainer_fp32_matches_reference_golden(name, mode, tmp_path):
     """fp32-grade mode: losses / weights within 1e-5 relative of the reference trace, TopK sets
     identical (no near-ties occur in these traces at tau = 1e-5 * max|pre|), counters bit-exact."""
     _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
@@ -144,7 +144,10 @@ def test_trainer_fp32_matches_reference_golden(name, fused_opt, tmp_path):
     sae = TopKSAE(r["d"], r["F"], k=r["k"], dead_feature_threshold=r["dead_threshold"])
     cfg = TrainingConfig(batch_size=r["B"], learning_rate=r["lr"], warmup_steps=r["warmup"], epochs=1,
                          use_amp=False, num_workers=0)
-    tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path, fused_optimizer=fused_opt)
+    # graph: CUDA-graphed step; fused: autograd node + fused clip/AdamW; torch: autograd + torch.optim
+    tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path, fused_optimizer=(mode != "torch"),
+                    cuda_graph=(mode == "graph"))
+    assert tr.cuda_graph == (mode == "graph")
     tr.setup_scheduler(r["total_steps"])
     x_all = O.synthetic_activations(r["B"] * r["steps"], r["d"], r["data_seed"])
     strict = True
@@ -179,6 +182,8 @@ def test_trainer_fp32_matches_reference_golden(name, fused_opt, tmp_path):
     sd = sae.state_dict()
     tol = 1e-5 if strict else 2e-3
     for n in O.PARAM_ORDER:
+        if not strict and not n.endswith("weight"):
+            continue   # AdamW turns ~eps-sized bias gradients into sign-like updates: not comparable after a flip
         ref = fx["final_params"][n]
         t = sd[n].cpu()
         if isinstance(ref, dict):     # digest: strided sample + abs-sum; tolerance at tensor scale

@@ -147,20 +147,31 @@ backward_sparse_kernel(const float* __restrict__ resid, const float* __restrict_
     for (int i = threadIdx.x; i < d; i += blockDim.x) atomicAdd(d_b_dec + i, s_g[i]);
 }
 
-// db_pre[c] = db_dec[c] - sum_f db_enc[f] * W_enc[f, c].   grid.x tiles columns, grid.y splits F.
+// db_pre[c] = db_dec[c] - sum_f db_enc[f] * W_enc[f, c].  One block per chunk of 32 features;
+// thread t owns columns {t, t + blockDim, ...}; features with a zero bias gradient (never selected
+// in this batch) are skipped, so only fired rows of W_enc are read.
+constexpr int kBpreFeat = 32;
 __global__ void __launch_bounds__(256)
 bpre_grad_kernel(const float* __restrict__ d_b_dec, const float* __restrict__ d_b_enc,
-                 const float* __restrict__ w_enc, int F, int d, int f_per_block,
-                 float* __restrict__ d_b_pre) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const int f0 = blockIdx.y * f_per_block;
-  const int f1 = min(F, f0 + f_per_block);
-  if (col >= d) return;
-  float acc = 0.f;
-  for (int f = f0; f < f1; ++f) acc = fmaf(d_b_enc[f], w_enc[static_cast<size_t>(f) * d + col], acc);
-  float out = -acc;
-  if (blockIdx.y == 0) out += d_b_dec[col];
-  atomicAdd(d_b_pre + col, out);
+                 const float* __restrict__ w_enc, int F, int d, float* __restrict__ d_b_pre) {
+  __shared__ float s_coef[kBpreFeat];
+  const int f0 = blockIdx.x * kBpreFeat;
+  if (threadIdx.x < kBpreFeat) {
+    const int f = f0 + threadIdx.x;
+    s_coef[threadIdx.x] = f < F ? d_b_enc[f] : 0.f;
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < d; col += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < kBpreFeat; ++j) {
+      const float c = s_coef[j];
+      if (c != 0.f) acc = fmaf(c, __ldg(w_enc + static_cast<size_t>(f0 + j) * d + col), acc);
+    }
+    float out = -acc;
+    if (blockIdx.x == 0) out += d_b_dec[col];
+    if (out != 0.f) atomicAdd(d_b_pre + col, out);
+  }
 }
 
 // dx[b, :] = sum_j dv_j * W_enc[i_j, :] - g[b, :]    (only when the input itself requires grad)
@@ -244,13 +255,9 @@ extern "C" int wsae_bpre_grad(const float* d_b_dec, const float* d_b_enc, const 
   if (!d_b_dec || !d_b_enc || !w_enc || !d_b_pre || F <= 0 || d <= 0) return kBadArg;
   cudaError_t e = cudaMemsetAsync(d_b_pre, 0, static_cast<size_t>(d) * sizeof(float), stream);
   if (e != cudaSuccess) return static_cast<int>(e);
-  const int threads = 128;
-  int fsplit = F / 256;
-  if (fsplit < 1) fsplit = 1;
-  if (fsplit > 512) fsplit = 512;
-  const int fpb = ceil_div(F, fsplit);
-  dim3 grid(ceil_div(d, threads), ceil_div(F, fpb));
-  bpre_grad_kernel<<<grid, threads, 0, stream>>>(d_b_dec, d_b_enc, w_enc, F, d, fpb, d_b_pre);
+  const int threads = d >= 256 ? 256 : 128;
+  bpre_grad_kernel<<<ceil_div(F, kBpreFeat), threads, 0, stream>>>(d_b_dec, d_b_enc, w_enc, F, d,
+                                                                 d_b_pre);
   return static_cast<int>(cudaGetLastError());
 }
 

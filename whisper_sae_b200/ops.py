@@ -214,9 +214,10 @@ def backward_sparse(resid: Tensor, x: Tensor | None, b_pre: Tensor | None, w_dec
     _run("wsae_backward_sparse", lib.wsae_backward_sparse, _ptr(resid), _ptr(x), _ptr(b_pre), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(d_w_enc), _ptr(d_w_decT), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _stream())
 
 
-def bpre_grad(d_b_dec: Tensor, d_b_enc: Tensor, w_enc: Tensor) -> Tensor:
+def bpre_grad(d_b_dec: Tensor, d_b_enc: Tensor, w_enc: Tensor, out: Tensor | None = None) -> Tensor:
     F, d = w_enc.shape
-    out = torch.empty(d, dtype=torch.float32, device=w_enc.device)
+    if out is None:
+        out = torch.empty(d, dtype=torch.float32, device=w_enc.device)
     lib = _lib.load()
     _run("wsae_bpre_grad", lib.wsae_bpre_grad, _ptr(d_b_dec), _ptr(d_b_enc), _ptr(w_enc), F, d, _ptr(out), _stream())
     return out

@@ -292,9 +292,13 @@ class TopKSAE(nn.Module):
         def _hidden() -> Tensor:
             return ops.densify_hidden(st.idx, st.val, F)
 
-        l0 = st.stats[1].to(torch.float32) / float(B)
-        sparsity = torch.tensor(0.0, device=x.device)
-        out = SAEOutput(_recon, _hidden, loss, loss, sparsity, l0)
+        def _l0() -> Tensor:
+            return st.stats[1].to(torch.float32) / float(B)
+
+        def _sparsity() -> Tensor:
+            return torch.zeros((), dtype=torch.float32, device=x.device)
+
+        out = SAEOutput(_recon, _hidden, loss, loss, _sparsity, _l0)
         self._last_sparse = st
         return out
 

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import json
 import math
+import os
 from dataclasses import asdict, dataclass
 from pathlib import Path
 
@@ -31,7 +32,7 @@ from torch.utils.data import DataLoader
 
 from .. import ops
 from ..config import TrainingConfig
-from .model import SAEOutput, TopKSAE
+from .model import SAEOutput, TopKSAE, _fp32_terms, _SparseState
 
 
 @dataclass
@@ -45,6 +46,148 @@ class TrainingMetrics:
     dead_feature_ratio: float
     learning_rate: float
     step: int
+
+
+def _ensure_adamw_state(optimizer: AdamW, p: Tensor) -> dict:
+    """AdamW state for ``p`` exactly as torch.optim.AdamW creates it (float32 CPU ``step``), with the
+    moments in the parameter's own dense layout so flat elementwise kernels can walk the storage."""
+    st = optimizer.state[p]
+    if len(st) == 0:
+        st["step"] = torch.tensor(0.0, dtype=torch.float32)
+        st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+    for name in ("exp_avg", "exp_avg_sq"):
+        t = st[name]
+        if t.stride() != p.stride() or t.device != p.device:
+            st[name] = torch.empty_strided(p.shape, p.stride(), dtype=p.dtype, device=p.device).copy_(t)
+    return st
+
+
+class _GraphedStep:
+    """One full train step (K0..K5 + clip + AdamW + renorm) at a fixed batch shape, launched from a
+    CUDA graph: the per-step host work drops from ~40 launches to one ``replay()``.
+
+    No autograd: the kernels are called in the same order the autograd node would run them, with
+    ``grad_output = 1``.  The first call runs the body eagerly (it is a real step and also warms
+    up per-function attributes), the second call captures, later calls replay.  Learning rate and
+    Adam bias corrections live in a device ``hyper`` vector refreshed from pinned memory before
+    every replay, so the captured graph never goes stale.
+    """
+
+    def __init__(self, trainer: "SAETrainer", rows: int):
+        m = trainer.model
+        dev = m.b_pre.device
+        self.trainer = trainer
+        self.rows = rows
+        self.bf16 = bool(trainer.use_amp)
+        self.x = torch.empty((rows, m.input_dim), dtype=torch.float32, device=dev)
+        self.stats = torch.zeros(3, dtype=torch.int64, device=dev)
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.one = torch.ones((), dtype=torch.float32, device=dev)
+        self.params = [m.b_pre, m.encoder.weight, m.encoder.bias, m.decoder.weight, m.decoder.bias]
+        m._w_decT()
+        F, d = m.hidden_dim, m.input_dim
+        self.g_b_pre = torch.zeros(d, dtype=torch.float32, device=dev)
+        self.g_w_enc = torch.zeros((F, d), dtype=torch.float32, device=dev)
+        self.g_b_enc = torch.zeros(F, dtype=torch.float32, device=dev)
+        self.g_w_decT = torch.zeros((F, d), dtype=torch.float32, device=dev)
+        self.g_b_dec = torch.zeros(d, dtype=torch.float32, device=dev)
+        self.grads = [self.g_b_pre, self.g_w_enc, self.g_b_enc, self.g_w_decT, self.g_b_dec]
+        self.state = _SparseState()
+        self.graph: torch.cuda.CUDAGraph | None = None
+        self.calls = 0
+        for p in self.params:
+            _ensure_adamw_state(trainer.optimizer, p)
+        self._ptrs: tuple[int, ...] = ()
+
+    def _pointer_key(self) -> tuple[int, ...]:
+        m = self.trainer.model
+        opt_state = self.trainer.optimizer.state
+        ptrs = [p.data_ptr() for p in self.params]
+        ptrs += [m.feature_last_activated.data_ptr(), m.step_count.data_ptr()]
+        for p in self.params:
+            ptrs += [opt_state[p]["exp_avg"].data_ptr(), opt_state[p]["exp_avg_sq"].data_ptr()]
+        return tuple(ptrs)
+
+    def _body(self) -> None:
+        m = self.trainer.model
+        x = self.x
+        B, d = x.shape
+        F, k = m.hidden_dim, m.k
+        terms = 1 if self.bf16 else _fp32_terms()
+        w_decT = m.decoder.weight.data.t()
+        self.stats.zero_()
+        a_packed = ops.pack_activations(x, m.b_pre.data, terms)
+        w_packed = ops.pack_encoder(m.encoder.weight.data, m.encoder.bias.data, terms)
+        idx, val = ops.encode_topk(a_packed, w_packed, B, F, d, terms, k)
+        w_used = ops.cast_bf16(w_decT) if self.bf16 else w_decT
+        resid, _ = ops.decode_mse(x, w_used, m.decoder.bias.data, m.b_pre.data, idx, val,
+                                  stats=self.stats, last_activated=m.feature_last_activated,
+                                  step_count=m.step_count)
+        ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold, True,
+                            self.stats[2:])
+        rows_total = m._global_rows or B
+        for g in self.grads:
+            g.zero_()
+        dpre = torch.empty((B, k), dtype=torch.float32, device=x.device)
+        ops.backward_sparse(resid, x, m.b_pre.data, w_used, idx, val, self.one,
+                            2.0 / (float(rows_total) * d), d_w_enc=self.g_w_enc,
+                            d_w_decT=self.g_w_decT, d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec,
+                            dpre_val=dpre)
+        ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
+        self.sumsq.zero_()
+        for g in self.grads:
+            ops.sumsq_(g, self.sumsq)
+        opt_state = self.trainer.optimizer.state
+        for p, g in zip(self.params, self.grads):
+            st = opt_state[p]
+            ops.fused_adamw_(p.data, g, st["exp_avg"], st["exp_avg_sq"], self.hyper, self.sumsq)
+        ops.renorm_decoder_(w_decT, 1e-12)
+        s = self.state
+        s.idx, s.val, s.resid, s.stats, s.w_dec_used, s.rows_total = idx, val, resid, self.stats, w_used, rows_total
+
+    def run(self, batch: Tensor) -> None:
+        tr = self.trainer
+        self.x.copy_(batch, non_blocking=True)
+        group = tr.optimizer.param_groups[0]
+        step_t = 0.0
+        for p in self.params:
+            st = tr.optimizer.state[p]
+            st["step"] += 1
+            step_t = float(st["step"])
+        beta1, beta2 = group["betas"]
+        h = self.hyper_host
+        h[0], h[1], h[2], h[3], h[4] = group["lr"], beta1, beta2, group["eps"], group["weight_decay"]
+        h[5] = 1.0 - beta1 ** step_t
+        h[6] = math.sqrt(1.0 - beta2 ** step_t)
+        h[7] = tr.config.gradient_clip
+        self.hyper.copy_(h, non_blocking=True)
+        self.calls += 1
+        m = tr.model
+        m._w_decT()
+        for p in self.params:
+            _ensure_adamw_state(tr.optimizer, p)
+        key = self._pointer_key()
+        if key != self._ptrs:      # storage was swapped behind our back (.data = ..., load): re-capture
+            self.graph = None
+            self._ptrs = key
+            self.calls = 1
+        if self.calls == 1:
+            self._body()
+        else:
+            if self.graph is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._body()
+                self.graph = g
+            self.graph.replay()
+        # expose grads the way autograd would (decoder.weight's grad is the [d, F] transposed view)
+        for p, g in zip(self.params, self.grads):
+            p.grad = g.t() if p is tr.model.decoder.weight else g
+        tr.model._last_sparse = self.state
 
 
 class SAETrainer:
@@ -61,6 +204,7 @@ class SAETrainer:
         *,
         grad_scaler: bool = False,
         fused_optimizer: bool | None = None,
+        cuda_graph: bool | None = None,
     ):
         self.model = model.to(device)
         self.config = config
@@ -87,6 +231,10 @@ class SAETrainer:
         self._resample_dataset = None
         self._hyper: Tensor | None = None
         self._sumsq: Tensor | None = None
+        if cuda_graph is None:
+            cuda_graph = os.environ.get("WSAE_CUDA_GRAPH", "1") != "0"
+        self.cuda_graph = bool(cuda_graph) and self.fused_optimizer and not self.scaler.is_enabled()
+        self._graphs: dict[int, _GraphedStep] = {}
 
     # ------------------------------------------------------------------ resampling plumbing
     def set_resample_dataset(self, dataset: torch.utils.data.Dataset) -> None:
@@ -141,11 +289,7 @@ class SAETrainer:
         # optimizer state, created exactly like torch.optim.AdamW does (step as a float32 tensor)
         step_t = None
         for p in params:
-            state = self.optimizer.state[p]
-            if len(state) == 0:
-                state["step"] = torch.tensor(0.0, dtype=torch.float32)
-                state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            state = _ensure_adamw_state(self.optimizer, p)
             state["step"] += 1
             step_t = float(state["step"])
         beta1, beta2 = group["betas"]
@@ -171,6 +315,16 @@ class SAETrainer:
         self.model.train()
         if isinstance(batch, (tuple, list)):
             batch = batch[0]
+        if self._graph_ok(batch):
+            gs = self._graphs.get(batch.shape[0])
+            if gs is None:
+                gs = self._graphs[batch.shape[0]] = _GraphedStep(self, batch.shape[0])
+            gs.run(batch)
+            if self.scheduler is not None:
+                self.scheduler.step()
+            self.global_step += 1
+            return self._read_metrics(None, batch.shape[0])
+
         batch = batch.to(self.device, non_blocking=True)
 
         with torch.amp.autocast("cuda", enabled=self.use_amp):
@@ -196,10 +350,17 @@ class SAETrainer:
         metrics = self._read_metrics(output, batch.shape[0])
         return metrics
 
-    def _read_metrics(self, output: SAEOutput, rows: int) -> TrainingMetrics:
+    def _graph_ok(self, batch: Tensor) -> bool:
+        m = self.model
+        return (self.cuda_graph and isinstance(m, TopKSAE) and type(m).forward is TopKSAE.forward
+                and batch.dim() == 2 and batch.shape[1] == m.input_dim and m.input_dim % 4 == 0
+                and batch.dtype == torch.float32 and m.k <= 64 and m.precision is None
+                and all(p.requires_grad for p in m.parameters()))
+
+    def _read_metrics(self, output: SAEOutput | None, rows: int) -> TrainingMetrics:
         lr = self.optimizer.param_groups[0]["lr"]
         st = getattr(self.model, "_last_sparse", None)
-        if st is not None and st.stats is not None and output.loss.is_cuda:
+        if st is not None and st.stats is not None and (output is None or output.loss.is_cuda):
             raw = st.stats.cpu()  # the step's single device->host sync (24 bytes)
             sse = raw[:1].view(torch.float64).item()
             d_out = st.resid.shape[1]
