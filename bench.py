@@ -106,7 +106,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_trainer(batch: int, device: str, layer_seed: int, use_amp: bool = True):
+def make_trainer(batch: int, device: str, layer_seed: int, use_amp: bool = True, cuda_graph=None):
     from whisper_sae_b200.config import ExperimentConfig
     from whisper_sae_b200.sae import SAETrainer, create_sae
 
@@ -116,7 +116,7 @@ def make_trainer(batch: int, device: str, layer_seed: int, use_amp: bool = True)
     torch.manual_seed(cfg.training.seed + layer_seed)
     sae = create_sae(cfg.sae, cfg.whisper.hidden_dim)
     run_dir = Path(tempfile.mkdtemp(prefix="wsae_bench_"))
-    tr = SAETrainer(sae, cfg.training, device=device, run_dir=run_dir)
+    tr = SAETrainer(sae, cfg.training, device=device, run_dir=run_dir, cuda_graph=cuda_graph)
     tr.setup_scheduler(100_000)
     return tr, cfg
 
@@ -348,7 +348,13 @@ def main() -> None:
 
     line = None
     if rank == 0:
-        prof = kernel_profile(tr, dev_batches, min(args.steps, 20))
+        # per-kernel CUDA-event timing needs eager launches: same kernels, graph replay switched off
+        tr_eager, _ = make_trainer(args.batch, dev, layer_seed=rank, use_amp=(args.precision == "bf16"),
+                                   cuda_graph=False)
+        for i in range(3):
+            tr_eager.train_step(dev_batches[i % nb])
+        prof = kernel_profile(tr_eager, dev_batches, min(args.steps, 20))
+        del tr_eager
         roof = roofline(prof, args.batch, D_MODEL, HIDDEN, TOPK, peaks, args.precision == "bf16")
         roof["peak_source"] = f"{peak_src} (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"
         shares = {n: round(v["share_of_step"], 4) for n, v in prof.items() if not n.startswith("_")}

@@ -97,6 +97,7 @@ class _GraphedStep:
         self.grads = [self.g_b_pre, self.g_w_enc, self.g_b_enc, self.g_w_decT, self.g_b_dec]
         self.state = _SparseState()
         self.graph: torch.cuda.CUDAGraph | None = None
+        self.kernels_per_replay = 0
         self.calls = 0
         for p in self.params:
             _ensure_adamw_state(trainer.optimizer, p)
@@ -180,10 +181,14 @@ class _GraphedStep:
             if self.graph is None:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
+                before = ops.GPU_LAUNCHES
                 with torch.cuda.graph(g):
                     self._body()
+                self.kernels_per_replay = ops.GPU_LAUNCHES - before   # captured, not yet executed
+                ops.GPU_LAUNCHES = before
                 self.graph = g
             self.graph.replay()
+            ops.GPU_LAUNCHES += self.kernels_per_replay
         # expose grads the way autograd would (decoder.weight's grad is the [d, F] transposed view)
         for p, g in zip(self.params, self.grads):
             p.grad = g.t() if p is tr.model.decoder.weight else g
