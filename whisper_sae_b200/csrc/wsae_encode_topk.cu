@@ -61,28 +61,52 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
 // Thread-private candidate list: slot s of row r lives at base[s * 128 + r].
 // Raise tau so that at most k + slack candidates (exactly k when slack == 0) survive, and
 // compact the list in place.  Warp-synchronous: every lane of the warp must call it.
+//
+// The candidates are pulled into registers once; the k-th largest is then bracketed by a
+// bisection over the order-preserving integer image of the floats (so it terminates on ties and
+// needs no assumptions about the value distribution), while every comparison is done in float
+// space with 4 independent counters (the counting loop is the hot spot: FSET + FADD per element,
+// no serial predicate chain).  All comparisons use float semantics, so -0.0 == +0.0 throughout.
 template <int CAP>
 __device__ __forceinline__ void topk_compact(float* cv, uint32_t* ci, int& cnt, float& tau, int k,
                                              int slack) {
-  uint32_t key[CAP];
-  uint32_t hi = 0;
+  const float ninf = __uint_as_float(0xff800000u);
+  const float pinf = __uint_as_float(0x7f800000u);
+  float v[CAP];
+  float vmax = ninf, vmin = pinf;
 #pragma unroll
   for (int s = 0; s < CAP; ++s) {
-    key[s] = (s < cnt) ? f2key(cv[s * kBM]) : 0u;
-    hi = max(hi, key[s]);
+    const bool valid = s < cnt;
+    const float x = valid ? cv[s * kBM] : ninf;
+    v[s] = x;
+    vmax = fmaxf(vmax, x);
+    vmin = fminf(vmin, valid ? x : pinf);
   }
-  // Stored keys are > key(tau), or == key(tau) when tau came from a tie break (then exactly k are
-  // stored).  Starting one below key(tau) covers both: count(key > lo) == cnt.
-  uint32_t lo = f2key(tau) - 1u;  // invariant: count(key > lo) >= min(cnt, k); count(key > hi) < k
+  const bool keep_all = cnt <= k + slack;   // nothing to drop for this lane (it still loops along)
+  // invariants (float semantics): count(v > f(lo)) >= k,  count(v > f(hi)) < k
+  uint32_t lo = f2key(vmin) - 1u;           // below every candidate: count == cnt
+  uint32_t hi = f2key(vmax);                // count == 0
   int c_lo = cnt;
-  bool done = (c_lo <= k + slack);
+  bool done = keep_all;
+  int it = 0;
   while (true) {
     const bool active = !done && (hi - lo > 1u);
     if (!__any_sync(0xffffffffu, active)) break;
-    const uint32_t mid = lo + ((hi - lo) >> 1);
-    int c = 0;
+    const uint32_t span = hi - lo;
+    // the k-th largest sits in the dense lower part of [vmin, vmax]: first probes split 1:3
+    const uint32_t step = max(1u, span >> (it < 2 ? 2 : 1));
+    ++it;
+    const uint32_t mid = lo + step;
+    const float midf = key2f(mid);
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
-    for (int s = 0; s < CAP; ++s) c += (key[s] > mid) ? 1 : 0;
+    for (int s = 0; s < CAP; s += 4) {
+      c0 += (v[s] > midf) ? 1.f : 0.f;
+      if (s + 1 < CAP) c1 += (v[s + 1] > midf) ? 1.f : 0.f;
+      if (s + 2 < CAP) c2 += (v[s + 2] > midf) ? 1.f : 0.f;
+      if (s + 3 < CAP) c3 += (v[s + 3] > midf) ? 1.f : 0.f;
+    }
+    const int c = static_cast<int>((c0 + c1) + (c2 + c3));
     if (active) {
       if (c >= k) {
         lo = mid;
@@ -93,36 +117,40 @@ __device__ __forceinline__ void topk_compact(float* cv, uint32_t* ci, int& cnt, 
       }
     }
   }
-  // done: keep key > lo.  otherwise hi == lo + 1 and the values equal to hi are tied across the
-  // k-th position: keep everything above hi plus the first (k - m) ties (lowest index first).
-  uint32_t thr = lo, tie_key = 0xFFFFFFFFu;
+  // done: keep v > f(lo).  otherwise hi == lo + 1: the values equal to f(hi) tie across the k-th
+  // position; keep everything above plus the first (k - m) ties (lowest feature index first).
+  const float thrf = key2f(done ? lo : hi);
   int tie_left = 0;
   if (!done) {
-    int m = 0;
+    float m0 = 0.f, m1 = 0.f;
 #pragma unroll
-    for (int s = 0; s < CAP; ++s) m += (key[s] > hi) ? 1 : 0;
-    thr = hi;
-    tie_key = hi;
-    tie_left = k - m;
+    for (int s = 0; s < CAP; s += 2) {
+      m0 += (v[s] > thrf) ? 1.f : 0.f;
+      if (s + 1 < CAP) m1 += (v[s + 1] > thrf) ? 1.f : 0.f;
+    }
+    tie_left = k - static_cast<int>(m0 + m1);
   }
-  int w = 0;
+  if (!keep_all) {
+    int w = 0;
 #pragma unroll
-  for (int s = 0; s < CAP; ++s) {
-    const uint32_t kk = key[s];
-    bool keep = kk > thr;
-    if (!keep && kk == tie_key && tie_left > 0) {
-      keep = true;
-      --tie_left;
+    for (int s = 0; s < CAP; ++s) {
+      const float x = v[s];
+      bool keep = x > thrf;
+      if (!done && x == thrf && tie_left > 0) {
+        keep = true;
+        --tie_left;
+      }
+      if (keep) {
+        if (w != s) {
+          cv[w * kBM] = x;
+          ci[w * kBM] = ci[s * kBM];
+        }
+        ++w;
+      }
     }
-    if (keep) {
-      const uint32_t id = ci[s * kBM];
-      cv[w * kBM] = key2f(kk);
-      ci[w * kBM] = id;
-      ++w;
-    }
+    cnt = w;
+    if (c_lo >= k) tau = thrf;
   }
-  cnt = w;
-  if (c_lo >= k) tau = key2f(thr);
 }
 
 template <int CAP, int STAGES>
@@ -131,9 +159,10 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_w, int B, int F, int k, int ksteps,
                    int num_m_blocks, int num_n_tiles, int nsplit, int tiles_per_split,
                    float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B tiles, computed as an OFFSET so that the pointers keep
+  // their shared address space (a uintptr_t round-trip would demote every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* pipe = smem;
   float* cand_val = reinterpret_cast<float*>(smem + EncodeSmem<CAP, STAGES>::kPipeBytes);
   uint32_t* cand_idx = reinterpret_cast<uint32_t*>(cand_val + CAP * kBM);

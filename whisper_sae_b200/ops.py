@@ -151,7 +151,9 @@ def choose_nsplit(B: int, F: int, k: int, num_sms: int) -> int:
         if ns > 1 and (ns * k + 31) // 32 > 64:
             break
         waves = (m_blocks * ns + num_sms - 1) // num_sms
-        cost = waves * tps + (0.15 * ns if ns > 1 else 0.0)  # small penalty for the merge pass
+        # every work item pays a fixed start-up cost (the running threshold restarts at -inf and the
+        # first few hundred columns are almost all accepted): measured ~8 tile-times per item
+        cost = waves * (tps + 8) + (0.15 * ns if ns > 1 else 0.0)
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = ns, cost
     return best

@@ -384,10 +384,47 @@ class SAETrainer:
             step=self.global_step,
         )
 
+    def _prefetched(self, dataloader):
+        """Iterate ``dataloader`` one batch ahead: the host->device copy of batch n+1 is issued on a
+        side stream before step n runs, so PCIe traffic hides behind compute (pinned batches, which
+        is what ``FeatureCache.get_dataloader`` yields with ``pin_memory=True``)."""
+        if not str(self.device).startswith("cuda"):
+            yield from dataloader
+            return
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+
+        def stage(item):
+            t = item[0] if isinstance(item, (tuple, list)) else item
+            if t.is_cuda:
+                return t, None
+            with torch.cuda.stream(self._copy_stream):
+                dev = t.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return dev, ev
+
+        it = iter(dataloader)
+        try:
+            ahead = stage(next(it))
+        except StopIteration:
+            return
+        while ahead is not None:
+            dev, ev = ahead
+            try:
+                ahead = stage(next(it))
+            except StopIteration:
+                ahead = None
+            if ev is not None:
+                main = torch.cuda.current_stream()
+                main.wait_event(ev)
+                dev.record_stream(main)
+            yield dev
+
     def train_epoch(self, dataloader: DataLoader, progress: Progress | None = None,
                     task_id: int | None = None) -> list[TrainingMetrics]:
         epoch_metrics: list[TrainingMetrics] = []
-        for batch in dataloader:
+        for batch in self._prefetched(dataloader):
             m = self.train_step(batch)
             epoch_metrics.append(m)
             self.metrics_history.append(m)
