@@ -179,6 +179,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
+// Wait for the tcgen05.ld that filled r[]; the "+r" operands pin the uses after the wait.
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]),
+                 "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
+                 "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major bf16 operand tile stored with the 128-byte
 // swizzle exactly as TMA (CU_TENSOR_MAP_SWIZZLE_128B) writes it: rows of 64 bf16 = 128 B,
 // 8-row groups 1024 B apart (SBO), descriptor version 1 (Blackwell), layout type 2 (SW128).

@@ -48,16 +48,6 @@ struct EncodeSmem {
   static constexpr int kTotal = kPipeBytes + kCandBytes + kBarBytes + 1024;  // +1024 align slack
 };
 
-// Wait for the tcgen05.ld that filled r[]; the "+r" operands pin the uses after the wait.
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]),
-                 "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
-                 "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-
 // Thread-private candidate list: slot s of row r lives at base[s * 128 + r].
 // Raise tau so that at most k + slack candidates (exactly k when slack == 0) survive, and
 // compact the list in place.  Warp-synchronous: every lane of the warp must call it.

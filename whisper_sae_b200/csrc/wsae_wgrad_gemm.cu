@@ -1,0 +1,407 @@
+// wsae_wgrad_gemm.cu — K4: the two weight-gradient GEMMs of the TopK-SAE backward on tcgen05.
+//
+// Autograd of the reference's two Linear layers (model.py:111 encoder, :129 decoder) produces
+//   dW_enc [F,d]  = dpre^T   . xc      (dpre  [B,F]: k nonzeros per row, values dv)
+//   dW_decT[F,d]  = hidden^T . g       (hidden[B,F]: same pattern,       values relu(v))
+// as dense [F,B]x[B,d] products over >= 99 %-zero operands (training.py:184).  Both are
+//   OUT[F, d] (+)= alpha * S^T . R,   S = k-sparse [B,F] given as bucketed entries, R = bf16 [B,d]
+// and are computed here as a tensor-core GEMM with M = 128 features, N = d, K = batch rows:
+//   * R tiles ([64 rows] x [n_tile cols], MN-major for the MMA) arrive by TMA as n_tile/64
+//     swizzled 64x64 blocks on one mbarrier;
+//   * the sparse operand is expanded on the fly: for every (feature tile, 64-row chunk) the builder
+//     warps zero a 128x64 bf16 tile in shared memory and scatter that cell's few entries into it,
+//     in the SWIZZLE_128B K-major layout the MMA expects — S is never dense in HBM;
+//   * fp32 accumulators live in TMEM; split-K CTAs combine with red.global.add.f32.
+// The bucketing (entries grouped by feature tile, then by row chunk) is three small kernels below.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "wsae_common.cuh"
+
+namespace wsae {
+
+constexpr int kWgFeat = 128;   // features per MMA tile (M, TMEM lanes)
+constexpr int kWgRows = 64;    // batch rows per pipeline stage (K per stage)
+constexpr int kWgATile = kWgFeat * kWgRows * 2;   // 16 KB
+constexpr int kWgRBlock = kWgRows * 64 * 2;       // one 64x64 bf16 block: 8 KB
+constexpr int kWgMaxNB = 8;                       // n_tile <= 512 columns (TMEM)
+
+// ------------------------------------------------------------------------------------------------
+// bucketing: entries of (idx,val) grouped by (feature tile, row chunk)
+// ------------------------------------------------------------------------------------------------
+// counts[ft * n_chunks + chunk] = number of active entries (value > 0) of that cell
+__global__ void __launch_bounds__(256)
+bucket_count_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, int B, int F,
+                    int k, int n_chunks, int n_ft, int* __restrict__ counts) {
+  extern __shared__ int s_cnt[];  // [n_ft]
+  const int chunk = blockIdx.x;
+  for (int i = threadIdx.x; i < n_ft; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const int row0 = chunk * kWgRows;
+  const int nrow = min(kWgRows, B - row0);
+  for (int e = threadIdx.x; e < nrow * k; e += blockDim.x) {
+    const int32_t f = idx[static_cast<size_t>(row0) * k + e];
+    const float v = val[static_cast<size_t>(row0) * k + e];
+    if (f >= 0 && f < F && v > 0.f) atomicAdd(&s_cnt[f / kWgFeat], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_ft; i += blockDim.x) counts[static_cast<size_t>(i) * n_chunks + chunk] = s_cnt[i];
+}
+
+// in-place exclusive scan of counts[0..n) -> offsets[0..n], offsets[n] = total.  Single block.
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(int* __restrict__ counts_offsets, int n) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? counts_offsets[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int incl = x + (warp > 0 ? s_warp[warp - 1] : 0) + carry;
+    if (i < n) counts_offsets[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts_offsets[n] = s_carry;
+}
+
+// meta = row_local (0..63) | f_local << 8 ; va = dv ; vb = relu(val)
+__global__ void __launch_bounds__(256)
+bucket_fill_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val,
+                   const float* __restrict__ dpre, int B, int F, int k, int n_chunks, int n_ft,
+                   const int* __restrict__ offsets, uint32_t* __restrict__ ent_meta,
+                   float* __restrict__ ent_a, float* __restrict__ ent_b) {
+  extern __shared__ int s_cur[];  // [n_ft]
+  const int chunk = blockIdx.x;
+  for (int i = threadIdx.x; i < n_ft; i += blockDim.x)
+    s_cur[i] = offsets[static_cast<size_t>(i) * n_chunks + chunk];
+  __syncthreads();
+  const int row0 = chunk * kWgRows;
+  const int nrow = min(kWgRows, B - row0);
+  for (int e = threadIdx.x; e < nrow * k; e += blockDim.x) {
+    const size_t g = static_cast<size_t>(row0) * k + e;
+    const int32_t f = idx[g];
+    const float v = val[g];
+    if (f >= 0 && f < F && v > 0.f) {
+      const int ft = f / kWgFeat;
+      const int pos = atomicAdd(&s_cur[ft], 1);
+      ent_meta[pos] = static_cast<uint32_t>(e / k) | (static_cast<uint32_t>(f - ft * kWgFeat) << 8);
+      ent_a[pos] = dpre[g];
+      ent_b[pos] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM
+// ------------------------------------------------------------------------------------------------
+// MN-major bf16 operand stored as 64x64 blocks (rows = K index, 128 B each, SWIZZLE_128B), blocks
+// along N spaced `block_bytes` apart: LBO = block stride (N direction), SBO = 8 rows = 1024 B.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t block_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((block_bytes >> 4) & 0x3FFFu) << 16;   // LBO
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                      // SBO
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16, A = bf16 K-major, B = bf16 MN-major, D = fp32
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(256, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int n_chunks, int n_ft,
+                  int n_nt, int nb_tile, int ksplit, const int* __restrict__ offsets,
+                  const uint32_t* __restrict__ ent_meta, const float* __restrict__ ent_val,
+                  const float* __restrict__ grad_out, float alpha, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stage_bytes = kWgATile + nb_tile * kWgRBlock;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* r_full = bars;               // [STAGES]  TMA landed
+  uint64_t* a_full = bars + STAGES;      // [STAGES]  sparse tile built (128 arrivals)
+  uint64_t* empty = bars + 2 * STAGES;   // [STAGES]  MMAs that read the stage have retired
+  uint64_t* acc_full = bars + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // work item -> (feature tile, n tile, k split)
+  int item = blockIdx.x;
+  const int ks = item % ksplit;
+  item /= ksplit;
+  const int nt = item % n_nt;
+  const int ft = item / n_nt;
+  const int per = ceil_div(n_chunks, ksplit);
+  const int c0 = ks * per;
+  const int c1 = min(n_chunks, c0 + per);
+  const int nchunk = max(0, c1 - c0);
+  const int nb0 = nt * nb_tile;                       // first 64-column block of this n tile
+  const int nb_total = ceil_div(d, 64);
+  const int nb_here = min(nb_tile, nb_total - nb0);   // blocks that exist
+  const int n_cols = nb_here * 64;
+  const uint32_t tmem_cols = n_cols > 256 ? 512u : (n_cols > 128 ? 256u : (n_cols > 64 ? 128u : 64u));
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_r);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&r_full[s], 1);
+      mbar_init(&a_full[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: R tiles =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nchunk; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&r_full[stage], static_cast<uint32_t>(nb_here * kWgRBlock));
+        uint8_t* dst = smem + stage * stage_bytes + kWgATile;
+        for (int b = 0; b < nb_here; ++b)   // one swizzled 64x64 block per bulk copy
+          tma_load_2d(dst + b * kWgRBlock, &tmap_r, &r_full[stage], (nb0 + b) * 64, (c0 + c) * kWgRows);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const int n1 = min(256, n_cols);
+    const int n2 = n_cols - n1;
+    const uint32_t idesc1 = umma_idesc_bf16_bmn(kWgFeat, n1);
+    const uint32_t idesc2 = umma_idesc_bf16_bmn(kWgFeat, n2 > 0 ? n2 : 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int c = 0; c < nchunk; ++c) {
+      mbar_wait(&r_full[stage], phase);
+      mbar_wait(&a_full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sr = sa + kWgATile;
+        const uint64_t da = umma_desc_sw128_kmajor(sa);
+        const uint64_t db1 = umma_desc_sw128_mnmajor(sr, kWgRBlock);
+        const uint64_t db2 = umma_desc_sw128_mnmajor(sr + 4 * kWgRBlock, kWgRBlock);
+#pragma unroll
+        for (int kk = 0; kk < kWgRows / 16; ++kk) {
+          const uint32_t acc = (c | kk) != 0 ? 1u : 0u;
+          // A: +32 B per 16 K elements inside the swizzled 128 B row; R: +16 rows * 128 B
+          umma_bf16(tmem_base, da + static_cast<uint64_t>(2 * kk),
+                    db1 + static_cast<uint64_t>((kk * 16 * 128) >> 4), idesc1, acc);
+          if (n2 > 0)
+            umma_bf16(tmem_base + 256, da + static_cast<uint64_t>(2 * kk),
+                      db2 + static_cast<uint64_t>((kk * 16 * 128) >> 4), idesc2, acc);
+        }
+        umma_commit(&empty[stage]);
+        if (c == nchunk - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== sparse-tile builders, then epilogue =====================
+    const int t = threadIdx.x - 128;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int c = 0; c < nchunk; ++c) {
+      mbar_wait(&empty[stage], phase ^ 1u);
+      uint8_t* a_tile = smem + stage * stage_bytes;
+      // zero 16 KB: thread t clears row t (128 B)
+      uint4* rowp = reinterpret_cast<uint4*>(a_tile + t * 128);
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rowp[i] = z;
+      named_bar_sync(1, 128);
+      const size_t cell = static_cast<size_t>(ft) * n_chunks + (c0 + c);
+      const int e0 = offsets[cell], e1 = offsets[cell + 1];
+      for (int e = e0 + t; e < e1; e += 128) {
+        const uint32_t m = ent_meta[e];
+        const uint32_t row = m & 0xFFu, fl = m >> 8;
+        const uint32_t off = fl * 128u + ((((row >> 3) ^ (fl & 7u)) & 7u) << 4) + ((row & 7u) << 1);
+        *reinterpret_cast<__nv_bfloat16*>(a_tile + off) = __float2bfloat16_rn(ent_val[e]);
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&a_full[stage]);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    if (nchunk > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const float s = alpha * (grad_out != nullptr ? *grad_out : 1.f);
+      const int q = warp - 4;
+      const int f = ft * kWgFeat + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      for (int cb = 0; cb < n_cols; cb += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + cb, r);
+        tmem_ld_wait16(r);
+        const int col0 = nb0 * 64 + cb;
+        if (f < F) {
+          float* orow = out + static_cast<size_t>(f) * d + col0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (col0 + j + 3 < d) {
+              const float a = s * __uint_as_float(r[j]), b = s * __uint_as_float(r[j + 1]);
+              const float cc = s * __uint_as_float(r[j + 2]), dd = s * __uint_as_float(r[j + 3]);
+              if (a != 0.f || b != 0.f || cc != 0.f || dd != 0.f) red_add_f32x4(orow + j, a, b, cc, dd);
+            } else {
+              for (int jj = j; jj < j + 4; ++jj)
+                if (col0 + jj < d) atomicAdd(orow + jj, s * __uint_as_float(r[jj]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 wg_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return static_cast<PFN_cuTensorMapEncodeTiled_v12000>(nullptr);
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+}  // namespace wsae
+
+using namespace wsae;
+
+extern "C" int wsae_bucket_cells(int B, int F, int* n_chunks, int* n_ft) {
+  if (B <= 0 || F <= 0) return kBadArg;
+  if (n_chunks) *n_chunks = ceil_div(B, kWgRows);
+  if (n_ft) *n_ft = ceil_div(F, kWgFeat);
+  return kOk;
+}
+
+extern "C" int wsae_bucket_by_tile(const int32_t* idx, const float* val, const float* dpre, int B,
+                                   int F, int k, int* offsets, uint32_t* ent_meta, float* ent_a,
+                                   float* ent_b, cudaStream_t stream) {
+  if (!idx || !val || !dpre || !offsets || !ent_meta || !ent_a || !ent_b) return kBadArg;
+  if (B <= 0 || F <= 0 || k <= 0) return kBadArg;
+  const int n_chunks = ceil_div(B, kWgRows), n_ft = ceil_div(F, kWgFeat);
+  const size_t smem = static_cast<size_t>(n_ft) * sizeof(int);
+  if (smem > 48 * 1024) return kUnsupported;
+  bucket_count_kernel<<<n_chunks, 256, smem, stream>>>(idx, val, B, F, k, n_chunks, n_ft, offsets);
+  bucket_scan_kernel<<<1, 1024, 0, stream>>>(offsets, n_chunks * n_ft);
+  bucket_fill_kernel<<<n_chunks, 256, smem, stream>>>(idx, val, dpre, B, F, k, n_chunks, n_ft, offsets,
+                                                      ent_meta, ent_a, ent_b);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// out[F,d] += alpha * (*grad_out) * S^T . R, S from the bucketed entries with values ent_val,
+// R = bf16 [B rows, >= ceil(d/64)*64 columns] with row pitch r_pitch_elems.
+extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int F, int d,
+                               const int* offsets, const uint32_t* ent_meta, const float* ent_val,
+                               const float* grad_out, float alpha, float* out,
+                               cudaStream_t stream) {
+  if (!r_bf16 || !offsets || !ent_meta || !ent_val || !out) return kBadArg;
+  if (B <= 0 || F <= 0 || d <= 0) return kBadArg;
+  const int nb_total = ceil_div(d, 64);
+  if (r_pitch_elems < nb_total * 64 || (r_pitch_elems % 8) != 0) return kBadArg;
+  const int n_chunks = ceil_div(B, kWgRows), n_ft = ceil_div(F, kWgFeat);
+  const int n_nt = ceil_div(nb_total, kWgMaxNB);
+  const int nb_tile = ceil_div(nb_total, n_nt);
+
+  auto fn = wg_encode_fn();
+  if (!fn) return kNoDriver;
+  CUtensorMap tm;
+  // [B rows, nb_total*64 columns] bf16, row pitch r_pitch_elems; box = 64 rows x 64 columns
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(nb_total) * 64, static_cast<cuuint64_t>(B)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(r_pitch_elems) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kWgRows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(r_bf16), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return static_cast<int>(1000 + cr);
+
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int ksplit = sms / (n_ft * n_nt);
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > n_chunks) ksplit = n_chunks;
+  const int stage_bytes = kWgATile + nb_tile * kWgRBlock;
+  const int grid = n_ft * n_nt * ksplit;
+  cudaError_t e;
+  if (3 * stage_bytes + 1024 + 256 <= 227 * 1024) {
+    const int smem = 3 * stage_bytes + 1024 + 256;
+    e = cudaFuncSetAttribute(wgrad_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    wgrad_gemm_kernel<3><<<grid, 256, smem, stream>>>(tm, F, d, n_chunks, n_ft, n_nt, nb_tile, ksplit,
+                                                      offsets, ent_meta, ent_val, grad_out, alpha, out);
+  } else {
+    const int smem = 2 * stage_bytes + 1024 + 256;
+    if (smem > 227 * 1024) return kUnsupported;
+    e = cudaFuncSetAttribute(wgrad_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    wgrad_gemm_kernel<2><<<grid, 256, smem, stream>>>(tm, F, d, n_chunks, n_ft, n_nt, nb_tile, ksplit,
+                                                      offsets, ent_meta, ent_val, grad_out, alpha, out);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
