@@ -29,7 +29,7 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 100). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 101). */
 int wsae_abi_version(void);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
@@ -72,13 +72,15 @@ int wsae_decode_mse(const float* target, const void* w_decT, int w_is_bf16, cons
 /* ---- K3: sparse backward (autograd of sae/model.py:108-145, run at sae/training.py:184) -------
  * s = coef * (*grad_out) with coef = 2 / (B_total * d).  Accumulates (+=) into the caller-zeroed
  * gradient buffers; any of d_w_enc / d_w_decT / d_b_enc / d_b_dec / dpre_val may be NULL to skip
- * that output.  dpre_val[b,j] = [val>0] * s * (resid_b . W_decT[idx,:]).  d % 4 == 0. */
+ * that output.  dpre_val[b,j] = [val>0] * s * (resid_b . W_decT[idx,:]).  d % 4 == 0.
+ * resid_bf16 (optional) receives bf16(resid), the dense operand of the K4 dW_decT GEMM. */
 int wsae_backward_sparse(const float* resid, const float* x /*nullable if !d_w_enc*/,
                          const float* b_pre /*nullable*/, const void* w_decT, int w_is_bf16,
                          const int32_t* idx, const float* val, const float* grad_out /*nullable*/,
                          float coef, int B, int d, int F, int k, float* d_w_enc /*[F,d]*/,
                          float* d_w_decT /*[F,d]*/, float* d_b_enc /*[F]*/, float* d_b_dec /*[d]*/,
-                         float* dpre_val /*[B,k]*/, wsae_stream_t stream);
+                         float* dpre_val /*[B,k]*/, void* resid_bf16 /*nullable bf16 [B,d]*/,
+                         wsae_stream_t stream);
 /* db_pre = db_dec - db_enc . W_enc  (overwrites d_b_pre). */
 int wsae_bpre_grad(const float* d_b_dec, const float* d_b_enc, const float* w_enc, int F, int d,
                    float* d_b_pre, wsae_stream_t stream);
@@ -87,11 +89,25 @@ int wsae_input_grad(const float* resid, const float* w_enc, const int32_t* idx,
                     const float* dpre_val, const float* grad_out, float coef, int B, int d, int F,
                     int k, int subtract_g, float* dx, wsae_stream_t stream);
 
-/* ---- K4: tensor-core weight gradients (autograd `mm`s of sae/model.py:111,129) ----------------
- * dW[F,d] += P^T . R, with P the k-sparse [B,F] matrix given as (idx, pval)[B,k] and R a dense
- * bf16 [B,d] matrix; tcgen05 GEMM with the sparse operand expanded to dense bf16 tiles in shared
- * memory.  Used for dW_enc (pval = dpre_val, R = bf16(x - b_pre)) and dW_decT (pval = relu(val),
- * R = bf16(s * resid)).  Requires the bucket arrays from wsae_bucket_by_tile. (see wsae_wgrad_gemm.cu) */
+/* ---- K4: tensor-core weight gradients (autograd `mm`s of sae/model.py:111,129 at training.py:184)
+ * OUT[F,d] += alpha * (*grad_out) * S^T . R, with S the k-sparse [B,F] matrix given as (idx, value)
+ * entries and R a dense bf16 [B,d] matrix (row pitch r_pitch_elems, a multiple of 8, base 16-byte
+ * aligned); tcgen05 GEMM (M = 128 features, N = d, K = batch rows) whose sparse operand is expanded
+ * to dense bf16 tiles in shared memory only.  Used for
+ *   dW_enc  : values = dpre_val,  R = bf16(x - b_pre)   (the packed activations of K0, terms = 1)
+ *   dW_decT : values = relu(val), R = bf16(resid), alpha = 2 / (B_total * d)
+ * wsae_bucket_by_tile groups the active entries (val > 0) by (128-feature tile, 64-row chunk):
+ *   offsets  int32 [n_ft * n_chunks + 1]   (cell c = ft * n_chunks + chunk owns [offsets[c], offsets[c+1]))
+ *   ent_meta uint32 [B*k]  = row_in_chunk | feature_in_tile << 8
+ *   ent_a / ent_b float [B*k] = dpre_val / val of the entry
+ * with n_chunks, n_ft from wsae_bucket_cells.  OUT is accumulated with red.global.add (split-K). */
+int wsae_bucket_cells(int B, int F, int* n_chunks, int* n_ft);
+int wsae_bucket_by_tile(const int32_t* idx, const float* val, const float* dpre, int B, int F,
+                        int k, int* offsets, uint32_t* ent_meta, float* ent_a, float* ent_b,
+                        wsae_stream_t stream);
+int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int F, int d, const int* offsets,
+                    const uint32_t* ent_meta, const float* ent_val, const float* grad_out /*nullable*/,
+                    float alpha, float* out /*[F,d]*/, wsae_stream_t stream);
 
 /* ---- K5: elementwise / reductions ------------------------------------------------------------
  * renorm: rows of W_decT /= max(||row||, eps)  (sae/model.py:91-96, F.normalize(dim=0), eps 1e-12);

@@ -61,7 +61,19 @@ _SIGNATURES = {
     ),
     "wsae_backward_sparse": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float,
-         c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+         c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p],
+        c_int,
+    ),
+    "wsae_bucket_cells": ([c_int, c_int, POINTER(c_int), POINTER(c_int)], c_int),
+    "wsae_bucket_by_tile": (
+        [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p],
+        c_int,
+    ),
+    "wsae_wgrad_gemm": (
+        [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+         c_void_p, c_void_p],
         c_int,
     ),
     "wsae_bpre_grad": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),

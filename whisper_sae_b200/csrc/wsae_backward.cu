@@ -36,7 +36,7 @@ backward_sparse_kernel(const float* __restrict__ resid, const float* __restrict_
                        const float* __restrict__ grad_out, float coef, int B, int d, int F, int k,
                        float* __restrict__ d_w_enc, float* __restrict__ d_w_decT,
                        float* __restrict__ d_b_enc, float* __restrict__ d_b_dec,
-                       float* __restrict__ dpre_val) {
+                       float* __restrict__ dpre_val, __nv_bfloat16* __restrict__ resid_bf16) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -63,6 +63,14 @@ backward_sparse_kernel(const float* __restrict__ resid, const float* __restrict_
       if (col < d) {
         const float4 r = *reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * d + col);
         g[c] = make_float4(s * r.x, s * r.y, s * r.z, s * r.w);
+        if (resid_bf16 != nullptr) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(r.z, r.w);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&lo);
+          o.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(resid_bf16 + static_cast<size_t>(row) * d + col) = o;
+        }
         gsum[c].x += g[c].x; gsum[c].y += g[c].y; gsum[c].z += g[c].z; gsum[c].w += g[c].w;
         if (d_w_enc != nullptr) {
           const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d + col);
@@ -200,7 +208,8 @@ template <typename WT>
 static int launch_backward(const float* resid, const float* x, const float* b_pre, const void* w,
                            const int32_t* idx, const float* val, const float* grad_out, float coef,
                            int B, int d, int F, int k, float* d_w_enc, float* d_w_decT,
-                           float* d_b_enc, float* d_b_dec, float* dpre_val, cudaStream_t stream) {
+                           float* d_b_enc, float* d_b_dec, float* dpre_val, void* resid_bf16,
+                           cudaStream_t stream) {
   if (d % 4 != 0 || d > 128 * 16) return kUnsupported;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -214,7 +223,7 @@ static int launch_backward(const float* resid, const float* x, const float* b_pr
 #define WSAE_BWD_CASE(NVV)                                                                       \
   backward_sparse_kernel<WT, NVV><<<blocks, threads, smem, stream>>>(                            \
       resid, x, b_pre, wt, idx, val, grad_out, coef, B, d, F, k, d_w_enc, d_w_decT, d_b_enc,      \
-      d_b_dec, dpre_val)
+      d_b_dec, dpre_val, static_cast<__nv_bfloat16*>(resid_bf16))
   const int nv = ceil_div(d, 128);
   if (nv <= 1) WSAE_BWD_CASE(1);
   else if (nv <= 2) WSAE_BWD_CASE(2);
@@ -238,16 +247,16 @@ extern "C" int wsae_backward_sparse(const float* resid, const float* x, const fl
                                     const float* val, const float* grad_out, float coef, int B,
                                     int d, int F, int k, float* d_w_enc, float* d_w_decT,
                                     float* d_b_enc, float* d_b_dec, float* dpre_val,
-                                    cudaStream_t stream) {
+                                    void* resid_bf16, cudaStream_t stream) {
   if (!resid || !w_decT || !idx || !val) return kBadArg;
   if (d_w_enc != nullptr && x == nullptr) return kBadArg;
   if (B <= 0 || d <= 0 || F <= 0 || k <= 0) return kBadArg;
   if (w_is_bf16)
     return launch_backward<__nv_bfloat16>(resid, x, b_pre, w_decT, idx, val, grad_out, coef, B, d,
                                           F, k, d_w_enc, d_w_decT, d_b_enc, d_b_dec, dpre_val,
-                                          stream);
+                                          resid_bf16, stream);
   return launch_backward<float>(resid, x, b_pre, w_decT, idx, val, grad_out, coef, B, d, F, k,
-                                d_w_enc, d_w_decT, d_b_enc, d_b_dec, dpre_val, stream);
+                                d_w_enc, d_w_decT, d_b_enc, d_b_dec, dpre_val, resid_bf16, stream);
 }
 
 extern "C" int wsae_bpre_grad(const float* d_b_dec, const float* d_b_enc, const float* w_enc,

@@ -256,11 +256,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
     for (int c = 0; c < nchunk; ++c) {
       mbar_wait(&empty[stage], phase ^ 1u);
       uint8_t* a_tile = smem + stage * stage_bytes;
-      // zero 16 KB: thread t clears row t (128 B)
-      uint4* rowp = reinterpret_cast<uint4*>(a_tile + t * 128);
+      // zero 16 KB: consecutive threads clear consecutive 16-byte words (conflict-free)
+      uint4* tile4 = reinterpret_cast<uint4*>(a_tile);
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) rowp[i] = z;
+      for (int i = 0; i < 8; ++i) tile4[i * 128 + t] = z;
       named_bar_sync(1, 128);
       const size_t cell = static_cast<size_t>(ft) * n_chunks + (c0 + c);
       const int e0 = offsets[cell], e1 = offsets[cell + 1];
@@ -362,7 +362,8 @@ extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int
   if (!r_bf16 || !offsets || !ent_meta || !ent_val || !out) return kBadArg;
   if (B <= 0 || F <= 0 || d <= 0) return kBadArg;
   const int nb_total = ceil_div(d, 64);
-  if (r_pitch_elems < nb_total * 64 || (r_pitch_elems % 8) != 0) return kBadArg;
+  if (r_pitch_elems < d || (r_pitch_elems % 8) != 0) return kBadArg;
+  if ((reinterpret_cast<uintptr_t>(r_bf16) & 15u) != 0) return kBadArg;
   const int n_chunks = ceil_div(B, kWgRows), n_ft = ceil_div(F, kWgFeat);
   const int n_nt = ceil_div(nb_total, kWgMaxNB);
   const int nb_tile = ceil_div(nb_total, n_nt);
@@ -370,8 +371,9 @@ extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int
   auto fn = wg_encode_fn();
   if (!fn) return kNoDriver;
   CUtensorMap tm;
-  // [B rows, nb_total*64 columns] bf16, row pitch r_pitch_elems; box = 64 rows x 64 columns
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(nb_total) * 64, static_cast<cuuint64_t>(B)};
+  // [B rows, d columns] bf16, row pitch r_pitch_elems; box = 64 rows x 64 columns; columns >= d and
+  // rows >= B of a box are zero-filled by TMA
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(B)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(r_pitch_elems) * 2};
   cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kWgRows)};
   cuuint32_t estr[2] = {1, 1};

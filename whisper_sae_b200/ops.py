@@ -205,15 +205,66 @@ def decode_mse(target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: Tensor | No
 def backward_sparse(resid: Tensor, x: Tensor | None, b_pre: Tensor | None, w_decT: Tensor,
                     idx: Tensor, val: Tensor, grad_out: Tensor | None, coef: float, *,
                     d_w_enc: Tensor | None, d_w_decT: Tensor | None, d_b_enc: Tensor | None,
-                    d_b_dec: Tensor | None, dpre_val: Tensor | None) -> None:
-    """K3 (scatter form). Accumulates into the provided (pre-zeroed) gradient buffers."""
+                    d_b_dec: Tensor | None, dpre_val: Tensor | None,
+                    resid_bf16: Tensor | None = None) -> None:
+    """K3. Accumulates into the provided (pre-zeroed) gradient buffers; ``d_w_enc``/``d_w_decT`` =
+    None skips the weight-gradient scatters (the tensor-core K4 path computes them instead)."""
     _need_cuda(resid, x, w_decT, idx, val, grad_out)
     F, d = w_decT.shape
     B, k = idx.shape
     if d % 4 != 0:
         raise RuntimeError("input_dim must be a multiple of 4 for the sparse backward kernels")
     lib = _lib.load()
-    _run("wsae_backward_sparse", lib.wsae_backward_sparse, _ptr(resid), _ptr(x), _ptr(b_pre), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(d_w_enc), _ptr(d_w_decT), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _stream())
+    _run("wsae_backward_sparse", lib.wsae_backward_sparse, _ptr(resid), _ptr(x), _ptr(b_pre), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(d_w_enc), _ptr(d_w_decT), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _ptr(resid_bf16), _stream())
+
+
+@dataclass
+class TileBuckets:
+    """Active (idx, val) entries grouped by (128-feature tile, 64-row chunk) for the K4 GEMMs."""
+
+    offsets: Tensor    # int32 [n_ft * n_chunks + 1]
+    meta: Tensor       # int32 [B*k]  row_in_chunk | feature_in_tile << 8
+    dpre: Tensor       # float32 [B*k]  dv of the entry      (values of the dW_enc GEMM)
+    act: Tensor        # float32 [B*k]  relu(val) of the entry (values of the dW_decT GEMM)
+
+
+def bucket_cells(B: int, F: int) -> tuple[int, int]:
+    lib = _lib.load()
+    nc, nf = ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.wsae_bucket_cells(B, F, ctypes.byref(nc), ctypes.byref(nf)), "wsae_bucket_cells")
+    return nc.value, nf.value
+
+
+def bucket_by_tile(idx: Tensor, val: Tensor, dpre_val: Tensor, F: int,
+                   out: TileBuckets | None = None) -> TileBuckets:
+    _need_cuda(idx, val, dpre_val)
+    B, k = idx.shape
+    n_chunks, n_ft = bucket_cells(B, F)
+    dev = idx.device
+    if out is None:
+        out = TileBuckets(
+            torch.empty(n_chunks * n_ft + 1, dtype=torch.int32, device=dev),
+            torch.empty(B * k, dtype=torch.int32, device=dev),
+            torch.empty(B * k, dtype=torch.float32, device=dev),
+            torch.empty(B * k, dtype=torch.float32, device=dev))
+    lib = _lib.load()
+    _run("wsae_bucket_by_tile", lib.wsae_bucket_by_tile, _ptr(idx), _ptr(val), _ptr(dpre_val), B, F, k, _ptr(out.offsets), _ptr(out.meta), _ptr(out.dpre), _ptr(out.act), _stream(), launches=3)
+    return out
+
+
+def wgrad_gemm_(out: Tensor, r_bf16: Tensor, B: int, d: int, buckets: TileBuckets, values: Tensor,
+                grad_out: Tensor | None, alpha: float) -> None:
+    """K4. out[F, d] += alpha * grad_out * S^T @ r_bf16[:B, :d] (S = bucketed sparse entries of the
+    same B rows)."""
+    _need_cuda(out, r_bf16, values, grad_out)
+    _f32c(out, "out")
+    if r_bf16.dtype != torch.bfloat16 or r_bf16.dim() != 2 or r_bf16.stride(1) != 1:
+        raise RuntimeError("r_bf16 must be a row-major bfloat16 matrix")
+    F = out.shape[0]
+    if r_bf16.shape[0] < B or r_bf16.shape[1] < d:
+        raise RuntimeError("r_bf16 is smaller than [B, d]")
+    lib = _lib.load()
+    _run("wsae_wgrad_gemm", lib.wsae_wgrad_gemm, _ptr(r_bf16), r_bf16.stride(0), B, F, d, _ptr(buckets.offsets), _ptr(buckets.meta), _ptr(values), _ptr(grad_out), float(alpha), _ptr(out), _stream())
 
 
 def bpre_grad(d_b_dec: Tensor, d_b_enc: Tensor, w_enc: Tensor, out: Tensor | None = None) -> Tensor:
