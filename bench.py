@@ -215,7 +215,7 @@ def roofline(prof: dict, batch: int, d: int, F: int, k: int, peaks: dict, bf16_d
     top = max(kern, key=lambda n: kern[n]["total_ms"])
     per_launch_s = kern[top]["avg_ms"] / 1e3
     w = 2 if bf16_dec else 4
-    if top == "wsae_encode_topk":
+    if top in ("wsae_encode_topk", "wsae_wgrad_gemm"):
         work = 2.0 * batch * d * F
         peak = peaks["bf16_tflops_sustained"]
         return {"kernel": top, "bound": "tensor", "achieved": work / per_launch_s / 1e12, "peak": peak,

@@ -8,6 +8,7 @@ tensors.  CPU tensors are rejected — there is deliberately no CPU fallback.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -250,6 +251,12 @@ def bucket_by_tile(idx: Tensor, val: Tensor, dpre_val: Tensor, F: int,
     lib = _lib.load()
     _run("wsae_bucket_by_tile", lib.wsae_bucket_by_tile, _ptr(idx), _ptr(val), _ptr(dpre_val), B, F, k, _ptr(out.offsets), _ptr(out.meta), _ptr(out.dpre), _ptr(out.act), _stream(), launches=3)
     return out
+
+
+def wgrad_gemm_supported(d: int) -> bool:
+    """K4 needs 16-byte aligned bf16 rows for TMA (d % 8 == 0); WSAE_WGRAD=scatter forces K3's
+    red.global.add form (kept for the ncu comparison in DESIGN.md)."""
+    return d % 8 == 0 and os.environ.get("WSAE_WGRAD", "gemm") != "scatter"
 
 
 def wgrad_gemm_(out: Tensor, r_bf16: Tensor, B: int, d: int, buckets: TileBuckets, values: Tensor,

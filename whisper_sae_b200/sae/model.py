@@ -137,6 +137,8 @@ class _FusedTopKSAE(torch.autograd.Function):
         st.idx, st.val, st.resid, st.stats, st.w_dec_used, st.rows_total = idx, val, resid, stats, w_used, rows_total
         ctx.st = st
         ctx.same_target = same_target
+        ctx.bf16 = bf16
+        ctx.a_packed = a_packed if bf16 else None   # bf16(x - b_pre): dense operand of the dW_enc GEMM
         ctx.save_for_backward(x, b_pre, w_enc)
         return loss
 
@@ -157,9 +159,21 @@ class _FusedTopKSAE(torch.autograd.Function):
         d_b_enc = torch.zeros(F, dtype=torch.float32, device=dev)
         d_b_dec = torch.zeros(d_out, dtype=torch.float32, device=dev)
         dpre = torch.empty(st.idx.shape, dtype=torch.float32, device=dev)
-        ops.backward_sparse(st.resid, x, b_pre, st.w_dec_used, st.idx, st.val, go, coef,
-                            d_w_enc=d_w_enc, d_w_decT=d_w_decT, d_b_enc=d_b_enc, d_b_dec=d_b_dec,
-                            dpre_val=dpre)
+        if ctx.bf16 and ops.wgrad_gemm_supported(d_in) and ops.wgrad_gemm_supported(d_out):
+            resid_bf = torch.empty(st.resid.shape, dtype=torch.bfloat16, device=dev)
+            ops.backward_sparse(st.resid, None, None, st.w_dec_used, st.idx, st.val, go, coef,
+                                d_w_enc=None, d_w_decT=None, d_b_enc=d_b_enc, d_b_dec=d_b_dec,
+                                dpre_val=dpre, resid_bf16=resid_bf)
+            if d_w_enc is not None or d_w_decT is not None:
+                buckets = ops.bucket_by_tile(st.idx, st.val, dpre, F)
+                if d_w_enc is not None:      # dpre already carries coef * grad_out
+                    ops.wgrad_gemm_(d_w_enc, ctx.a_packed, B, d_in, buckets, buckets.dpre, None, 1.0)
+                if d_w_decT is not None:
+                    ops.wgrad_gemm_(d_w_decT, resid_bf, B, d_out, buckets, buckets.act, go, coef)
+        else:
+            ops.backward_sparse(st.resid, x, b_pre, st.w_dec_used, st.idx, st.val, go, coef,
+                                d_w_enc=d_w_enc, d_w_decT=d_w_decT, d_b_enc=d_b_enc, d_b_dec=d_b_dec,
+                                dpre_val=dpre)
         d_b_pre = None
         if b_pre is not None and needs[5]:
             if ctx.same_target:

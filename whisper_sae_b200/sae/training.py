@@ -133,10 +133,20 @@ class _GraphedStep:
         for g in self.grads:
             g.zero_()
         dpre = torch.empty((B, k), dtype=torch.float32, device=x.device)
-        ops.backward_sparse(resid, x, m.b_pre.data, w_used, idx, val, self.one,
-                            2.0 / (float(rows_total) * d), d_w_enc=self.g_w_enc,
-                            d_w_decT=self.g_w_decT, d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec,
-                            dpre_val=dpre)
+        coef = 2.0 / (float(rows_total) * d)
+        if self.bf16 and ops.wgrad_gemm_supported(d):
+            # weight gradients on the tensor cores (K4); K3 only produces dv and the bias sums
+            resid_bf = torch.empty((B, d), dtype=torch.bfloat16, device=x.device)
+            ops.backward_sparse(resid, None, None, w_used, idx, val, self.one, coef, d_w_enc=None,
+                                d_w_decT=None, d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec,
+                                dpre_val=dpre, resid_bf16=resid_bf)
+            buckets = ops.bucket_by_tile(idx, val, dpre, F)
+            ops.wgrad_gemm_(self.g_w_enc, a_packed, B, d, buckets, buckets.dpre, None, 1.0)
+            ops.wgrad_gemm_(self.g_w_decT, resid_bf, B, d, buckets, buckets.act, self.one, coef)
+        else:
+            ops.backward_sparse(resid, x, m.b_pre.data, w_used, idx, val, self.one, coef,
+                                d_w_enc=self.g_w_enc, d_w_decT=self.g_w_decT, d_b_enc=self.g_b_enc,
+                                d_b_dec=self.g_b_dec, dpre_val=dpre)
         ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
         self.sumsq.zero_()
         for g in self.grads:
