@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""K1 micro-benchmark: time wsae_encode_topk alone (CUDA events, L2-cold rotation of inputs).
+
+    python tools/bench_k1.py [--d 384 --F 3072 --k 32 --batches 16384,65536] [--modes 0,1,2]
+
+modes (experiments, wsae_debug_encode_mode): 0 = product kernel, 1 = GEMM pipeline only (epilogue
+releases the accumulators unread), 2 = scan without compaction (results invalid).
+"""
+import argparse
+import ctypes
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from whisper_sae_b200 import _lib, ops  # noqa: E402
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--d", type=int, default=384)
+    ap.add_argument("--F", type=int, default=3072)
+    ap.add_argument("--k", type=int, default=32)
+    ap.add_argument("--batches", default="16384,65536")
+    ap.add_argument("--modes", default="0,1,2")
+    ap.add_argument("--iters", type=int, default=20)
+    args = ap.parse_args()
+    lib = _lib.load()
+    lib.wsae_debug_encode_mode.argtypes = [ctypes.c_int]
+    dev = "cuda"
+    torch.manual_seed(0)
+    w = torch.randn(args.F, args.d, device=dev) / args.d ** 0.5
+    b = torch.zeros(args.F, device=dev)
+    wp = ops.pack_encoder(w, b, 1)
+    for B in [int(s) for s in args.batches.split(",")]:
+        nrot = max(2, int(256e6 // (B * args.d * 2)) + 1)
+        xs = [ops.pack_activations(torch.randn(B, args.d, device=dev), None, 1) for _ in range(nrot)]
+        for mode in [int(s) for s in args.modes.split(",")]:
+            lib.wsae_debug_encode_mode(mode)
+            for i in range(3):
+                ops.encode_topk(xs[i % nrot], wp, B, args.F, args.d, 1, args.k)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for i in range(args.iters):
+                ops.encode_topk(xs[i % nrot], wp, B, args.F, args.d, 1, args.k)
+            t1.record()
+            torch.cuda.synchronize()
+            ms = t0.elapsed_time(t1) / args.iters
+            tf = 2.0 * B * args.d * args.F / ms / 1e9
+            print(f"B={B} d={args.d} F={args.F} k={args.k} mode={mode}: {ms * 1e3:8.1f} us  "
+                  f"{tf:7.1f} TFLOP/s (algorithmic)  {B / ms / 1e3:8.2f} Mrows/s", flush=True)
+        lib.wsae_debug_encode_mode(0)
+        del xs
+
+
+if __name__ == "__main__":
+    main()

@@ -48,33 +48,121 @@ struct EncodeSmem {
   static constexpr int kTotal = kPipeBytes + kCandBytes + kBarBytes + 1024;  // +1024 align slack
 };
 
-// Thread-private candidate list: slot s of row r lives at base[s * 128 + r].
-// Raise tau so that at most k + slack candidates (exactly k when slack == 0) survive, and
-// compact the list in place.  Warp-synchronous: every lane of the warp must call it.
+// Thread-private candidate list: slot s of row r lives at base[s * 128 + r] (values), with the
+// feature indices CAP * 512 bytes further on.  `wbase` is the shared-space byte address of the
+// thread's slot 0, `waddr` the cursor (address of the first free slot).
 //
-// The candidates are pulled into registers once; the k-th largest is then bracketed by a
-// bisection over the order-preserving integer image of the floats (so it terminates on ties and
-// needs no assumptions about the value distribution), while every comparison is done in float
-// space with 4 independent counters (the counting loop is the hot spot: FSET + FADD per element,
-// no serial predicate chain).  All comparisons use float semantics, so -0.0 == +0.0 throughout.
+// topk_compact raises tau so that at most k + slack candidates (exactly k when slack == 0) survive
+// and compacts the list in place, preserving order (ascending feature index).  Warp-synchronous:
+// every lane of the warp must call it.
+//
+// The candidate values are pulled into registers once.  The k-th largest is bracketed by a
+// bisection over the order-preserving integer image of the floats (it terminates on ties and
+// needs no assumption about the value distribution); every comparison is done in float space with
+// four independent counters (FSET + FADD per element).  The survivors are then re-appended with
+// the same branch-free predicated stores as the scan.  -0.0 == +0.0 throughout (float compares).
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int CAP, bool TIES>
+__device__ __forceinline__ uint32_t compact_move(const float (&v)[CAP], uint32_t wbase, float thrf,
+                                                 int tie_left) {
+  uint32_t w = wbase;
+#pragma unroll
+  for (int s = 0; s < CAP; s += 4) {
+    uint32_t wn;
+    if (!TIES) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p0, p1, p2, p3;\n\t"
+          ".reg .u32 a1, a2, a3, t0, t1, t2, t3, i0, i1, i2, i3;\n\t"
+          "setp.gt.f32 p0, %3, %7;\n\t"
+          "setp.gt.f32 p1, %4, %7;\n\t"
+          "setp.gt.f32 p2, %5, %7;\n\t"
+          "setp.gt.f32 p3, %6, %7;\n\t"
+          "@p0 ld.shared.u32 i0, [%2+%8];\n\t"
+          "@p1 ld.shared.u32 i1, [%2+%9];\n\t"
+          "@p2 ld.shared.u32 i2, [%2+%10];\n\t"
+          "@p3 ld.shared.u32 i3, [%2+%11];\n\t"
+          "selp.u32 t0, %13, 0, p0;\n\t"
+          "selp.u32 t1, %13, 0, p1;\n\t"
+          "selp.u32 t2, %13, 0, p2;\n\t"
+          "selp.u32 t3, %13, 0, p3;\n\t"
+          "add.u32 a1, %1, t0;\n\t"
+          "add.u32 a2, a1, t1;\n\t"
+          "add.u32 a3, a2, t2;\n\t"
+          "add.u32 %0, a3, t3;\n\t"
+          "@p0 st.shared.f32 [%1], %3;\n\t"
+          "@p0 st.shared.u32 [%1+%12], i0;\n\t"
+          "@p1 st.shared.f32 [a1], %4;\n\t"
+          "@p1 st.shared.u32 [a1+%12], i1;\n\t"
+          "@p2 st.shared.f32 [a2], %5;\n\t"
+          "@p2 st.shared.u32 [a2+%12], i2;\n\t"
+          "@p3 st.shared.f32 [a3], %6;\n\t"
+          "@p3 st.shared.u32 [a3+%12], i3;\n\t"
+          "}\n"
+          : "=r"(wn)
+          : "r"(w), "r"(wbase), "f"(v[s]), "f"(v[s + 1]), "f"(v[s + 2]), "f"(v[s + 3]), "f"(thrf),
+            "n"(CAP * kBM * 4 + 0 * kBM * 4), "n"(CAP * kBM * 4 + 1 * kBM * 4),
+            "n"(CAP * kBM * 4 + 2 * kBM * 4), "n"(CAP * kBM * 4 + 3 * kBM * 4),
+            "n"(CAP * kBM * 4), "n"(kBM * 4)
+          : "memory");
+      // the four index loads above address slots s .. s+3: fold the slot offset into the base
+      wbase += 4 * kBM * 4;
+    } else {
+      wn = w;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float x = v[s + u];
+        const bool tie = (x == thrf) && tie_left > 0;
+        tie_left -= tie ? 1 : 0;
+        if (x > thrf || tie) {
+          const uint32_t src = wbase + u * (kBM * 4) + CAP * kBM * 4;
+          uint32_t ix;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ix) : "r"(src) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.u32 [%0+%3], %2;" ::"r"(wn), "f"(x),
+                       "r"(ix), "n"(CAP * kBM * 4)
+                       : "memory");
+          wn += kBM * 4;
+        }
+      }
+      wbase += 4 * kBM * 4;
+    }
+    w = wn;
+  }
+  return w;
+}
+
 template <int CAP>
-__device__ __forceinline__ void topk_compact(float* cv, uint32_t* ci, int& cnt, float& tau, int k,
-                                             int slack) {
+__device__ __noinline__ void topk_compact(uint32_t wbase, uint32_t& waddr, float& tau, int k,
+                                          int slack) {
+  static_assert(CAP % 4 == 0, "CAP must be a multiple of 4");
   const float ninf = __uint_as_float(0xff800000u);
   const float pinf = __uint_as_float(0x7f800000u);
+  const uint32_t used = waddr - wbase;          // bytes: cnt * 512
+  const int cnt = static_cast<int>(used / (kBM * 4));
   float v[CAP];
-  float vmax = ninf, vmin = pinf;
+  float vmax = ninf;
 #pragma unroll
   for (int s = 0; s < CAP; ++s) {
-    const bool valid = s < cnt;
-    const float x = valid ? cv[s * kBM] : ninf;
-    v[s] = x;
-    vmax = fmaxf(vmax, x);
-    vmin = fminf(vmin, valid ? x : pinf);
+    const float x = lds_f32(wbase + s * (kBM * 4));
+    v[s] = (static_cast<uint32_t>(s * (kBM * 4)) < used) ? x : ninf;
+    vmax = fmaxf(vmax, v[s]);
   }
   const bool keep_all = cnt <= k + slack;   // nothing to drop for this lane (it still loops along)
   // invariants (float semantics): count(v > f(lo)) >= k,  count(v > f(hi)) < k
-  uint32_t lo = f2key(vmin) - 1u;           // below every candidate: count == cnt
+  uint32_t lo;
+  if (tau == ninf) {                        // first compaction of a work item (warp-uniform)
+    float vmin = pinf;
+#pragma unroll
+    for (int s = 0; s < CAP; ++s) vmin = fminf(vmin, (v[s] == ninf) ? pinf : v[s]);
+    lo = f2key(vmin) - 1u;                  // below every candidate: count == cnt
+  } else {
+    lo = f2key(tau);                        // every candidate is > tau: count == cnt
+  }
   uint32_t hi = f2key(vmax);                // count == 0
   int c_lo = cnt;
   bool done = keep_all;
@@ -92,9 +180,9 @@ __device__ __forceinline__ void topk_compact(float* cv, uint32_t* ci, int& cnt, 
 #pragma unroll
     for (int s = 0; s < CAP; s += 4) {
       c0 += (v[s] > midf) ? 1.f : 0.f;
-      if (s + 1 < CAP) c1 += (v[s + 1] > midf) ? 1.f : 0.f;
-      if (s + 2 < CAP) c2 += (v[s + 2] > midf) ? 1.f : 0.f;
-      if (s + 3 < CAP) c3 += (v[s + 3] > midf) ? 1.f : 0.f;
+      c1 += (v[s + 1] > midf) ? 1.f : 0.f;
+      c2 += (v[s + 2] > midf) ? 1.f : 0.f;
+      c3 += (v[s + 3] > midf) ? 1.f : 0.f;
     }
     const int c = static_cast<int>((c0 + c1) + (c2 + c3));
     if (active) {
@@ -109,36 +197,23 @@ __device__ __forceinline__ void topk_compact(float* cv, uint32_t* ci, int& cnt, 
   }
   // done: keep v > f(lo).  otherwise hi == lo + 1: the values equal to f(hi) tie across the k-th
   // position; keep everything above plus the first (k - m) ties (lowest feature index first).
-  const float thrf = key2f(done ? lo : hi);
-  int tie_left = 0;
-  if (!done) {
-    float m0 = 0.f, m1 = 0.f;
+  const bool ties = !done;
+  const float thrf = keep_all ? ninf : key2f(done ? lo : hi);
+  uint32_t wnew;
+  if (!__any_sync(0xffffffffu, ties)) {
+    wnew = compact_move<CAP, false>(v, wbase, thrf, 0);
+  } else {
+    int tie_left = 0;
+    if (ties) {
+      int m = 0;
 #pragma unroll
-    for (int s = 0; s < CAP; s += 2) {
-      m0 += (v[s] > thrf) ? 1.f : 0.f;
-      if (s + 1 < CAP) m1 += (v[s + 1] > thrf) ? 1.f : 0.f;
+      for (int s = 0; s < CAP; ++s) m += (v[s] > thrf) ? 1 : 0;
+      tie_left = k - m;
     }
-    tie_left = k - static_cast<int>(m0 + m1);
+    wnew = compact_move<CAP, true>(v, wbase, thrf, tie_left);
   }
   if (!keep_all) {
-    int w = 0;
-#pragma unroll
-    for (int s = 0; s < CAP; ++s) {
-      const float x = v[s];
-      bool keep = x > thrf;
-      if (!done && x == thrf && tie_left > 0) {
-        keep = true;
-        --tie_left;
-      }
-      if (keep) {
-        if (w != s) {
-          cv[w * kBM] = x;
-          ci[w * kBM] = ci[s * kBM];
-        }
-        ++w;
-      }
-    }
-    cnt = w;
+    waddr = wnew;
     if (c_lo >= k) tau = thrf;
   }
 }
@@ -148,7 +223,7 @@ __global__ void __launch_bounds__(256, 1)
 encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_w, int B, int F, int k, int ksteps,
                    int num_m_blocks, int num_n_tiles, int nsplit, int tiles_per_split,
-                   float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+                   float* __restrict__ out_val, int32_t* __restrict__ out_idx, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles, computed as an OFFSET so that the pointers keep
   // their shared address space (a uintptr_t round-trip would demote every access to generic LD/ST)
@@ -266,13 +341,15 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     float* cv = cand_val + row_in_blk;
     uint32_t* ci = cand_idx + row_in_blk;
     const float neg_inf = __uint_as_float(0xff800000u);
+    const uint32_t wbase = smem_u32(cv);                           // list cursor = byte address
+    const uint32_t wlimit = wbase + (CAP - kChunk) * (kBM * 4);    // a full chunk must still fit
     uint32_t tile = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int m_blk = item / nsplit;
       const int sp = item - m_blk * nsplit;
       const int t0 = sp * tiles_per_split;
       const int t1 = min(t0 + tiles_per_split, num_n_tiles);
-      int cnt = 0;
+      uint32_t waddr = wbase;
       float tau = neg_inf;
       for (int nt = t0; nt < t1; ++nt, ++tile) {
         const uint32_t as = tile & 1u;
@@ -280,56 +357,86 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const int col0 = nt * kBN;
-        const int ncols = min(kBN, F - col0);
-        const int nchunks = ceil_div(ncols, kChunk);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBN;
 
+        // Branch-free append, four values per block: a value above tau is stored at the list
+        // cursor and the cursor advances.  No warp-level branch (some lane would take it for
+        // nearly every value: ~k*ln(F/k) values pass per row), and the cursor chain is kept in
+        // fresh registers (a0 -> a1 -> a2 -> a3 -> a0') so that no address register is rewritten
+        // while a store that reads it is still in flight (the read-after-write scoreboard wait
+        // on an in-place `@p add` costs ~20 cycles per value).
+        // Zero-padded feature rows of W' carry a -3.4e38 bias (wsae_pack.cu), so they never pass.
         auto process = [&](uint32_t (&r)[16], int cbase) {
-          const int lim = F - cbase;  // columns >= F are zero padding of W'
-          if (lim >= kChunk) {
 #pragma unroll
-            for (int j = 0; j < kChunk; ++j) {
-              const float v = __uint_as_float(r[j]);
-              if (v > tau) {
-                cv[cnt * kBM] = v;
-                ci[cnt * kBM] = static_cast<uint32_t>(cbase + j);
-                ++cnt;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j) {
-              const float v = __uint_as_float(r[j]);
-              if (j < lim && v > tau) {
-                cv[cnt * kBM] = v;
-                ci[cnt * kBM] = static_cast<uint32_t>(cbase + j);
-                ++cnt;
-              }
-            }
+          for (int j = 0; j < kChunk; j += 4) {
+            uint32_t wnext;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p0, p1, p2, p3;\n\t"
+                ".reg .u32 a1, a2, a3, t0, t1, t2, t3, i1, i2, i3;\n\t"
+                "setp.gt.f32 p0, %2, %6;\n\t"
+                "setp.gt.f32 p1, %3, %6;\n\t"
+                "setp.gt.f32 p2, %4, %6;\n\t"
+                "setp.gt.f32 p3, %5, %6;\n\t"
+                "selp.u32 t0, %9, 0, p0;\n\t"
+                "selp.u32 t1, %9, 0, p1;\n\t"
+                "selp.u32 t2, %9, 0, p2;\n\t"
+                "selp.u32 t3, %9, 0, p3;\n\t"
+                "add.u32 a1, %1, t0;\n\t"
+                "add.u32 a2, a1, t1;\n\t"
+                "add.u32 a3, a2, t2;\n\t"
+                "add.u32 %0, a3, t3;\n\t"
+                "add.u32 i1, %7, 1;\n\t"
+                "add.u32 i2, %7, 2;\n\t"
+                "add.u32 i3, %7, 3;\n\t"
+                "@p0 st.shared.f32 [%1], %2;\n\t"
+                "@p0 st.shared.u32 [%1+%8], %7;\n\t"
+                "@p1 st.shared.f32 [a1], %3;\n\t"
+                "@p1 st.shared.u32 [a1+%8], i1;\n\t"
+                "@p2 st.shared.f32 [a2], %4;\n\t"
+                "@p2 st.shared.u32 [a2+%8], i2;\n\t"
+                "@p3 st.shared.f32 [a3], %5;\n\t"
+                "@p3 st.shared.u32 [a3+%8], i3;\n\t"
+                "}\n"
+                : "=r"(wnext)
+                : "r"(waddr), "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
+                  "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])), "f"(tau),
+                  "r"(static_cast<uint32_t>(cbase + j)), "n"(CAP * kBM * 4), "n"(kBM * 4)
+                : "memory");
+            waddr = wnext;
           }
-          if (__any_sync(0xffffffffu, cnt > CAP - kChunk)) {
-            topk_compact<CAP>(cv, ci, cnt, tau, k, kSlack);
-          }
+          if (dbg == 2) { if (waddr > wlimit) waddr = wbase; return; }
+          if (__any_sync(0xffffffffu, waddr > wlimit)) topk_compact<CAP>(wbase, waddr, tau, k, kSlack);
         };
 
+        // Every tile is scanned in full: columns >= F are padding rows of W' (never selected).
         uint32_t ra[16], rb[16];
+        if (dbg == 1) { tc_fence_before(); mbar_arrive(&tempty_bar[as]); continue; }
         tmem_ld16(taddr, ra);
-        for (int c = 0; c < nchunks; c += 2) {
+#pragma unroll 1
+        for (int c4 = 0; c4 < kBN / 64; ++c4) {
+          const uint32_t ta = taddr + c4 * 64;
+          const int cb = col0 + c4 * 64;
           tmem_ld_wait16(ra);
-          if (c + 1 < nchunks) tmem_ld16(taddr + (c + 1) * kChunk, rb);
-          process(ra, col0 + c * kChunk);
-          if (c + 1 < nchunks) {
-            tmem_ld_wait16(rb);
-            if (c + 2 < nchunks) tmem_ld16(taddr + (c + 2) * kChunk, ra);
-            process(rb, col0 + (c + 1) * kChunk);
-          }
+          tmem_ld16(ta + 16, rb);
+          process(ra, cb);
+          tmem_ld_wait16(rb);
+          tmem_ld16(ta + 32, ra);
+          process(rb, cb + 16);
+          tmem_ld_wait16(ra);
+          tmem_ld16(ta + 48, rb);
+          process(ra, cb + 32);
+          tmem_ld_wait16(rb);
+          if (c4 + 1 < kBN / 64) tmem_ld16(ta + 64, ra);
+          process(rb, cb + 48);
         }
         // accumulator stage fully read: hand it back to the MMA warp
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);
       }
       // ---- end of work item: exact select, write k (val, idx) pairs for this row/split ----
-      topk_compact<CAP>(cv, ci, cnt, tau, k, 0);
+      topk_compact<CAP>(wbase, waddr, tau, k, 0);
+      const int cnt = static_cast<int>((waddr - wbase) / (kBM * 4));
       const int row = m_blk * kBM + row_in_blk;
       if (row < B) {
         const size_t base = (static_cast<size_t>(row) * nsplit + sp) * k;
@@ -464,6 +571,8 @@ static int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint
   return r == CUDA_SUCCESS ? kOk : static_cast<int>(1000 + r);
 }
 
+static int g_encode_dbg = 0;  // experiments only (wsae_debug_encode_mode): 1 = skip epilogue, 2 = no compaction
+
 template <int CAP, int STAGES>
 static int launch_encode(const CUtensorMap& ta, const CUtensorMap& tw, int B, int F, int k,
                          int ksteps, int num_m_blocks, int num_n_tiles, int nsplit,
@@ -482,7 +591,7 @@ static int launch_encode(const CUtensorMap& ta, const CUtensorMap& tw, int B, in
   const int total = num_m_blocks * nsplit;
   const int grid = total < num_sms ? total : num_sms;
   kern<<<grid, 256, smem, stream>>>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
-                                    tiles_per_split, out_val, out_idx);
+                                    tiles_per_split, out_val, out_idx, g_encode_dbg);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -536,6 +645,8 @@ extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int 
   }
   return rc;
 }
+
+extern "C" int wsae_debug_encode_mode(int mode) { g_encode_dbg = mode; return 0; }
 
 // Number of F-splits wsae_encode_topk will actually use for a requested nsplit (so callers can
 // size part_val / part_idx = B * nsplit_eff * k entries).
