@@ -222,6 +222,8 @@ def roofline(prof: dict, batch: int, d: int, F: int, k: int, peaks: dict, bf16_d
                 "unit": "TFLOP/s", "frac": work / per_launch_s / 1e12 / peak, "traffic": None}
     if top == "wsae_decode_mse":
         nbytes = batch * (k * d * w + 2 * d * 4 + k * 8)
+    elif top == "wsae_decode_backward":   # gathered rows once + x read + bf16 residual write + idx/val/dv
+        nbytes = batch * (k * d * w + d * 4 + d * 2 + k * 12)
     elif top == "wsae_backward_sparse":
         nbytes = batch * (k * d * w + 2 * 2 * k * d * 4 + 2 * d * 4 + k * 12)
     elif top == "wsae_fused_adamw":
@@ -376,7 +378,7 @@ def main() -> None:
     if rank == 0:
         # per-kernel CUDA-event timing needs eager launches: same kernels, graph replay switched off
         tr_eager, _ = make_trainer(args.batch, dev, layer_seed=rank, use_amp=(args.precision == "bf16"),
-                                   cuda_graph=False)
+                                   cuda_graph="eager")
         for i in range(3):
             tr_eager.train_step(dev_batches[i % nb])
         prof = kernel_profile(tr_eager, dev_batches, min(args.steps, 20))

@@ -81,6 +81,22 @@ int wsae_backward_sparse(const float* resid, const float* x /*nullable if !d_w_e
                          float* d_w_decT /*[F,d]*/, float* d_b_enc /*[F]*/, float* d_b_dec /*[d]*/,
                          float* dpre_val /*[B,k]*/, void* resid_bf16 /*nullable bf16 [B,d]*/,
                          wsae_stream_t stream);
+/* ---- K23: K2 and the sparse part of K3 fused into one pass over the gathered decoder rows -------
+ * (sae/model.py:115-116,129,145,148,174-181 + the dv / bias part of its autograd).  For the train
+ * step where grad_out is known when the forward runs (loss.backward() with grad_output = 1, i.e.
+ * the CUDA-graphed SAETrainer.train_step).  One warp per activation row; the k selected decoder
+ * rows (bf16 shadow) are loaded into registers once, 128 columns at a time, and used for both the
+ * reconstruction and the k dot products (bf16 x bf16 -> fp32 FHFMA against the bf16-rounded
+ * residual, the same rounding K4 consumes).  Outputs as in wsae_decode_mse / wsae_backward_sparse
+ * (weight gradients are left to K4); resid / resid_bf16 / stats / last_activated / d_b_enc /
+ * d_b_dec / dpre_val may each be NULL.  d_b_enc and d_b_dec are accumulated (+=).  Returns
+ * WSAE_E_UNSUPPORTED for an fp32 decoder, k > 32 or d % 8 != 0: use K2 + K3 then. */
+int wsae_decode_backward(const float* target, const void* w_decT, int w_is_bf16,
+                         const float* b_dec, const float* b_pre /*nullable*/, const int32_t* idx,
+                         const float* val, const float* grad_out /*nullable*/, float coef, int B,
+                         int d, int F, int k, float* resid, void* resid_bf16, void* stats,
+                         long long* last_activated, const long long* step_count, float* d_b_enc,
+                         float* d_b_dec, float* dpre_val, wsae_stream_t stream);
 /* db_pre = db_dec - db_enc . W_enc  (overwrites d_b_pre). */
 int wsae_bpre_grad(const float* d_b_dec, const float* d_b_enc, const float* w_enc, int F, int d,
                    float* d_b_pre, wsae_stream_t stream);

@@ -105,6 +105,78 @@ def test_backward_sparse_fp32(B, d, F, k):
     close(dx, ref["dx"], "dx")
 
 
+FUSED_SHAPES = [(1, 32, 128, 4), (33, 64, 256, 8), (64, 384, 3072, 32), (257, 768, 1024, 32),
+                (40, 1280, 2048, 32), (300, 392, 512, 17)]
+
+
+def test_decode_backward_fused_rejects_fp32_decoder():
+    ops = _ops()
+    assert not ops.decode_backward_supported(384, 32, False)
+    assert not ops.decode_backward_supported(384, 64, True)
+
+
+@pytest.mark.parametrize("B,d,F,k", FUSED_SHAPES)
+@pytest.mark.parametrize("wdtype", ["bf16"])
+def test_decode_backward_fused(B, d, F, k, wdtype):
+    """K23 (one pass over the gathered decoder rows) against the oracle forward + backward.
+    The dot products use the bf16-rounded residual (the rounding K4 consumes), so dv / db_enc are
+    compared at bf16 tolerance; everything on the forward side stays at fp32 tolerance."""
+    ops = _ops()
+    state, x, fwd = _case(B, d, F, k, seed=3 * B + d)
+    if wdtype == "bf16":   # the decoder the kernel reads is the bf16 shadow: same rounding in the oracle
+        state = dict(state)
+        state["decoder.weight"] = state["decoder.weight"].to(torch.bfloat16).float()
+        fwd = O.forward(state, x, k, training=False)
+    # force a few selected values non-positive: relu-masked entries must contribute nothing
+    val = fwd.val.clone()
+    val[::3, 0] = -val[::3, 0].abs()
+    recon = (torch.relu(val).unsqueeze(-1) * state["decoder.weight"].t()[fwd.idx]).sum(1) \
+        + state["decoder.bias"] + state["b_pre"]
+    resid_ref = recon - x
+    grad_out = 0.5
+    coef = 2.0 / (B * d)
+    g = resid_ref * (coef * grad_out)
+    dv_ref = (g.unsqueeze(1) * state["decoder.weight"].t()[fwd.idx]).sum(-1) * (val > 0)
+    dbe_ref = torch.zeros(F).index_add_(0, fwd.idx.reshape(-1), dv_ref.reshape(-1))
+    dev = "cuda"
+    w_decT = state["decoder.weight"].t().contiguous()
+    w_used = _dev(w_decT.to(torch.bfloat16) if wdtype == "bf16" else w_decT)
+    stats = torch.zeros(3, dtype=torch.int64, device=dev)
+    last = torch.zeros(F, dtype=torch.int64, device=dev)
+    step = torch.tensor(41, dtype=torch.int64, device=dev)
+    resid = torch.empty(B, d, device=dev)
+    resid_bf = torch.empty(B, d, dtype=torch.bfloat16, device=dev)
+    dbe = torch.zeros(F, device=dev)
+    dbd = torch.zeros(d, device=dev)
+    dpre = torch.empty(B, k, device=dev)
+    assert ops.decode_backward_supported(d, k, wdtype == "bf16")
+    ops.decode_backward(_dev(x), w_used, _dev(state["decoder.bias"]), _dev(state["b_pre"]),
+                        _dev(fwd.idx.to(torch.int32)), _dev(val), torch.tensor(grad_out, device=dev), coef,
+                        resid=resid, resid_bf16=resid_bf, stats=stats, last_activated=last,
+                        step_count=step, d_b_enc=dbe, d_b_dec=dbd, dpre_val=dpre)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(resid.cpu(), resid_ref, rtol=1e-5, atol=2e-6)
+    assert torch.equal(resid_bf.cpu(), resid.cpu().to(torch.bfloat16))
+    raw = stats.cpu()
+    assert raw[:1].view(torch.float64).item() == pytest.approx((resid_ref.double() ** 2).sum().item(), rel=1e-6)
+    assert raw[1].item() == int((val > 0).sum())
+    want_last = torch.zeros(F, dtype=torch.int64)
+    want_last[fwd.idx[val > 0]] = 42
+    assert torch.equal(last.cpu(), want_last)
+
+    def close(a, b, name, rtol=2e-5, arel=2e-6):
+        scale = b.abs().max().item() + 1e-30
+        torch.testing.assert_close(a.cpu(), b, rtol=rtol, atol=arel * scale, msg=lambda m: f"{name}: {m}")
+
+    close(dpre, dv_ref, "dpre", rtol=2e-2, arel=4e-3)
+    close(dbe, dbe_ref, "db_enc", rtol=2e-2, arel=4e-3)
+    close(dbd, g.sum(0), "db_dec")
+    # and exactly the value the bf16-rounded residual implies (fp32 accumulation of bf16 products)
+    g_bf = resid_bf.float().cpu() * (coef * grad_out)
+    dv_bf = (g_bf.unsqueeze(1) * state["decoder.weight"].t()[fwd.idx]).sum(-1) * (val > 0)
+    close(dpre, dv_bf, "dpre vs bf16-residual reference", rtol=1e-4, arel=1e-5)
+
+
 def test_renorm_and_shadow():
     ops = _ops()
     torch.manual_seed(0)

@@ -65,6 +65,12 @@ _SIGNATURES = {
          c_void_p],
         c_int,
     ),
+    "wsae_decode_backward": (
+        [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+         c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p],
+        c_int,
+    ),
     "wsae_bucket_cells": ([c_int, c_int, POINTER(c_int), POINTER(c_int)], c_int),
     "wsae_bucket_by_tile": (
         [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,0 +1,233 @@
+// wsae_decode_backward.cu — K23: the k-sparse decode (K2) and the sparse part of the backward (K3)
+// fused into ONE pass over the gathered decoder rows, for the train step where grad_output is known
+// when the forward runs (the CUDA-graphed SAETrainer step: loss.backward() with grad_output = 1).
+//
+// Replaces (reference, /root/reference/src/whisper_sae/sae/model.py, and its autograd at
+// sae/training.py:184):
+//   :115-116,129  recon = sum_j relu(v_j) * W_dec[:, i_j] + b_dec + b_pre
+//   :145,148      mse numerator, l0 count                         -> stats
+//   :174-181      last_activated[fired] = step_count + 1
+//   backward      g = s * (recon - x);  db_dec = sum_b g;  dv_j = [v_j > 0] * (g . W_dec[:, i_j]);
+//                 db_enc[i_j] += dv_j      (the two weight gradients are K4's tensor-core GEMMs,
+//                                           fed with bf16(recon - x) and dv from here)
+//
+// Why fused: decode and backward need the same k decoder rows per activation row (k * d * 2 bytes =
+// 24 KB at d = 384 with the bf16 shadow).  Unfused they are fetched from L2 twice, each time inside a
+// dependent loop that exposes the load latency.  Here one warp owns one activation row and walks it
+// in slices of 128 columns: lane l owns 4 consecutive columns, so the slice of one decoder row is one
+// coalesced 8-byte load per lane.  The 32 row slices are loaded into REGISTERS with all 32 loads in
+// flight at once, used for the reconstruction (fp32 FMA), and - still in registers - for the 32
+// partial dot products with the residual (FHFMA.BF16: bf16 x bf16 products, fp32 accumulate, no
+// conversion instructions; the residual enters in the same bf16 rounding that K4 consumes).
+// Every decoder byte is read from L2 exactly once.  (A first version staged the rows in shared
+// memory with one cp.async.bulk per row: 32 bulk copies of 768 B per activation row saturate the
+// TMA unit at ~45 ns per copy - 4x slower than this form; profiles/r1_k23_notes.md.)
+#include "wsae_common.cuh"
+
+namespace wsae {
+
+struct FusedStats {
+  double sse;
+  unsigned long long l0_count;
+};
+
+// d += bf16(a.lo) * bf16(b.lo)  /  d += bf16(a.hi) * bf16(b.hi)   (fp32 accumulate, SASS FHFMA.BF16)
+__device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uint32_t b) {
+  asm("{\n\t"
+      ".reg .b16 a0, a1, b0, b1;\n\t"
+      "mov.b32 {a0, a1}, %2;\n\t"
+      "mov.b32 {b0, b1}, %3;\n\t"
+      "fma.rn.f32.bf16 %0, a0, b0, %0;\n\t"
+      "fma.rn.f32.bf16 %1, a1, b1, %1;\n\t"
+      "}\n"
+      : "+f"(acc0), "+f"(acc1)
+      : "r"(a), "r"(b));
+}
+
+constexpr int kFusedWarps = 4;
+
+// bf16 decoder shadow only.  k <= 32, d % 8 == 0.
+__global__ void __launch_bounds__(kFusedWarps * 32, 3)
+decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __restrict__ w_decT,
+                       const float* __restrict__ b_dec, const float* __restrict__ b_pre,
+                       const int32_t* __restrict__ idx, const float* __restrict__ val,
+                       const float* __restrict__ grad_out, float coef, int B, int d, int F, int k,
+                       float* __restrict__ resid, __nv_bfloat16* __restrict__ resid_bf16,
+                       FusedStats* __restrict__ stats, long long* __restrict__ last_activated,
+                       const long long* __restrict__ step_count, float* __restrict__ d_b_enc,
+                       float* __restrict__ d_b_dec, float* __restrict__ dpre_val) {
+  extern __shared__ __align__(16) float fsm[];   // [dp] bias (b_dec + b_pre), then one [dp] db_dec accumulator per warp
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int dp = round_up(d, 128);
+  float* s_bias = fsm;
+  float* s_g = fsm + dp + warp * dp;       // warp-private: plain read-modify-write, no atomics
+  for (int i = threadIdx.x; i < dp; i += blockDim.x) {
+    float b = 0.f;
+    if (i < d) b = b_dec[i] + (b_pre != nullptr ? b_pre[i] : 0.f);
+    s_bias[i] = b;
+#pragma unroll
+    for (int w = 0; w < kFusedWarps; ++w) fsm[dp + w * dp + i] = 0.f;
+  }
+  __syncthreads();
+
+  const float s = coef * (grad_out != nullptr ? *grad_out : 1.f);
+  const long long stamp = (last_activated != nullptr && step_count != nullptr) ? (*step_count + 1) : 0;
+  const int warp_global = blockIdx.x * kFusedWarps + warp;
+  const int warp_stride = gridDim.x * kFusedWarps;
+  const uint2* wbase = reinterpret_cast<const uint2*>(w_decT);   // 4 bf16 per element
+  const int d4 = d >> 2;
+
+  float sse_local = 0.f;
+  unsigned int l0_local = 0;
+
+  for (int row = warp_global; row < B; row += warp_stride) {
+    int32_t my_i = -1;
+    float my_v = 0.f;
+    if (lane < k) {
+      my_i = idx[static_cast<size_t>(row) * k + lane];
+      my_v = val[static_cast<size_t>(row) * k + lane];
+    }
+    const bool fired = (my_i >= 0) && (my_i < F) && (my_v > 0.f);
+    if (fired && last_activated != nullptr) last_activated[my_i] = stamp;
+    if (!fired) my_v = 0.f;                         // relu; also neutralises invalid entries
+    const uint32_t mask = __ballot_sync(0xffffffffu, fired);
+    l0_local += (lane == 0) ? __popc(mask) : 0;
+    // element offset (in uint2 units) of each selected decoder row; inactive entries read row 0
+    // with weight 0, so every lane issues the same, fully unrolled load sequence
+    const int my_off = fired ? my_i * d4 : 0;
+
+    float part[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) part[j] = 0.f;
+
+    for (int c0 = 0; c0 < d; c0 += 128) {
+      const int col = c0 + lane * 4;
+      const bool ok = col < d;
+      // ---- gather: 32 independent 8-byte loads per lane, all in flight together ----
+      uint2 w[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int off = __shfl_sync(0xffffffffu, my_off, j);
+        w[j] = make_uint2(0u, 0u);
+        if (ok) w[j] = __ldg(wbase + off + (col >> 2));
+      }
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) t = __ldg(reinterpret_cast<const float4*>(target + static_cast<size_t>(row) * d + col));
+      float4 acc = *reinterpret_cast<const float4*>(s_bias + col);
+      // ---- reconstruction of this slice (fp32) ----
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float h = __shfl_sync(0xffffffffu, my_v, j);
+        const float4 wf = bf16x4_to_float4(w[j]);
+        acc.x = fmaf(h, wf.x, acc.x);
+        acc.y = fmaf(h, wf.y, acc.y);
+        acc.z = fmaf(h, wf.z, acc.z);
+        acc.w = fmaf(h, wf.w, acc.w);
+      }
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+        r.x = acc.x - t.x; r.y = acc.y - t.y; r.z = acc.z - t.z; r.w = acc.w - t.w;
+      }
+      sse_local = fmaf(r.x, r.x, sse_local);
+      sse_local = fmaf(r.y, r.y, sse_local);
+      sse_local = fmaf(r.z, r.z, sse_local);
+      sse_local = fmaf(r.w, r.w, sse_local);
+      __nv_bfloat162 rlo = __floats2bfloat162_rn(r.x, r.y);
+      __nv_bfloat162 rhi = __floats2bfloat162_rn(r.z, r.w);
+      uint2 rb;
+      rb.x = *reinterpret_cast<uint32_t*>(&rlo);
+      rb.y = *reinterpret_cast<uint32_t*>(&rhi);
+      if (ok) {
+        if (resid != nullptr) *reinterpret_cast<float4*>(resid + static_cast<size_t>(row) * d + col) = r;
+        if (resid_bf16 != nullptr)
+          *reinterpret_cast<uint2*>(resid_bf16 + static_cast<size_t>(row) * d + col) = rb;
+        // db_dec partial sums (unscaled; s is applied once at the end)
+        float4 gs = *reinterpret_cast<float4*>(s_g + col);
+        gs.x += r.x; gs.y += r.y; gs.z += r.z; gs.w += r.w;
+        *reinterpret_cast<float4*>(s_g + col) = gs;
+      }
+      // ---- partial dots bf16(r) . W_dec[i_j] over this slice ----
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float a0 = 0.f, a1 = 0.f;
+        fhfma2(a0, a1, w[j].x, rb.x);
+        fhfma2(a0, a1, w[j].y, rb.y);
+        part[j] += a0 + a1;
+      }
+    }
+    // ---- transpose-reduce: lane j ends up with the sum over lanes of part[j] ----
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = upper ? part[i] : part[i + off];
+        const float keep = upper ? part[i + off] : part[i];
+        part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    const float my_dv = fired ? s * part[0] : 0.f;
+    if (lane < k) {
+      if (dpre_val != nullptr) dpre_val[static_cast<size_t>(row) * k + lane] = my_dv;
+      if (fired && d_b_enc != nullptr) atomicAdd(d_b_enc + my_i, my_dv);
+    }
+  }
+
+  // ---- block reductions: db_dec (per column), SSE (double), L0 (integer) ----
+  __shared__ float s_sse[kFusedWarps];
+  __shared__ unsigned int s_l0[kFusedWarps];
+  const float wsum = warp_sum(sse_local);
+  if (lane == 0) {
+    s_sse[warp] = wsum;
+    s_l0[warp] = l0_local;
+  }
+  __syncthreads();
+  if (d_b_dec != nullptr)
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kFusedWarps; ++w) t += fsm[dp + w * dp + i];
+      atomicAdd(d_b_dec + i, s * t);
+    }
+  if (threadIdx.x == 0 && stats != nullptr) {
+    double tsum = 0.0;
+    unsigned long long c = 0;
+    for (int w = 0; w < kFusedWarps; ++w) {
+      tsum += static_cast<double>(s_sse[w]);
+      c += s_l0[w];
+    }
+    atomicAdd(&stats->sse, tsum);
+    atomicAdd(&stats->l0_count, c);
+  }
+}
+
+}  // namespace wsae
+
+using namespace wsae;
+
+// See include/wsae.h.  Returns WSAE_E_UNSUPPORTED for shapes the fused kernel does not cover
+// (fp32 decoder, k > 32, d % 8 != 0): callers then use K2 + K3.
+extern "C" int wsae_decode_backward(const float* target, const void* w_decT, int w_is_bf16,
+                                    const float* b_dec, const float* b_pre, const int32_t* idx,
+                                    const float* val, const float* grad_out, float coef, int B,
+                                    int d, int F, int k, float* resid, void* resid_bf16,
+                                    void* stats, long long* last_activated,
+                                    const long long* step_count, float* d_b_enc, float* d_b_dec,
+                                    float* dpre_val, cudaStream_t stream) {
+  if (!target || !w_decT || !b_dec || !idx || !val) return kBadArg;
+  if (B <= 0 || d <= 0 || F <= 0 || k <= 0) return kBadArg;
+  if (!w_is_bf16 || k > 32 || d % 8 != 0 || d > 8192) return kUnsupported;
+  if (static_cast<long long>(F) * (d / 4) > 0x7fffffffLL) return kUnsupported;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int blocks = ceil_div(B, kFusedWarps);
+  if (blocks > sms * 3) blocks = sms * 3;
+  const size_t smem = (1 + kFusedWarps) * static_cast<size_t>(round_up(d, 128)) * sizeof(float);
+  decode_backward_kernel<<<blocks, kFusedWarps * 32, smem, stream>>>(
+      target, static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B,
+      d, F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
+      last_activated, step_count, d_b_enc, d_b_dec, dpre_val);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -219,6 +219,27 @@ def backward_sparse(resid: Tensor, x: Tensor | None, b_pre: Tensor | None, w_dec
     _run("wsae_backward_sparse", lib.wsae_backward_sparse, _ptr(resid), _ptr(x), _ptr(b_pre), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(d_w_enc), _ptr(d_w_decT), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _ptr(resid_bf16), _stream())
 
 
+def decode_backward_supported(d: int, k: int, bf16: bool) -> bool:
+    """Shapes covered by the fused K23 kernel (else: decode_mse + backward_sparse)."""
+    return bf16 and k <= 32 and d % 8 == 0 and os.environ.get("WSAE_FUSED_DECODE", "1") != "0"
+
+
+def decode_backward(target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: Tensor | None,
+                    idx: Tensor, val: Tensor, grad_out: Tensor | None, coef: float, *,
+                    resid: Tensor | None, resid_bf16: Tensor | None, stats: Tensor | None,
+                    last_activated: Tensor | None, step_count: Tensor | None,
+                    d_b_enc: Tensor | None, d_b_dec: Tensor | None, dpre_val: Tensor | None) -> None:
+    """K23: sparse decode + MSE + L0 + fired stamps + dv / bias gradients in one pass."""
+    _need_cuda(target, w_decT, b_dec, b_pre, idx, val, grad_out)
+    _f32c(target, "target")
+    F, d = w_decT.shape
+    B, k = idx.shape
+    if not w_decT.is_contiguous() or w_decT.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("w_decT must be contiguous [F, d] float32 or bfloat16")
+    lib = _lib.load()
+    _run("wsae_decode_backward", lib.wsae_decode_backward, _ptr(target), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16), _ptr(b_dec), _ptr(b_pre), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(resid), _ptr(resid_bf16), _ptr(stats), _ptr(last_activated), _ptr(step_count), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _stream())
+
+
 @dataclass
 class TileBuckets:
     """Active (idx, val) entries grouped by (128-feature tile, 64-row chunk) for the K4 GEMMs."""

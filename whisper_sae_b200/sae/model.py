@@ -90,11 +90,12 @@ def _fp32_terms() -> int:
 class _SparseState:
     """Per-forward sparse results shared between the autograd node and the lazy SAEOutput."""
 
-    __slots__ = ("idx", "val", "resid", "stats", "w_dec_used", "rows_total")
+    __slots__ = ("idx", "val", "resid", "stats", "w_dec_used", "rows_total", "d_out")
 
     def __init__(self):
         self.idx = self.val = self.resid = self.stats = self.w_dec_used = None
         self.rows_total = None
+        self.d_out = None
 
 
 class _FusedTopKSAE(torch.autograd.Function):
@@ -135,6 +136,7 @@ class _FusedTopKSAE(torch.autograd.Function):
         numel = float(rows_total) * float(tgt.shape[1])
         loss = (stats[:1].view(torch.float64)[0] / numel).to(torch.float32)
         st.idx, st.val, st.resid, st.stats, st.w_dec_used, st.rows_total = idx, val, resid, stats, w_used, rows_total
+        st.d_out = tgt.shape[1]
         ctx.st = st
         ctx.same_target = same_target
         ctx.bf16 = bf16

@@ -124,29 +124,42 @@ class _GraphedStep:
         w_packed = ops.pack_encoder(m.encoder.weight.data, m.encoder.bias.data, terms)
         idx, val = ops.encode_topk(a_packed, w_packed, B, F, d, terms, k)
         w_used = ops.cast_bf16(w_decT) if self.bf16 else w_decT
-        resid, _ = ops.decode_mse(x, w_used, m.decoder.bias.data, m.b_pre.data, idx, val,
-                                  stats=self.stats, last_activated=m.feature_last_activated,
-                                  step_count=m.step_count)
-        ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold, True,
-                            self.stats[2:])
         rows_total = m._global_rows or B
+        coef = 2.0 / (float(rows_total) * d)
         for g in self.grads:
             g.zero_()
         dpre = torch.empty((B, k), dtype=torch.float32, device=x.device)
-        coef = 2.0 / (float(rows_total) * d)
-        if self.bf16 and ops.wgrad_gemm_supported(d):
-            # weight gradients on the tensor cores (K4); K3 only produces dv and the bias sums
+        use_gemm = self.bf16 and ops.wgrad_gemm_supported(d)
+        if use_gemm and ops.decode_backward_supported(d, k, True):
+            # K23: decode + MSE + stamps + dv + bias gradients in one pass over the gathered rows
+            resid = None          # fp32 residual only on demand (SAEOutput.reconstructed, resampling)
             resid_bf = torch.empty((B, d), dtype=torch.bfloat16, device=x.device)
-            ops.backward_sparse(resid, None, None, w_used, idx, val, self.one, coef, d_w_enc=None,
-                                d_w_decT=None, d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec,
-                                dpre_val=dpre, resid_bf16=resid_bf)
+            ops.decode_backward(x, w_used, m.decoder.bias.data, m.b_pre.data, idx, val, self.one, coef,
+                                resid=None, resid_bf16=resid_bf, stats=self.stats,
+                                last_activated=m.feature_last_activated, step_count=m.step_count,
+                                d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre)
+            ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold,
+                                True, self.stats[2:])
+        else:
+            resid, _ = ops.decode_mse(x, w_used, m.decoder.bias.data, m.b_pre.data, idx, val,
+                                      stats=self.stats, last_activated=m.feature_last_activated,
+                                      step_count=m.step_count)
+            ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold,
+                                True, self.stats[2:])
+            if use_gemm:
+                resid_bf = torch.empty((B, d), dtype=torch.bfloat16, device=x.device)
+                ops.backward_sparse(resid, None, None, w_used, idx, val, self.one, coef, d_w_enc=None,
+                                    d_w_decT=None, d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec,
+                                    dpre_val=dpre, resid_bf16=resid_bf)
+            else:
+                ops.backward_sparse(resid, x, m.b_pre.data, w_used, idx, val, self.one, coef,
+                                    d_w_enc=self.g_w_enc, d_w_decT=self.g_w_decT,
+                                    d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre)
+        if use_gemm:
+            # weight gradients on the tensor cores (K4)
             buckets = ops.bucket_by_tile(idx, val, dpre, F)
             ops.wgrad_gemm_(self.g_w_enc, a_packed, B, d, buckets, buckets.dpre, None, 1.0)
             ops.wgrad_gemm_(self.g_w_decT, resid_bf, B, d, buckets, buckets.act, self.one, coef)
-        else:
-            ops.backward_sparse(resid, x, m.b_pre.data, w_used, idx, val, self.one, coef,
-                                d_w_enc=self.g_w_enc, d_w_decT=self.g_w_decT, d_b_enc=self.g_b_enc,
-                                d_b_dec=self.g_b_dec, dpre_val=dpre)
         ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
         self.sumsq.zero_()
         for g in self.grads:
@@ -158,6 +171,7 @@ class _GraphedStep:
         ops.renorm_decoder_(w_decT, 1e-12)
         s = self.state
         s.idx, s.val, s.resid, s.stats, s.w_dec_used, s.rows_total = idx, val, resid, self.stats, w_used, rows_total
+        s.d_out = d
 
     def run(self, batch: Tensor) -> None:
         tr = self.trainer
@@ -185,7 +199,7 @@ class _GraphedStep:
             self.graph = None
             self._ptrs = key
             self.calls = 1
-        if self.calls == 1:
+        if self.calls == 1 or tr.cuda_graph == "eager":
             self._body()
         else:
             if self.graph is None:
@@ -248,7 +262,9 @@ class SAETrainer:
         self._sumsq: Tensor | None = None
         if cuda_graph is None:
             cuda_graph = os.environ.get("WSAE_CUDA_GRAPH", "1") != "0"
-        self.cuda_graph = bool(cuda_graph) and self.fused_optimizer and not self.scaler.is_enabled()
+        # "eager": same kernel sequence as the captured graph, launched one by one (per-kernel timing)
+        self.cuda_graph = cuda_graph if (cuda_graph and self.fused_optimizer
+                                         and not self.scaler.is_enabled()) else False
         self._graphs: dict[int, _GraphedStep] = {}
 
     # ------------------------------------------------------------------ resampling plumbing
@@ -378,7 +394,7 @@ class SAETrainer:
         if st is not None and st.stats is not None and (output is None or output.loss.is_cuda):
             raw = st.stats.cpu()  # the step's single device->host sync (24 bytes)
             sse = raw[:1].view(torch.float64).item()
-            d_out = st.resid.shape[1]
+            d_out = st.d_out
             loss = float(torch.tensor(sse / (float(st.rows_total) * d_out), dtype=torch.float32))
             l0 = float(torch.tensor(raw[1].item() / float(rows), dtype=torch.float32))
             hidden_dim = self.model.feature_last_activated.numel()
