@@ -11,7 +11,7 @@ configs/tiny_default.yaml (lr 1e-4, warm-up 1000, clip 1.0, AMP on => bf16 path)
 row-standardised Gaussian activations.  One "step" = one `SAETrainer.train_step`
 (pack, tcgen05 GEMM + fused TopK, sparse decode + MSE, sparse backward, clip + AdamW, decoder
 renorm, counters, stats readback).  The YAML batch (128) is launch-latency bound by construction,
-so the headline batch is `--batch` (default 16384, config-legal: TrainingConfig.batch_size >= 1);
+so the headline batch is `--batch` (default 65536, config-legal: TrainingConfig.batch_size >= 1);
 the YAML-batch number is reported next to it as `yaml_batch`.
 
 N > 1: one process per GPU, each training an independent layer's SAE (4 encoder + 4 decoder
@@ -50,27 +50,66 @@ def load_peaks() -> tuple[dict, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: an NVML polling thread (5 ms
+    cadence, so even a 30 ms region gets several samples); falls back to `nvidia-smi -lms`."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    _REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
+        self.samples: list[tuple[float, float, int]] = []
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
         self.proc = None
         self.lines: list[str] = []
 
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
+
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self._t = threading.Thread(target=self._pump, daemon=True)
-            self._t.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self._nvml = pynvml
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            rs = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((sm, mx, rs))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.005)
+
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._nvml = None
+            try:
+                fields = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                          "clocks_event_reasons.hw_thermal_slowdown,"
+                          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={fields}",
+                     "--format=csv,noheader,nounits", "-lms", "100"],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self._thread = threading.Thread(target=self._pump, daemon=True)
+                self._thread.start()
+            except OSError:
+                self.proc = None
         return self
 
     def _pump(self):
@@ -78,14 +117,27 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def __exit__(self, *exc):
+        self._stop.set()
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
 
     def summary(self) -> dict:
+        if self.samples:
+            sm = [x[0] for x in self.samples]
+            reasons = set()
+            for _, _, rs in self.samples:
+                for name, bit in self._REASONS:
+                    if rs & bit:
+                        reasons.add(name)
+            return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm),
+                    "sm_max_mhz": self.samples[0][1], "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "nvml"}
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for ln in self.lines:
@@ -101,9 +153,9 @@ class ClockSampler:
                 if flag.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def make_trainer(batch: int, device: str, layer_seed: int, use_amp: bool = True, cuda_graph=None):
@@ -320,9 +372,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
-    ap.add_argument("--resident-batches", type=int, default=8)
+    ap.add_argument("--resident-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--value-only", action="store_true",
                     help="only the HBM-resident timed leg (used under ncu; prints a reduced line)")
