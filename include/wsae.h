@@ -112,8 +112,9 @@ int wsae_input_grad(const float* resid, const float* w_enc, const int32_t* idx,
  * to dense bf16 tiles in shared memory only.  Used for
  *   dW_enc  : values = dpre_val,  R = bf16(x - b_pre)   (the packed activations of K0, terms = 1)
  *   dW_decT : values = relu(val), R = bf16(resid), alpha = 2 / (B_total * d)
- * wsae_bucket_by_tile groups the active entries (val > 0) by (128-feature tile, 64-row chunk):
- *   offsets  int32 [n_ft * n_chunks + 1]   (cell c = ft * n_chunks + chunk owns [offsets[c], offsets[c+1]))
+ * wsae_bucket_by_tile groups the active entries (val > 0) by (64-row chunk, 128-feature tile); the
+ * entries of chunk c live in its own segment [c * 64 * k, ...) of the entry arrays:
+ *   offsets  int32 [n_chunks * (n_ft + 1)]  (cell (c, ft) owns [offsets[c*(n_ft+1)+ft], offsets[c*(n_ft+1)+ft+1]))
  *   ent_meta uint32 [B*k]  = row_in_chunk | feature_in_tile << 8
  *   ent_a / ent_b float [B*k] = dpre_val / val of the entry
  * with n_chunks, n_ft from wsae_bucket_cells.  OUT is accumulated with red.global.add (split-K). */
@@ -146,6 +147,23 @@ int wsae_sumsq(const float* g, long long n, double* out, wsae_stream_t stream);
  * max_norm}; grad_sumsq (device double, nullable) = total squared grad norm over all params. */
 int wsae_fused_adamw(float* p, const float* grad, float* m, float* v, long long n,
                      const float* hyper, const double* grad_sumsq, wsae_stream_t stream);
+
+/* The same update for up to 8 parameter tensors in ONE launch.  row_len > 0 marks a
+ * [n / row_len, row_len] matrix whose rows are re-normalised to unit L2 norm (clamped at
+ * renorm_eps) right after the update: optimizer.step() followed by normalize_decoder_weights()
+ * (sae/training.py:193-198, sae/model.py:91-96) in a single pass over the decoder.  `tensors` is a
+ * HOST array (copied into the kernel arguments); the pointers inside are device pointers. */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  int row_len;
+  int reserved;
+} wsae_adamw_tensor_t;
+int wsae_adamw_multi(const wsae_adamw_tensor_t* tensors, int count, const float* hyper,
+                     const double* grad_sumsq, float renorm_eps, wsae_stream_t stream);
 
 #ifdef __cplusplus
 }

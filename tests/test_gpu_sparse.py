@@ -251,3 +251,37 @@ def test_fused_adamw_matches_torch():
         torch.cuda.synchronize()
         for p, r in zip(gp, ref_p):
             torch.testing.assert_close(p.cpu(), r.detach(), rtol=2e-6, atol=1e-7)
+
+
+def test_adamw_multi_matches_torch_with_renorm():
+    """One launch: clip + AdamW over 5 tensors + unit-norm rows of the (feature-major) decoder."""
+    ops = _ops()
+    torch.manual_seed(1)
+    F, d = 1000, 392
+    shapes = [(d,), (F, d), (F,), (F, d), (d,)]
+    ps = [torch.randn(s) for s in shapes]
+    ref_p = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.AdamW(ref_p, lr=1e-3, weight_decay=0.01)
+    gp = [p.clone().cuda() for p in ps]
+    m = [torch.zeros_like(p) for p in gp]
+    v = [torch.zeros_like(p) for p in gp]
+    hyper = torch.empty(8, device="cuda")
+    for step in range(1, 4):
+        grads = [torch.randn(s) * (10.0 if step == 2 else 0.01) for s in shapes]
+        for p, g in zip(ref_p, grads):
+            p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(ref_p, 1.0)
+        opt.step()
+        with torch.no_grad():    # decoder (index 3) stored feature-major: unit rows == unit columns of W_dec
+            ref_p[3].copy_(torch.nn.functional.normalize(ref_p[3], dim=1))
+        gg = [g.cuda() for g in grads]
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        for g in gg:
+            ops.sumsq_(g, ss)
+        hyper.copy_(torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.01, 1 - 0.9 ** step,
+                                  math.sqrt(1 - 0.999 ** step), 1.0]))
+        entries = [(p, g, mm, vv, d if i == 3 else 0) for i, (p, g, mm, vv) in enumerate(zip(gp, gg, m, v))]
+        ops.adamw_multi_(entries, hyper, ss, 1e-12)
+        torch.cuda.synchronize()
+        for p, r in zip(gp, ref_p):
+            torch.testing.assert_close(p.cpu(), r.detach(), rtol=2e-6, atol=1e-7)

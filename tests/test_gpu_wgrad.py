@@ -23,10 +23,11 @@ def _case(B, d, F, k, seed, pitch=None):
     idx_d, val_d, dpre_d, R_d = idx.to(dev), val.to(dev), dpre.to(dev), R_bf.to(dev)
     buckets = ops.bucket_by_tile(idx_d, val_d, dpre_d, F)
     n_chunks, n_ft = ops.bucket_cells(B, F)
-    offs = buckets.offsets.cpu()
+    offs = buckets.offsets.cpu().view(n_chunks, n_ft + 1)    # per 64-row chunk: cell starts + end
     active = int((val > 0).sum())
-    assert offs[0] == 0 and offs[-1] == active
-    assert bool((offs[1:] >= offs[:-1]).all())
+    assert torch.equal(offs[:, 0], torch.arange(n_chunks, dtype=torch.int32) * 64 * k)
+    assert int((offs[:, -1] - offs[:, 0]).sum()) == active
+    assert bool((offs[:, 1:] >= offs[:, :-1]).all())
 
     def dense(values):
         S = torch.zeros(B, F, dtype=torch.float64)

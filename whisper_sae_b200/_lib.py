@@ -43,7 +43,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+class AdamwTensor(ctypes.Structure):
+    """wsae_adamw_tensor_t (include/wsae.h)."""
+
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p),
+                ("n", c_longlong), ("row_len", c_int), ("reserved", c_int)]
+
+
 _SIGNATURES = {
+    "wsae_adamw_multi": ([POINTER(AdamwTensor), c_int, c_void_p, c_void_p, c_float, c_void_p], c_int),
     "wsae_abi_version": ([], c_int),
     "wsae_packed_k": ([c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)], c_int),
     "wsae_pack_activations": ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p], c_int),

@@ -150,9 +150,138 @@ fused_adamw_kernel(float* __restrict__ p, const float* __restrict__ grad, float*
   }
 }
 
+// ---- multi-tensor AdamW (+ decoder renorm) in ONE launch --------------------------------------
+// Descriptor of one parameter tensor; row_len > 0 marks a [n / row_len, row_len] matrix whose rows
+// are re-normalised to unit L2 norm right after the update (sae/training.py:193-198: optimizer.step()
+// then normalize_decoder_weights(); sae/model.py:91-96), one warp per row, in the same pass.
+struct AdamwTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  int row_len;
+  int pad_;
+};
+constexpr int kAdamwMaxTensors = 8;
+struct AdamwBatch {
+  AdamwTensor t[kAdamwMaxTensors];
+  long long unit_start[kAdamwMaxTensors + 1];   // prefix of work units (1024 elements or 8 rows)
+  int count;
+};
+
+__device__ __forceinline__ void adamw_elem(float& pv, float g, float& mv, float& vv, float lr,
+                                           float b1, float b2, float eps, float wd, float bc2s,
+                                           float step_size) {
+  pv *= 1.f - lr * wd;
+  mv = mv + (g - mv) * (1.f - b1);
+  vv = b2 * vv + (1.f - b2) * g * g;
+  const float denom = sqrtf(vv) / bc2s + eps;
+  pv -= step_size * (mv / denom);
+}
+
+__global__ void __launch_bounds__(256)
+adamw_multi_kernel(const AdamwBatch batch, const float* __restrict__ hyper,
+                   const double* __restrict__ grad_sumsq, float renorm_eps) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const float bc1 = hyper[5], bc2s = hyper[6], max_norm = hyper[7];
+  float clip = 1.f;
+  if (grad_sumsq != nullptr && max_norm > 0.f) {
+    const float total = static_cast<float>(sqrt(*grad_sumsq));
+    const float c = max_norm / (total + 1e-6f);
+    clip = c < 1.f ? c : 1.f;
+  }
+  const float step_size = lr / bc1;
+  const long long total_units = batch.unit_start[batch.count];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long u = blockIdx.x; u < total_units; u += gridDim.x) {
+    int ti = 0;
+    while (ti + 1 < batch.count && u >= batch.unit_start[ti + 1]) ++ti;
+    const AdamwTensor& T = batch.t[ti];
+    const long long lu = u - batch.unit_start[ti];
+    if (T.row_len == 0) {
+      const long long i = lu * 1024 + threadIdx.x * 4;
+      if (i + 3 < T.n && ((reinterpret_cast<uintptr_t>(T.p) | reinterpret_cast<uintptr_t>(T.g) |
+                           reinterpret_cast<uintptr_t>(T.m) | reinterpret_cast<uintptr_t>(T.v)) & 15u) == 0) {
+        float4 pv = *reinterpret_cast<float4*>(T.p + i);
+        const float4 g = *reinterpret_cast<const float4*>(T.g + i);
+        float4 mv = *reinterpret_cast<float4*>(T.m + i);
+        float4 vv = *reinterpret_cast<float4*>(T.v + i);
+        adamw_elem(pv.x, g.x * clip, mv.x, vv.x, lr, b1, b2, eps, wd, bc2s, step_size);
+        adamw_elem(pv.y, g.y * clip, mv.y, vv.y, lr, b1, b2, eps, wd, bc2s, step_size);
+        adamw_elem(pv.z, g.z * clip, mv.z, vv.z, lr, b1, b2, eps, wd, bc2s, step_size);
+        adamw_elem(pv.w, g.w * clip, mv.w, vv.w, lr, b1, b2, eps, wd, bc2s, step_size);
+        *reinterpret_cast<float4*>(T.p + i) = pv;
+        *reinterpret_cast<float4*>(T.m + i) = mv;
+        *reinterpret_cast<float4*>(T.v + i) = vv;
+      } else {
+        for (long long j = i; j < T.n && j < i + 4; ++j) {
+          float pv = T.p[j], mv = T.m[j], vv = T.v[j];
+          adamw_elem(pv, T.g[j] * clip, mv, vv, lr, b1, b2, eps, wd, bc2s, step_size);
+          T.p[j] = pv; T.m[j] = mv; T.v[j] = vv;
+        }
+      }
+    } else {
+      const long long rows = T.n / T.row_len;
+      const long long row = lu * 8 + warp;
+      if (row < rows) {
+        const long long base = row * T.row_len;
+        float ss = 0.f;
+        // pass 1: update, store moments, keep the un-normalised weight in place
+        for (int c = lane; c < T.row_len; c += 32) {
+          float pv = T.p[base + c], mv = T.m[base + c], vv = T.v[base + c];
+          adamw_elem(pv, T.g[base + c] * clip, mv, vv, lr, b1, b2, eps, wd, bc2s, step_size);
+          T.p[base + c] = pv; T.m[base + c] = mv; T.v[base + c] = vv;
+          ss = fmaf(pv, pv, ss);
+        }
+        ss = warp_sum(ss);
+        const float nrm = fmaxf(sqrtf(ss), renorm_eps);
+        // pass 2 (same lane touches the same addresses: L1-resident): x / max(||x||, eps), the
+        // F.normalize formula
+        for (int c = lane; c < T.row_len; c += 32) T.p[base + c] = T.p[base + c] / nrm;
+      }
+    }
+  }
+}
+
 }  // namespace wsae
 
 using namespace wsae;
+
+// Host descriptor mirrored in include/wsae.h (wsae_adamw_tensor_t).
+struct wsae_adamw_tensor_host {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  int row_len;
+  int reserved;
+};
+
+extern "C" int wsae_adamw_multi(const wsae_adamw_tensor_host* tensors, int count, const float* hyper,
+                                const double* grad_sumsq, float renorm_eps, cudaStream_t stream) {
+  if (!tensors || !hyper || count <= 0 || count > kAdamwMaxTensors) return kBadArg;
+  AdamwBatch b;
+  long long units = 0;
+  for (int i = 0; i < count; ++i) {
+    const wsae_adamw_tensor_host& h = tensors[i];
+    if (!h.p || !h.g || !h.m || !h.v || h.n <= 0 || h.row_len < 0) return kBadArg;
+    if (h.row_len > 0 && h.n % h.row_len != 0) return kBadArg;
+    b.t[i] = AdamwTensor{h.p, h.g, h.m, h.v, h.n, h.row_len, 0};
+    b.unit_start[i] = units;
+    units += h.row_len == 0 ? (h.n + 1023) / 1024 : (h.n / h.row_len + 7) / 8;
+  }
+  b.unit_start[count] = units;
+  b.count = count;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long cap = static_cast<long long>(sms) * 16;
+  const unsigned blocks = static_cast<unsigned>(units < cap ? units : cap);
+  adamw_multi_kernel<<<blocks, 256, 0, stream>>>(b, hyper, grad_sumsq, renorm_eps);
+  return static_cast<int>(cudaGetLastError());
+}
 
 extern "C" int wsae_renorm_decoder(float* w_decT, int F, int d, float eps, void* bf16_shadow,
                                    cudaStream_t stream) {

@@ -83,6 +83,42 @@ pack_rows_kernel(const float* __restrict__ src, const float* __restrict__ center
       *reinterpret_cast<const uint4*>(out);
 }
 
+// bf16 fast path for activations (T = 1, d % 8 == 0): one thread converts 8 consecutive columns with
+// two 16-byte loads and one 16-byte store; the bias block and the K padding are written by the same
+// grid.  HBM bound: reads B*d*4, writes Bp*Kp*2 bytes.
+__global__ void __launch_bounds__(256)
+pack_activations_bf16_kernel(const float* __restrict__ x, const float* __restrict__ center, int rows,
+                             int rows_p, int d, int Kp, __nv_bfloat16* __restrict__ dst) {
+  const int groups = Kp >> 3;
+  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<size_t>(rows_p) * groups) return;
+  const int r = static_cast<int>(gid / groups);
+  const int c0 = static_cast<int>(gid - static_cast<size_t>(r) * groups) << 3;
+  uint4 out = make_uint4(0u, 0u, 0u, 0u);
+  if (r < rows) {
+    if (c0 < d) {
+      const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * d + c0);
+      float4 a = __ldcs(src), b = __ldcs(src + 1);        // streamed once: do not keep in L2/L1
+      if (center != nullptr) {
+        const float4 ca = __ldg(reinterpret_cast<const float4*>(center + c0));
+        const float4 cb = __ldg(reinterpret_cast<const float4*>(center + c0 + 4));
+        a.x -= ca.x; a.y -= ca.y; a.z -= ca.z; a.w -= ca.w;
+        b.x -= cb.x; b.y -= cb.y; b.z -= cb.z; b.w -= cb.w;
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+      out.x = *reinterpret_cast<uint32_t*>(&p0);
+      out.y = *reinterpret_cast<uint32_t*>(&p1);
+      out.z = *reinterpret_cast<uint32_t*>(&p2);
+      out.w = *reinterpret_cast<uint32_t*>(&p3);
+    } else if (c0 == d) {
+      out.x = 0x3F803F80u;   // bf16 1.0, 1.0
+      out.y = 0x00003F80u;   // bf16 1.0, 0
+    }
+  }
+  *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * Kp + c0) = out;
+}
+
 static bool make_schedule(int T, bool weights, PieceSchedule* s) {
   static const int8_t a1[6] = {0, 0, 0, 0, 0, 0}, w1[6] = {0, 0, 0, 0, 0, 0};
   static const int8_t a3[6] = {0, 1, 0, 0, 0, 0}, w3[6] = {0, 0, 1, 0, 0, 0};
@@ -120,7 +156,12 @@ static int pack_common(int kind, const float* src, const float* center, const fl
   const size_t total = static_cast<size_t>(rows_p) * (Kp >> 3);
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
-  if (kind == 0)
+  if (kind == 0 && terms == 1 && d % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(src) & 15u) == 0 &&
+      (center == nullptr || (reinterpret_cast<uintptr_t>(center) & 15u) == 0))
+    pack_activations_bf16_kernel<<<blocks, threads, 0, stream>>>(
+        src, center, rows, rows_p, d, Kp, static_cast<__nv_bfloat16*>(dst));
+  else if (kind == 0)
     pack_rows_kernel<0><<<blocks, threads, 0, stream>>>(src, center, bias, rows, rows_p, d, dp,
                                                         terms, Kp, s,
                                                         static_cast<__nv_bfloat16*>(dst));

@@ -29,86 +29,59 @@ constexpr int kWgMaxNB = 8;                       // n_tile <= 512 columns (TMEM
 // ------------------------------------------------------------------------------------------------
 // bucketing: entries of (idx,val) grouped by (feature tile, row chunk)
 // ------------------------------------------------------------------------------------------------
-// counts[ft * n_chunks + chunk] = number of active entries (value > 0) of that cell
+// One block per 64-row chunk: count the chunk's active entries (value > 0) per feature tile in
+// shared memory, scan, and write them grouped by feature tile into the chunk's own fixed segment
+// [chunk * 64 * k, ...) of the entry arrays.  No global scan: a chunk holds at most 64 * k entries.
+//   offsets[chunk * (n_ft + 1) + ft] = absolute index of the first entry of cell (chunk, ft)
+//   meta = row_local (0..63) | f_local << 8 ; va = dv ; vb = relu(val)
 __global__ void __launch_bounds__(256)
-bucket_count_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, int B, int F,
-                    int k, int n_chunks, int n_ft, int* __restrict__ counts) {
-  extern __shared__ int s_cnt[];  // [n_ft]
+bucket_chunk_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val,
+                    const float* __restrict__ dpre, int B, int F, int k, int n_ft,
+                    int* __restrict__ offsets, uint32_t* __restrict__ ent_meta,
+                    float* __restrict__ ent_a, float* __restrict__ ent_b) {
+  extern __shared__ int s_cell[];  // [n_ft] counts -> cursors
   const int chunk = blockIdx.x;
-  for (int i = threadIdx.x; i < n_ft; i += blockDim.x) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < n_ft; i += blockDim.x) s_cell[i] = 0;
   __syncthreads();
   const int row0 = chunk * kWgRows;
   const int nrow = min(kWgRows, B - row0);
+  const size_t g0 = static_cast<size_t>(row0) * k;
   for (int e = threadIdx.x; e < nrow * k; e += blockDim.x) {
-    const int32_t f = idx[static_cast<size_t>(row0) * k + e];
-    const float v = val[static_cast<size_t>(row0) * k + e];
-    if (f >= 0 && f < F && v > 0.f) atomicAdd(&s_cnt[f / kWgFeat], 1);
+    const int32_t f = idx[g0 + e];
+    const float v = val[g0 + e];
+    if (f >= 0 && f < F && v > 0.f) atomicAdd(&s_cell[f / kWgFeat], 1);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_ft; i += blockDim.x) counts[static_cast<size_t>(i) * n_chunks + chunk] = s_cnt[i];
-}
-
-// in-place exclusive scan of counts[0..n) -> offsets[0..n], offsets[n] = total.  Single block.
-__global__ void __launch_bounds__(1024)
-bucket_scan_kernel(int* __restrict__ counts_offsets, int n) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < n ? counts_offsets[i] : 0;
-    int x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      int w = s_warp[lane];
+  if (threadIdx.x < 32) {   // exclusive scan over the feature tiles, 32 at a time
+    const int lane = threadIdx.x;
+    int carry = static_cast<int>(g0);
+    int* orow = offsets + static_cast<size_t>(chunk) * (n_ft + 1);
+    for (int base = 0; base < n_ft; base += 32) {
+      const int i = base + lane;
+      const int c = i < n_ft ? s_cell[i] : 0;
+      int x = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += y;
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
       }
-      s_warp[lane] = w;
+      if (i < n_ft) {
+        s_cell[i] = carry + x - c;
+        orow[i] = carry + x - c;
+      }
+      carry += __shfl_sync(0xffffffffu, x, 31);
     }
-    __syncthreads();
-    const int carry = s_carry;
-    const int incl = x + (warp > 0 ? s_warp[warp - 1] : 0) + carry;
-    if (i < n) counts_offsets[i] = incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = incl;
-    __syncthreads();
+    if (lane == 0) orow[n_ft] = carry;
   }
-  if (threadIdx.x == 0) counts_offsets[n] = s_carry;
-}
-
-// meta = row_local (0..63) | f_local << 8 ; va = dv ; vb = relu(val)
-__global__ void __launch_bounds__(256)
-bucket_fill_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val,
-                   const float* __restrict__ dpre, int B, int F, int k, int n_chunks, int n_ft,
-                   const int* __restrict__ offsets, uint32_t* __restrict__ ent_meta,
-                   float* __restrict__ ent_a, float* __restrict__ ent_b) {
-  extern __shared__ int s_cur[];  // [n_ft]
-  const int chunk = blockIdx.x;
-  for (int i = threadIdx.x; i < n_ft; i += blockDim.x)
-    s_cur[i] = offsets[static_cast<size_t>(i) * n_chunks + chunk];
   __syncthreads();
-  const int row0 = chunk * kWgRows;
-  const int nrow = min(kWgRows, B - row0);
   for (int e = threadIdx.x; e < nrow * k; e += blockDim.x) {
-    const size_t g = static_cast<size_t>(row0) * k + e;
-    const int32_t f = idx[g];
-    const float v = val[g];
+    const int32_t f = idx[g0 + e];
+    const float v = val[g0 + e];
     if (f >= 0 && f < F && v > 0.f) {
       const int ft = f / kWgFeat;
-      const int pos = atomicAdd(&s_cur[ft], 1);
+      const int pos = atomicAdd(&s_cell[ft], 1);
       ent_meta[pos] = static_cast<uint32_t>(e / k) | (static_cast<uint32_t>(f - ft * kWgFeat) << 8);
-      ent_a[pos] = dpre[g];
+      ent_a[pos] = dpre[g0 + e];
       ent_b[pos] = v;
     }
   }
@@ -262,7 +235,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
 #pragma unroll
       for (int i = 0; i < 8; ++i) tile4[i * 128 + t] = z;
       named_bar_sync(1, 128);
-      const size_t cell = static_cast<size_t>(ft) * n_chunks + (c0 + c);
+      const size_t cell = static_cast<size_t>(c0 + c) * (n_ft + 1) + ft;
       const int e0 = offsets[cell], e1 = offsets[cell + 1];
       for (int e = e0 + t; e < e1; e += 128) {
         const uint32_t m = ent_meta[e];
@@ -346,10 +319,8 @@ extern "C" int wsae_bucket_by_tile(const int32_t* idx, const float* val, const f
   const int n_chunks = ceil_div(B, kWgRows), n_ft = ceil_div(F, kWgFeat);
   const size_t smem = static_cast<size_t>(n_ft) * sizeof(int);
   if (smem > 48 * 1024) return kUnsupported;
-  bucket_count_kernel<<<n_chunks, 256, smem, stream>>>(idx, val, B, F, k, n_chunks, n_ft, offsets);
-  bucket_scan_kernel<<<1, 1024, 0, stream>>>(offsets, n_chunks * n_ft);
-  bucket_fill_kernel<<<n_chunks, 256, smem, stream>>>(idx, val, dpre, B, F, k, n_chunks, n_ft, offsets,
-                                                      ent_meta, ent_a, ent_b);
+  bucket_chunk_kernel<<<n_chunks, 256, smem, stream>>>(idx, val, dpre, B, F, k, n_ft, offsets,
+                                                       ent_meta, ent_a, ent_b);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -244,7 +244,7 @@ def decode_backward(target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: Tensor
 class TileBuckets:
     """Active (idx, val) entries grouped by (128-feature tile, 64-row chunk) for the K4 GEMMs."""
 
-    offsets: Tensor    # int32 [n_ft * n_chunks + 1]
+    offsets: Tensor    # int32 [n_chunks * (n_ft + 1)]
     meta: Tensor       # int32 [B*k]  row_in_chunk | feature_in_tile << 8
     dpre: Tensor       # float32 [B*k]  dv of the entry      (values of the dW_enc GEMM)
     act: Tensor        # float32 [B*k]  relu(val) of the entry (values of the dW_decT GEMM)
@@ -265,12 +265,12 @@ def bucket_by_tile(idx: Tensor, val: Tensor, dpre_val: Tensor, F: int,
     dev = idx.device
     if out is None:
         out = TileBuckets(
-            torch.empty(n_chunks * n_ft + 1, dtype=torch.int32, device=dev),
+            torch.empty(n_chunks * (n_ft + 1), dtype=torch.int32, device=dev),
             torch.empty(B * k, dtype=torch.int32, device=dev),
             torch.empty(B * k, dtype=torch.float32, device=dev),
             torch.empty(B * k, dtype=torch.float32, device=dev))
     lib = _lib.load()
-    _run("wsae_bucket_by_tile", lib.wsae_bucket_by_tile, _ptr(idx), _ptr(val), _ptr(dpre_val), B, F, k, _ptr(out.offsets), _ptr(out.meta), _ptr(out.dpre), _ptr(out.act), _stream(), launches=3)
+    _run("wsae_bucket_by_tile", lib.wsae_bucket_by_tile, _ptr(idx), _ptr(val), _ptr(dpre_val), B, F, k, _ptr(out.offsets), _ptr(out.meta), _ptr(out.dpre), _ptr(out.act), _stream())
     return out
 
 
@@ -360,3 +360,17 @@ def fused_adamw_(p: Tensor, grad: Tensor, m: Tensor, v: Tensor, hyper: Tensor,
                  grad_sumsq: Tensor | None) -> None:
     lib = _lib.load()
     _run("wsae_fused_adamw", lib.wsae_fused_adamw, _ptr(p), _ptr(grad), _ptr(m), _ptr(v), p.numel(), _ptr(hyper), _ptr(grad_sumsq), _stream())
+
+
+def adamw_multi_(entries: list[tuple[Tensor, Tensor, Tensor, Tensor, int]], hyper: Tensor,
+                 grad_sumsq: Tensor | None, renorm_eps: float = 1e-12) -> None:
+    """Clip + AdamW for several tensors in one launch.  ``entries`` = (param, grad, exp_avg,
+    exp_avg_sq, row_len): row_len > 0 => rows of that length are re-normalised after the update
+    (the feature-major decoder); all four tensors of an entry share one dense layout."""
+    lib = _lib.load()
+    arr = (_lib.AdamwTensor * len(entries))()
+    for a, (p, g, m, v, row_len) in zip(arr, entries):
+        _need_cuda(p, g, m, v)
+        a.p, a.g, a.m, a.v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+        a.n, a.row_len, a.reserved = p.numel(), int(row_len), 0
+    _run("wsae_adamw_multi", lib.wsae_adamw_multi, arr, len(entries), _ptr(hyper), _ptr(grad_sumsq), float(renorm_eps), _stream())

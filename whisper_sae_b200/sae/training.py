@@ -89,11 +89,17 @@ class _GraphedStep:
         self.params = [m.b_pre, m.encoder.weight, m.encoder.bias, m.decoder.weight, m.decoder.bias]
         m._w_decT()
         F, d = m.hidden_dim, m.input_dim
-        self.g_b_pre = torch.zeros(d, dtype=torch.float32, device=dev)
-        self.g_w_enc = torch.zeros((F, d), dtype=torch.float32, device=dev)
-        self.g_b_enc = torch.zeros(F, dtype=torch.float32, device=dev)
-        self.g_w_decT = torch.zeros((F, d), dtype=torch.float32, device=dev)
-        self.g_b_dec = torch.zeros(d, dtype=torch.float32, device=dev)
+        # one flat gradient bucket (segments 64-byte aligned): a single memset and a single
+        # sum-of-squares pass per step; also the unit a data-parallel all-reduce ships
+        sizes = [d, F * d, F, F * d, d]
+        starts, off = [], 0
+        for n in sizes:
+            starts.append(off)
+            off += (n + 15) // 16 * 16
+        self.g_flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        seg = [self.g_flat[s0:s0 + n] for s0, n in zip(starts, sizes)]
+        self.g_b_pre, self.g_b_enc, self.g_b_dec = seg[0], seg[2], seg[4]
+        self.g_w_enc, self.g_w_decT = seg[1].view(F, d), seg[3].view(F, d)
         self.grads = [self.g_b_pre, self.g_w_enc, self.g_b_enc, self.g_w_decT, self.g_b_dec]
         self.state = _SparseState()
         self.graph: torch.cuda.CUDAGraph | None = None
@@ -126,8 +132,7 @@ class _GraphedStep:
         w_used = ops.cast_bf16(w_decT) if self.bf16 else w_decT
         rows_total = m._global_rows or B
         coef = 2.0 / (float(rows_total) * d)
-        for g in self.grads:
-            g.zero_()
+        self.g_flat.zero_()
         dpre = torch.empty((B, k), dtype=torch.float32, device=x.device)
         use_gemm = self.bf16 and ops.wgrad_gemm_supported(d)
         if use_gemm and ops.decode_backward_supported(d, k, True):
@@ -162,13 +167,14 @@ class _GraphedStep:
             ops.wgrad_gemm_(self.g_w_decT, resid_bf, B, d, buckets, buckets.act, self.one, coef)
         ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
         self.sumsq.zero_()
-        for g in self.grads:
-            ops.sumsq_(g, self.sumsq)
+        ops.sumsq_(self.g_flat, self.sumsq)
         opt_state = self.trainer.optimizer.state
+        entries = []
         for p, g in zip(self.params, self.grads):
             st = opt_state[p]
-            ops.fused_adamw_(p.data, g, st["exp_avg"], st["exp_avg_sq"], self.hyper, self.sumsq)
-        ops.renorm_decoder_(w_decT, 1e-12)
+            is_dec = p is m.decoder.weight          # feature-major storage: rows = decoder vectors
+            entries.append((p.data, g, st["exp_avg"], st["exp_avg_sq"], d if is_dec else 0))
+        ops.adamw_multi_(entries, self.hyper, self.sumsq, 1e-12)   # clip + AdamW + decoder renorm
         s = self.state
         s.idx, s.val, s.resid, s.stats, s.w_dec_used, s.rows_total = idx, val, resid, self.stats, w_used, rows_total
         s.d_out = d
