@@ -97,6 +97,11 @@ int wsae_decode_backward(const float* target, const void* w_decT, int w_is_bf16,
                          int d, int F, int k, float* resid, void* resid_bf16, void* stats,
                          long long* last_activated, const long long* step_count, float* d_b_enc,
                          float* d_b_dec, float* dpre_val, wsae_stream_t stream);
+/* out[idx[b,j], :] += vals[b,j] * (rows[b,:] - center): the encoder weight gradient as a sparse
+ * scatter when the input width differs from the decoder width (transcoders); dr % 4 == 0. */
+int wsae_scatter_rows(const float* rows, const float* center /*nullable*/, const int32_t* idx,
+                      const float* vals, int B, int dr, int F, int k, float* out /*[F,dr]*/,
+                      wsae_stream_t stream);
 /* db_pre = db_dec - db_enc . W_enc  (overwrites d_b_pre). */
 int wsae_bpre_grad(const float* d_b_dec, const float* d_b_enc, const float* w_enc, int F, int d,
                    float* d_b_pre, wsae_stream_t stream);

@@ -134,3 +134,38 @@ def test_backward_matches_reference_autograd_formula():
     torch.testing.assert_close(g["dx"], xr.grad, rtol=1e-4, atol=1e-8)
 
 
+
+
+# ---- transcoder / crosscoder variants (oracle/variants_oracle.py vs live-reference fixtures) ----
+VARIANT_CASES = ["transcoder_64_64_128_k8", "transcoder_96_64_256_k16", "skip_64_64_128_k8",
+                 "crosscoder_64x4_128_k8", "crosscoder_subset_64x2_128_k8"]
+
+
+def _variant_inputs(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("name", VARIANT_CASES)
+def test_variants_oracle_matches_reference(name):
+    from oracle import variants_oracle as V
+
+    fx = load_golden("variants")[name]
+    r = fx["recipe"]
+    if name.startswith("crosscoder"):
+        acts = {li: _variant_inputs(r["seed"] + 20 + i, r["B"], r["d"]) for i, li in enumerate(r["layer_indices"])}
+        out = V.crosscoder(fx["state"], acts, r["layer_indices"], r["k"])
+        for li, v in fx["per_layer_loss"].items():
+            assert out["per_layer_loss"][li] == pytest.approx(v, rel=1e-6)
+    else:
+        x = _variant_inputs(r["seed"] + 10, r["B"], r["d_in"])
+        y = _variant_inputs(r["seed"] + 11, r["B"], r["d_out"])
+        out = V.transcoder(fx["state"], x, y, r["k"])
+        torch.testing.assert_close(out["predicted"], fx["predicted"], rtol=1e-5, atol=1e-6)
+    assert out["loss"] == pytest.approx(fx["loss"], rel=1e-6)
+    assert out["l0"] == fx["l0"]
+    torch.testing.assert_close(out["hidden"], fx["hidden"], rtol=1e-5, atol=1e-6)
+    for n, g in fx["grads"].items():
+        torch.testing.assert_close(out["grads"][n], g, rtol=1e-5, atol=1e-7, msg=lambda m: f"{n}: {m}")
+    want = torch.zeros_like(fx["feature_last_activated"])
+    want[out["fired"]] = 1
+    assert torch.equal(want, fx["feature_last_activated"]) and fx["step_count"] == 1

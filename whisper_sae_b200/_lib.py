@@ -90,6 +90,7 @@ _SIGNATURES = {
          c_void_p, c_void_p],
         c_int,
     ),
+    "wsae_scatter_rows": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
     "wsae_bpre_grad": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
     "wsae_input_grad": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int,

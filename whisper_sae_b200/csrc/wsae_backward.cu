@@ -204,6 +204,31 @@ input_grad_kernel(const float* __restrict__ resid, const float* __restrict__ w_e
   }
 }
 
+// out[idx[b,j], :] += vals[b,j] * (rows[b, :] - center)   — the encoder weight gradient
+// dW_enc = dpre^T . (x - b_pre) as a sparse scatter, for the case where the input width differs
+// from the decoder width (transcoders: transcoder.py:105-138), which K3's single-`d` form cannot do.
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const float* __restrict__ rows, const float* __restrict__ center,
+                    const int32_t* __restrict__ idx, const float* __restrict__ vals, int B, int dr,
+                    int F, int k, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  for (int col = lane * 4; col < dr; col += 128) {
+    float4 xv = *reinterpret_cast<const float4*>(rows + static_cast<size_t>(row) * dr + col);
+    if (center != nullptr) {
+      const float4 c = *reinterpret_cast<const float4*>(center + col);
+      xv.x -= c.x; xv.y -= c.y; xv.z -= c.z; xv.w -= c.w;
+    }
+    for (int j = 0; j < k; ++j) {
+      const int32_t f = idx[static_cast<size_t>(row) * k + j];
+      const float v = vals[static_cast<size_t>(row) * k + j];
+      if (f >= 0 && f < F && v != 0.f)
+        red_add_f32x4(out + static_cast<size_t>(f) * dr + col, v * xv.x, v * xv.y, v * xv.z, v * xv.w);
+    }
+  }
+}
+
 template <typename WT>
 static int launch_backward(const float* resid, const float* x, const float* b_pre, const void* w,
                            const int32_t* idx, const float* val, const float* grad_out, float coef,
@@ -257,6 +282,17 @@ extern "C" int wsae_backward_sparse(const float* resid, const float* x, const fl
                                           resid_bf16, stream);
   return launch_backward<float>(resid, x, b_pre, w_decT, idx, val, grad_out, coef, B, d, F, k,
                                 d_w_enc, d_w_decT, d_b_enc, d_b_dec, dpre_val, resid_bf16, stream);
+}
+
+extern "C" int wsae_scatter_rows(const float* rows, const float* center, const int32_t* idx,
+                                 const float* vals, int B, int dr, int F, int k, float* out,
+                                 cudaStream_t stream) {
+  if (!rows || !idx || !vals || !out || B <= 0 || dr <= 0 || F <= 0 || k <= 0) return kBadArg;
+  if (dr % 4 != 0) return kUnsupported;
+  const int warps = 8;
+  scatter_rows_kernel<<<ceil_div(B, warps), warps * 32, 0, stream>>>(rows, center, idx, vals, B, dr,
+                                                                     F, k, out);
+  return static_cast<int>(cudaGetLastError());
 }
 
 extern "C" int wsae_bpre_grad(const float* d_b_dec, const float* d_b_enc, const float* w_enc,

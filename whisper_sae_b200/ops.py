@@ -295,6 +295,17 @@ def wgrad_gemm_(out: Tensor, r_bf16: Tensor, B: int, d: int, buckets: TileBucket
     _run("wsae_wgrad_gemm", lib.wsae_wgrad_gemm, _ptr(r_bf16), r_bf16.stride(0), B, F, d, _ptr(buckets.offsets), _ptr(buckets.meta), _ptr(values), _ptr(grad_out), float(alpha), _ptr(out), _stream())
 
 
+def scatter_rows_(out: Tensor, rows: Tensor, center: Tensor | None, idx: Tensor, vals: Tensor) -> None:
+    """out[idx[b,j], :] += vals[b,j] * (rows[b,:] - center)  (sparse dW_enc, input width != decoder width)."""
+    _need_cuda(out, rows, center, idx, vals)
+    _f32c(rows, "rows")
+    _f32c(out, "out")
+    B, dr = rows.shape
+    F = out.shape[0]
+    lib = _lib.load()
+    _run("wsae_scatter_rows", lib.wsae_scatter_rows, _ptr(rows), _ptr(center), _ptr(idx), _ptr(vals), B, dr, F, idx.shape[1], _ptr(out), _stream())
+
+
 def bpre_grad(d_b_dec: Tensor, d_b_enc: Tensor, w_enc: Tensor, out: Tensor | None = None) -> Tensor:
     F, d = w_enc.shape
     if out is None:

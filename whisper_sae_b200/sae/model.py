@@ -35,49 +35,56 @@ from ..config import SAEConfig
 _FIELDS = ("reconstructed", "hidden", "loss", "reconstruction_loss", "sparsity_loss", "l0")
 
 
-class SAEOutput:
-    """Result of an SAE forward pass; quacks like the reference's NamedTuple (model.py:15-23).
+class _LazyOutput:
+    """Tuple-like result object whose dense fields may be zero-argument callables: the dense tensors
+    are only built when somebody reads them (the trainer never does).  Subclasses set ``_fields``."""
 
-    ``reconstructed`` and ``hidden`` may be given as zero-argument callables, in which case the
-    dense tensors are only built when somebody reads them (the trainer never does).
-    """
-
-    _fields = _FIELDS
+    _fields: tuple[str, ...] = ()
     __slots__ = ("_vals",)
 
-    def __init__(self, reconstructed, hidden, loss, reconstruction_loss, sparsity_loss, l0):
-        self._vals = [reconstructed, hidden, loss, reconstruction_loss, sparsity_loss, l0]
+    def __init__(self, *vals, **kw):
+        vals = list(vals) + [kw[name] for name in self._fields[len(vals):]]
+        if len(vals) != len(self._fields):
+            raise TypeError(f"{type(self).__name__} takes {len(self._fields)} fields")
+        self._vals = vals
 
-    def _get(self, i: int) -> Tensor:
+    def _get(self, i: int):
         v = self._vals[i]
         if callable(v) and not isinstance(v, Tensor):
             v = v()
             self._vals[i] = v
         return v
 
-    reconstructed = property(lambda self: self._get(0))
-    hidden = property(lambda self: self._get(1))
-    loss = property(lambda self: self._get(2))
-    reconstruction_loss = property(lambda self: self._get(3))
-    sparsity_loss = property(lambda self: self._get(4))
-    l0 = property(lambda self: self._get(5))
+    def __getattr__(self, name: str):
+        fields = type(self)._fields
+        if name in fields:
+            return self._get(fields.index(name))
+        raise AttributeError(name)
 
-    def __iter__(self) -> Iterator[Tensor]:
-        return (self._get(i) for i in range(len(_FIELDS)))
+    def __iter__(self) -> Iterator:
+        return (self._get(i) for i in range(len(self._fields)))
 
     def __len__(self) -> int:
-        return len(_FIELDS)
+        return len(self._fields)
 
     def __getitem__(self, i):
         if isinstance(i, slice):
-            return tuple(self._get(j) for j in range(len(_FIELDS))[i])
-        return self._get(range(len(_FIELDS))[i])
+            return tuple(self._get(j) for j in range(len(self._fields))[i])
+        return self._get(range(len(self._fields))[i])
 
-    def _asdict(self) -> dict[str, Tensor]:
-        return {name: self._get(i) for i, name in enumerate(_FIELDS)}
+    def _asdict(self) -> dict:
+        return {name: self._get(i) for i, name in enumerate(self._fields)}
 
     def __repr__(self) -> str:
-        return "SAEOutput(" + ", ".join(_FIELDS) + ")"
+        return type(self).__name__ + "(" + ", ".join(self._fields) + ")"
+
+
+class SAEOutput(_LazyOutput):
+    """Result of an SAE forward pass; quacks like the reference's NamedTuple (model.py:15-23):
+    ``reconstructed, hidden, loss, reconstruction_loss, sparsity_loss, l0``."""
+
+    _fields = _FIELDS
+    __slots__ = ()
 
 
 def _fp32_terms() -> int:
@@ -172,6 +179,12 @@ class _FusedTopKSAE(torch.autograd.Function):
                     ops.wgrad_gemm_(d_w_enc, ctx.a_packed, B, d_in, buckets, buckets.dpre, None, 1.0)
                 if d_w_decT is not None:
                     ops.wgrad_gemm_(d_w_decT, resid_bf, B, d_out, buckets, buckets.act, go, coef)
+        elif d_in != d_out and d_w_enc is not None:
+            # K3 walks x and the residual with one row width: split off the encoder-gradient scatter
+            ops.backward_sparse(st.resid, None, None, st.w_dec_used, st.idx, st.val, go, coef,
+                                d_w_enc=None, d_w_decT=d_w_decT, d_b_enc=d_b_enc, d_b_dec=d_b_dec,
+                                dpre_val=dpre)
+            ops.scatter_rows_(d_w_enc, x, b_pre, st.idx, dpre)
         else:
             ops.backward_sparse(st.resid, x, b_pre, st.w_dec_used, st.idx, st.val, go, coef,
                                 d_w_enc=d_w_enc, d_w_decT=d_w_decT, d_b_enc=d_b_enc, d_b_dec=d_b_dec,
