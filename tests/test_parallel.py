@@ -1,0 +1,140 @@
+"""Multi-GPU host logic (sae/parallel.py): shard maps, the per-step exchange over a real
+``torch.distributed`` group (gloo, world_size 2, CPU), and - on a GPU - the batch-sharded step of
+two emulated ranks against the single-device step on the concatenated batch."""
+
+import os
+import threading
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from whisper_sae_b200.sae import parallel
+
+
+def test_shard_rows_and_layer_assignment():
+    for n, world in ((65536, 8), (1000, 3), (5, 8)):
+        spans = [parallel.shard_rows(n, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    units = [parallel.layer_assignment([0, 1, 2, 3], [0, 1, 2, 3], 8, r) for r in range(8)]
+    assert units == [[("encoder", i)] for i in range(4)] + [[("decoder", i)] for i in range(4)]
+    two = [parallel.layer_assignment([0, 1, 2, 3], [0, 1, 2, 3], 2, r) for r in range(2)]
+    assert sorted(two[0] + two[1]) == sorted([(c, i) for c in ("encoder", "decoder") for i in range(4)])
+    assert len(two[0]) == len(two[1]) == 4
+
+
+def _gloo_worker(rank: int, world: int, port: int, out_dir: str):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = parallel.TorchDistCommunicator()
+        g = torch.full((1000,), float(rank + 1))
+        stats = torch.zeros(3, dtype=torch.int64)
+        stats[:1].view(torch.float64)[0] = 0.5 * (rank + 1)
+        stats[1] = 10 + rank
+        stats[2] = 99                                   # dead count: not reduced
+        last = torch.zeros(16, dtype=torch.int64)
+        last[rank::2] = 7                               # each rank stamps its own fired features
+        last[0] = 3 if rank == 0 else 0
+        comm.reduce_step(g, stats, last)
+        torch.save({"g": g, "stats": stats, "last": last, "world": comm.world, "rank": comm.rank},
+                   os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reduce_step_gloo_world2(tmp_path):
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    outs = [torch.load(tmp_path / f"r{r}.pt") for r in range(2)]
+    for r, o in enumerate(outs):
+        assert o["world"] == 2 and o["rank"] == r
+        assert torch.equal(o["g"], torch.full((1000,), 3.0))                   # 1 + 2
+        assert o["stats"][:1].view(torch.float64).item() == 1.5               # 0.5 + 1.0
+        assert o["stats"][1].item() == 21 and o["stats"][2].item() == 99
+        want = torch.full((16,), 7, dtype=torch.int64)
+        want[0] = 3                                                            # max(3, 0)
+        assert torch.equal(o["last"], want)                                    # MAX = union of stamps
+
+
+def test_thread_communicator_cpu():
+    comms = parallel.ThreadCommunicator.make(2)
+    res = [None, None]
+
+    def work(r):
+        g = torch.full((8,), float(r + 1))
+        stats = torch.zeros(3, dtype=torch.int64)
+        stats[:1].view(torch.float64)[0] = float(r)
+        stats[1] = r + 1
+        last = torch.tensor([r, 5 * r, 2], dtype=torch.int64)
+        comms[r].reduce_step(g, stats, last)
+        res[r] = (g, stats, last)
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for g, stats, last in res:
+        assert torch.equal(g, torch.full((8,), 3.0))
+        assert stats[:1].view(torch.float64).item() == 1.0 and stats[1].item() == 3
+        assert torch.equal(last, torch.tensor([1, 5, 2]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_amp,tol", [(False, 2e-6), (True, 2e-3)])
+def test_batch_sharded_step_matches_single_device(tmp_path, use_amp, tol):
+    """Two emulated ranks (threads, one GPU) x B/2 rows == one device x B rows: same losses, same
+    counters (bit-exact), same weights after 3 steps."""
+    from oracle import topk_sae_oracle as O
+    from whisper_sae_b200.config import TrainingConfig
+    from whisper_sae_b200.sae import SAETrainer, TopKSAE
+
+    d, F, k, B, steps = 128, 1024, 16, 256, 3
+    cfg = TrainingConfig(batch_size=B, use_amp=use_amp, num_workers=0, learning_rate=1e-3, warmup_steps=2)
+    x = O.synthetic_activations(B * steps, d, seed=11).cuda()
+
+    def make(**kw):
+        torch.manual_seed(3)
+        sae = TopKSAE(d, F, k=k, dead_feature_threshold=1)
+        tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path / f"r{len(list(tmp_path.iterdir()))}", **kw)
+        tr.setup_scheduler(50)
+        return tr
+
+    single = make()
+    ref = [single.train_step(x[s * B:(s + 1) * B]) for s in range(steps)]
+    comms = parallel.ThreadCommunicator.make(2)
+    ranks = [make(data_parallel=True, dp_comm=c) for c in comms]
+    got = [[None] * steps for _ in range(2)]
+    errors = []
+
+    def work(r):
+        try:
+            torch.cuda.set_device(0)
+            for s in range(steps):
+                a, b = parallel.shard_rows(B, 2, r)
+                got[r][s] = ranks[r].train_step(x[s * B + a:s * B + b])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            comms[r].shared.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+    for s in range(steps):
+        for r in range(2):
+            assert got[r][s].loss == pytest.approx(ref[s].loss, rel=max(tol, 1e-6))
+            assert got[r][s].l0 == ref[s].l0
+            assert got[r][s].dead_feature_ratio == ref[s].dead_feature_ratio
+    for r in range(2):
+        m = ranks[r].model
+        assert torch.equal(m.feature_last_activated, single.model.feature_last_activated)
+        assert int(m.step_count) == steps
+        for (n, p), (_, q) in zip(m.named_parameters(), single.model.named_parameters()):
+            scale = q.abs().max().item()
+            torch.testing.assert_close(p, q, rtol=tol * 10, atol=tol * scale, msg=lambda msg: f"{n}: {msg}")
+    for p, q in zip(ranks[0].model.parameters(), ranks[1].model.parameters()):
+        assert torch.equal(p, q)          # replicas stay bit-identical without a broadcast

@@ -1,0 +1,115 @@
+"""Multi-GPU partitioning of the train step along its natural shards.  The reference
+has no distributed code at all (layers are trained sequentially, scripts/train.py:338-342); these
+helpers are new.  One process per GPU, ``torch.distributed`` (NCCL over NVLink on the GPU box,
+gloo in the CPU tests) for the plumbing.
+
+* Layer parallel (BASELINE config 2): whisper-tiny has 4 encoder + 4 decoder layers, each with its
+  own cache file, SAE, optimizer and run dir => ``layer_assignment`` deals them round-robin over the
+  ranks and **no collective** touches the data path.
+* Batch-sharded data parallel (configs 3-4): rows are i.i.d. and the loss is a mean over
+  B_global * d, so every rank runs the kernels on B_global / world rows with the *global*
+  denominator and ``reduce_step`` combines, per step,
+    - the flat fp32 gradient bucket ``[b_pre | W_enc | b_enc | W_decT | b_dec]``  (SUM),
+    - ``{sse, l0 count}``                                                        (SUM, f64 / i64),
+    - the fired stamps ``feature_last_activated``                                (MAX, i64: every
+      rank stamps ``step_count + 1``, so MAX is the union of fired features and the dead-feature
+      counters stay bit-exact against the single-device run).
+  Clip, AdamW and the decoder renorm then run identically on every rank (deterministic), so the
+  replicas stay bit-identical without a weight broadcast.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+COMPONENTS = ("encoder", "decoder")
+
+
+def shard_rows(n_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """[start, stop) of this rank's contiguous row shard; remainders go to the lowest ranks."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad world/rank")
+    base, rem = divmod(n_rows, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def layer_assignment(encoder_layers: list[int], decoder_layers: list[int], world: int,
+                     rank: int) -> list[tuple[str, int]]:
+    """(component, layer) units owned by ``rank``: all units dealt round-robin in the order the
+    reference loops over them (scripts/train.py:296-304: encoder layers, then decoder layers)."""
+    units = [("encoder", i) for i in encoder_layers] + [("decoder", i) for i in decoder_layers]
+    return [u for j, u in enumerate(units) if j % world == rank]
+
+
+def reduce_step(g_flat: Tensor, stats: Tensor, last_activated: Tensor | None,
+                group: dist.ProcessGroup | None = None) -> None:
+    """The per-step exchange of the batch-sharded step, in place (see module docstring).
+    ``stats`` is the kernels' packed int64[3] buffer: [0] = SSE as float64 bits, [1] = L0 count,
+    [2] = dead count (recomputed after the exchange, not reduced)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("reduce_step needs an initialised torch.distributed process group")
+    dist.all_reduce(g_flat, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(stats[:1].view(torch.float64), op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(stats[1:2], op=dist.ReduceOp.SUM, group=group)
+    if last_activated is not None:
+        dist.all_reduce(last_activated, op=dist.ReduceOp.MAX, group=group)
+
+
+class TorchDistCommunicator:
+    """The production communicator: ``torch.distributed`` collectives (NCCL on the GPU box)."""
+
+    def __init__(self, group: dist.ProcessGroup | None = None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("data_parallel=True needs torch.distributed to be initialised")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def reduce_step(self, g_flat: Tensor, stats: Tensor, last_activated: Tensor | None) -> None:
+        reduce_step(g_flat, stats, last_activated, self.group)
+
+
+class ThreadCommunicator:
+    """In-process stand-in with the same interface: ``world`` threads of ONE process (one GPU, or
+    the CPU) rendezvous on a barrier and combine their buffers.  Used to check the batch-sharded
+    step against the single-device step where only one GPU is available."""
+
+    class _Shared:
+        def __init__(self, world: int):
+            import threading
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots: list = [None] * world
+
+    def __init__(self, shared: "ThreadCommunicator._Shared", rank: int):
+        self.shared, self.rank, self.world = shared, rank, shared.world
+
+    @classmethod
+    def make(cls, world: int) -> list["ThreadCommunicator"]:
+        shared = cls._Shared(world)
+        return [cls(shared, r) for r in range(world)]
+
+    def reduce_step(self, g_flat: Tensor, stats: Tensor, last_activated: Tensor | None) -> None:
+        sh = self.shared
+        if g_flat.is_cuda:
+            torch.cuda.synchronize()
+        sh.slots[self.rank] = (g_flat.clone(), stats.clone(),
+                               None if last_activated is None else last_activated.clone())
+        sh.barrier.wait()
+        g_flat.zero_()
+        sse = torch.zeros(1, dtype=torch.float64, device=stats.device)
+        l0 = torch.zeros(1, dtype=torch.int64, device=stats.device)
+        for g, st, la in sh.slots:                      # same order on every rank => bit-identical
+            g_flat += g
+            sse += st[:1].view(torch.float64)
+            l0 += st[1:2]
+            if last_activated is not None:
+                torch.maximum(last_activated, la, out=last_activated)
+        stats[:1].view(torch.float64).copy_(sse)
+        stats[1:2].copy_(l0)
+        if g_flat.is_cuda:
+            torch.cuda.synchronize()
+        sh.barrier.wait()

@@ -119,6 +119,14 @@ class _GraphedStep:
         return tuple(ptrs)
 
     def _body(self) -> None:
+        self._compute()
+        if self.trainer.data_parallel:      # batch-sharded: exchange gradients / stats / fired stamps
+            self.trainer.dp_comm.reduce_step(self.g_flat, self.stats,
+                                             self.trainer.model.feature_last_activated)
+        self._update()
+
+    def _compute(self) -> None:
+        """Forward + backward kernels of this rank's rows: fills g_flat, stats[0:2], fired stamps."""
         m = self.trainer.model
         x = self.x
         B, d = x.shape
@@ -143,14 +151,10 @@ class _GraphedStep:
                                 resid=None, resid_bf16=resid_bf, stats=self.stats,
                                 last_activated=m.feature_last_activated, step_count=m.step_count,
                                 d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre)
-            ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold,
-                                True, self.stats[2:])
         else:
             resid, _ = ops.decode_mse(x, w_used, m.decoder.bias.data, m.b_pre.data, idx, val,
                                       stats=self.stats, last_activated=m.feature_last_activated,
                                       step_count=m.step_count)
-            ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold,
-                                True, self.stats[2:])
             if use_gemm:
                 resid_bf = torch.empty((B, d), dtype=torch.bfloat16, device=x.device)
                 ops.backward_sparse(resid, None, None, w_used, idx, val, self.one, coef, d_w_enc=None,
@@ -166,6 +170,16 @@ class _GraphedStep:
             ops.wgrad_gemm_(self.g_w_enc, a_packed, B, d, buckets, buckets.dpre, None, 1.0)
             ops.wgrad_gemm_(self.g_w_decT, resid_bf, B, d, buckets, buckets.act, self.one, coef)
         ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
+        s = self.state
+        s.idx, s.val, s.resid, s.stats, s.w_dec_used, s.rows_total = idx, val, resid, self.stats, w_used, rows_total
+        s.d_out = d
+
+    def _update(self) -> None:
+        """Counters, clip + AdamW + decoder renorm on the (possibly all-reduced) gradient bucket."""
+        m = self.trainer.model
+        d = m.input_dim
+        ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold, True,
+                            self.stats[2:])
         self.sumsq.zero_()
         ops.sumsq_(self.g_flat, self.sumsq)
         opt_state = self.trainer.optimizer.state
@@ -175,9 +189,6 @@ class _GraphedStep:
             is_dec = p is m.decoder.weight          # feature-major storage: rows = decoder vectors
             entries.append((p.data, g, st["exp_avg"], st["exp_avg_sq"], d if is_dec else 0))
         ops.adamw_multi_(entries, self.hyper, self.sumsq, 1e-12)   # clip + AdamW + decoder renorm
-        s = self.state
-        s.idx, s.val, s.resid, s.stats, s.w_dec_used, s.rows_total = idx, val, resid, self.stats, w_used, rows_total
-        s.d_out = d
 
     def run(self, batch: Tensor) -> None:
         tr = self.trainer
@@ -240,6 +251,9 @@ class SAETrainer:
         grad_scaler: bool = False,
         fused_optimizer: bool | None = None,
         cuda_graph: bool | None = None,
+        data_parallel: bool = False,
+        dp_comm=None,
+        global_batch_rows: int | None = None,
     ):
         self.model = model.to(device)
         self.config = config
@@ -272,6 +286,17 @@ class SAETrainer:
         self.cuda_graph = cuda_graph if (cuda_graph and self.fused_optimizer
                                          and not self.scaler.is_enabled()) else False
         self._graphs: dict[int, _GraphedStep] = {}
+        # batch-sharded data parallel (sae/parallel.py): every rank passes its own row shard to
+        # train_step; gradients, stats and fired stamps are all-reduced inside the step
+        self.data_parallel = bool(data_parallel)
+        self.dp_comm = None
+        self.global_batch_rows = global_batch_rows     # default: local rows x world (equal shards)
+        if self.data_parallel:
+            from .parallel import TorchDistCommunicator
+            self.dp_comm = dp_comm if dp_comm is not None else TorchDistCommunicator()
+            if not (is_cuda and self.fused_optimizer) or self.scaler.is_enabled():
+                raise RuntimeError("data_parallel=True needs the fused CUDA step (no GradScaler)")
+            self.cuda_graph = "eager"       # collectives between the kernels: launch them one by one
 
     # ------------------------------------------------------------------ resampling plumbing
     def set_resample_dataset(self, dataset: torch.utils.data.Dataset) -> None:
@@ -352,6 +377,10 @@ class SAETrainer:
         self.model.train()
         if isinstance(batch, (tuple, list)):
             batch = batch[0]
+        if self.data_parallel:
+            if not self._graph_ok(batch):
+                raise RuntimeError("data_parallel=True supports the fused TopKSAE step only")
+            self.model._global_rows = self.global_batch_rows or batch.shape[0] * self.dp_comm.world
         if self._graph_ok(batch):
             gs = self._graphs.get(batch.shape[0])
             if gs is None:
@@ -402,7 +431,8 @@ class SAETrainer:
             sse = raw[:1].view(torch.float64).item()
             d_out = st.d_out
             loss = float(torch.tensor(sse / (float(st.rows_total) * d_out), dtype=torch.float32))
-            l0 = float(torch.tensor(raw[1].item() / float(rows), dtype=torch.float32))
+            l0_rows = st.rows_total if self.data_parallel else rows
+            l0 = float(torch.tensor(raw[1].item() / float(l0_rows), dtype=torch.float32))
             hidden_dim = self.model.feature_last_activated.numel()
             dead = float(torch.tensor(raw[2].item(), dtype=torch.float32) / hidden_dim)
             return TrainingMetrics(loss, loss, 0.0, l0, dead, lr, self.global_step)
