@@ -36,8 +36,24 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+# Workloads (BASELINE.json configs): "tiny" = configs[1] (headline; N GPUs train N independent layer
+# SAEs, no collective); "small-dp" / "large-dp" = configs[2] / [3]: one SAE, global batch sharded over
+# the ranks, gradients all-reduced with NCCL (strong scaling).
+WORKLOADS = {
+    "tiny": dict(label="whisper-tiny", d=384, expansion=8, k=32, dp=False, cfg="configs[1]"),
+    "small-dp": dict(label="whisper-small", d=768, expansion=8, k=32, dp=True, cfg="configs[2]"),
+    "large-dp": dict(label="whisper-large-v3", d=1280, expansion=32, k=32, dp=True, cfg="configs[3]"),
+}
 D_MODEL, EXPANSION, TOPK = 384, 8, 32
 HIDDEN = D_MODEL * EXPANSION
+
+
+def set_workload(name: str) -> dict:
+    global D_MODEL, EXPANSION, TOPK, HIDDEN
+    w = WORKLOADS[name]
+    D_MODEL, EXPANSION, TOPK = w["d"], w["expansion"], w["k"]
+    HIDDEN = D_MODEL * EXPANSION
+    return w
 METRIC = "sae_train_step_activation_rows_per_sec"
 UNIT = "rows/s"
 
@@ -158,17 +174,21 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi"}
 
 
-def make_trainer(batch: int, device: str, layer_seed: int, use_amp: bool = True, cuda_graph=None):
+def make_trainer(batch: int, device: str, layer_seed: int, use_amp: bool = True, cuda_graph=None,
+                 data_parallel: bool = False):
     from whisper_sae_b200.config import ExperimentConfig
     from whisper_sae_b200.sae import SAETrainer, create_sae
 
     cfg = ExperimentConfig.from_yaml(ROOT / "configs" / "tiny_default.yaml")
     cfg.training.batch_size = batch
     cfg.training.use_amp = use_amp
+    cfg.sae.expansion_factor = EXPANSION
+    cfg.sae.k = TOPK
     torch.manual_seed(cfg.training.seed + layer_seed)
-    sae = create_sae(cfg.sae, cfg.whisper.hidden_dim)
+    sae = create_sae(cfg.sae, D_MODEL)
     run_dir = Path(tempfile.mkdtemp(prefix="wsae_bench_"))
-    tr = SAETrainer(sae, cfg.training, device=device, run_dir=run_dir, cuda_graph=cuda_graph)
+    tr = SAETrainer(sae, cfg.training, device=device, run_dir=run_dir, cuda_graph=cuda_graph,
+                    data_parallel=data_parallel)
     tr.setup_scheduler(100_000)
     return tr, cfg
 
@@ -354,12 +374,19 @@ def run_reference_arm(args) -> None:
 
 
 def workload_config(args, n_gpus: int) -> dict:
+    w = WORKLOADS[args.workload]
+    if w["dp"] and n_gpus > 1:
+        par = f"batch sharded over {n_gpus} GPUs, NCCL all-reduce of the gradient bucket"
+    elif n_gpus > 1:
+        par = "1 SAE (layer) per GPU, no data-path collective"
+    else:
+        par = "single GPU"
     return {
-        "workload": f"whisper-tiny TopKSAE {D_MODEL}->{HIDDEN} k={TOPK} train step "
-                    f"(configs/tiny_default.yaml hyper-parameters; BASELINE.json configs[1])",
+        "workload": f"{w['label']} TopKSAE {D_MODEL}->{HIDDEN} k={TOPK} train step "
+                    f"(configs/tiny_default.yaml hyper-parameters; BASELINE.json {w['cfg']})",
         "batch_rows_per_gpu": args.batch,
         "global_batch_rows": args.batch * n_gpus,
-        "parallelism": "1 SAE (layer) per GPU, no data-path collective" if n_gpus > 1 else "single GPU",
+        "parallelism": par,
         "precision_mode": args.precision,
         "l2_policy": f"{args.resident_batches} distinct resident batches cycled "
                      f"({args.resident_batches * args.batch * D_MODEL * 4 / 2**20:.0f} MiB > 126 MiB L2)",
@@ -372,7 +399,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="tiny")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="rows per GPU per step (default 65536; dp workloads: global 65536 / N)")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--resident-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -381,6 +410,12 @@ def main() -> None:
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    wl = set_workload(args.workload)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.batch is None:
+        args.batch = 65536 // world_env if wl["dp"] else 65536
+        if args.workload == "large-dp":
+            args.batch = 32768 // world_env
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -401,7 +436,9 @@ def main() -> None:
     from whisper_sae_b200 import ops
 
     peaks, peak_src = load_peaks()
-    tr, cfg = make_trainer(args.batch, dev, layer_seed=rank, use_amp=(args.precision == "bf16"))
+    dp = wl["dp"] and dist_on
+    tr, cfg = make_trainer(args.batch, dev, layer_seed=0 if dp else rank,
+                           use_amp=(args.precision == "bf16"), data_parallel=dp)
     nb = max(2, args.resident_batches)
     rows = synth(nb * args.batch, D_MODEL, seed=1234 + rank)
     dev_batches = [rows[i * args.batch:(i + 1) * args.batch].to(dev) for i in range(nb)]
@@ -430,7 +467,7 @@ def main() -> None:
     if rank == 0:
         # per-kernel CUDA-event timing needs eager launches: same kernels, graph replay switched off
         tr_eager, _ = make_trainer(args.batch, dev, layer_seed=rank, use_amp=(args.precision == "bf16"),
-                                   cuda_graph="eager")
+                                   cuda_graph="eager")       # single-rank kernels (no collective)
         for i in range(3):
             tr_eager.train_step(dev_batches[i % nb])
         prof = kernel_profile(tr_eager, dev_batches, min(args.steps, 20))
@@ -446,7 +483,7 @@ def main() -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong" if wl["dp"] else "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(args, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": args.batch * D_MODEL * 4,
