@@ -11,7 +11,8 @@ configs/tiny_default.yaml (lr 1e-4, warm-up 1000, clip 1.0, AMP on => bf16 path)
 row-standardised Gaussian activations.  One "step" = one `SAETrainer.train_step`
 (pack, tcgen05 GEMM + fused TopK, sparse decode + MSE, sparse backward, clip + AdamW, decoder
 renorm, counters, stats readback).  The YAML batch (128) is launch-latency bound by construction,
-so the headline batch is `--batch` (default 65536, config-legal: TrainingConfig.batch_size >= 1);
+so the headline batch is `--batch` (default 75776 = 4 waves of 148 x 128-row tiles; config-legal:
+TrainingConfig.batch_size >= 1);
 the YAML-batch number is reported next to it as `yaml_batch`.
 
 N > 1: one process per GPU, each training an independent layer's SAE (4 encoder + 4 decoder
@@ -401,7 +402,8 @@ def main() -> None:
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="tiny")
     ap.add_argument("--batch", type=int, default=None,
-                    help="rows per GPU per step (default 65536; dp workloads: global 65536 / N)")
+                    help="rows per GPU per step (default 75776 = 148 SMs x 128 rows x 4; dp workloads: "
+                         "that global batch / N)")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--resident-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -413,9 +415,11 @@ def main() -> None:
     wl = set_workload(args.workload)
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     if args.batch is None:
-        args.batch = 65536 // world_env if wl["dp"] else 65536
+        # K1 walks the batch in 128-row tiles on 148 persistent CTAs: 148 * 128 * 4 = 75776 rows is
+        # exactly four waves (65536 would be 3.46 -> 4 waves with a 14 % idle tail)
+        args.batch = 75776 // world_env if wl["dp"] else 75776
         if args.workload == "large-dp":
-            args.batch = 32768 // world_env
+            args.batch = 37888 // world_env
 
     if args.impl == "reference":
         run_reference_arm(args)

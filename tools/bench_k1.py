@@ -25,9 +25,13 @@ def main() -> None:
     ap.add_argument("--batches", default="16384,65536")
     ap.add_argument("--modes", default="0,1,2")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--counters", action="store_true")
+    ap.add_argument("--variant", type=int, default=2, help="1 = one epilogue warp per quarter, 2 = scanner + selector")
     args = ap.parse_args()
     lib = _lib.load()
     lib.wsae_debug_encode_mode.argtypes = [ctypes.c_int]
+    lib.wsae_debug_encode_variant.argtypes = [ctypes.c_int]
+    lib.wsae_debug_encode_variant(args.variant)
     dev = "cuda"
     torch.manual_seed(0)
     w = torch.randn(args.F, args.d, device=dev) / args.d ** 0.5
@@ -52,6 +56,20 @@ def main() -> None:
             print(f"B={B} d={args.d} F={args.F} k={args.k} mode={mode}: {ms * 1e3:8.1f} us  "
                   f"{tf:7.1f} TFLOP/s (algorithmic)  {B / ms / 1e3:8.2f} Mrows/s", flush=True)
         lib.wsae_debug_encode_mode(0)
+        if args.counters:     # scanner / selector wait breakdown of the v2 epilogue (one launch)
+            lib.wsae_debug_encode_counters.argtypes = [ctypes.c_void_p]
+            buf = torch.zeros(148 * 8 * 8, dtype=torch.int64, device=dev)
+            lib.wsae_debug_encode_counters(buf.data_ptr())
+            ops.encode_topk(xs[0], wp, B, args.F, args.d, 1, args.k)
+            torch.cuda.synchronize()
+            lib.wsae_debug_encode_counters(None)
+            c = buf.view(148, 8, 8).double()
+            items = B / 128 / 148
+            sc, se = c[:, :4], c[:, 4:]
+            print(f"  scanner : handoffs/item {sc[..., 0].mean() / items:6.1f}  wait-empty {sc[..., 1].mean() / items:9.0f} cyc/item"
+                  f"  wait-tmem {sc[..., 2].mean() / items:9.0f}  total {sc[..., 3].mean() / items:9.0f}")
+            print(f"  selector: selections/item {se[..., 0].mean() / items:6.1f}  wait-full {se[..., 1].mean() / items:9.0f} cyc/item"
+                  f"  total {se[..., 3].mean() / items:9.0f}", flush=True)
         del xs
 
 

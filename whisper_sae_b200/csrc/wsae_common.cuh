@@ -106,6 +106,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait with back-off: for hand-shakes between two warps that share an SM sub-partition, where a
+// tight try_wait loop would steal issue slots from the very warp it is waiting for.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(100);
+    if (++spins > WSAE_SPIN_LIMIT) __trap();
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — 2D tiled load, completion on an mbarrier
 // ----------------------------------------------------------------------------------------------

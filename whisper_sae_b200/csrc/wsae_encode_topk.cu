@@ -39,6 +39,7 @@ constexpr int kAStage = kBM * kBK * 2;
 constexpr int kBStage = kBN * kBK * 2;
 constexpr int kChunk = 16;  // accumulator columns per tcgen05.ld
 constexpr int kSlack = 8;   // intermediate selects may keep up to k + kSlack candidates
+constexpr int kCheck = 8;   // list-overflow check every kCheck appended-or-not values
 
 template <int CAP, int STAGES>
 struct EncodeSmem {
@@ -218,6 +219,143 @@ __device__ __noinline__ void topk_compact(uint32_t wbase, uint32_t& waddr, float
   }
 }
 
+// End of a work item: reduce the list to exactly k entries and write them to global memory.
+// After one ordinary compaction (<= k + kSlack survivors) the few surplus entries are removed by
+// repeated min-extraction in registers - much cheaper than bisecting down to adjacent float keys.
+// Ties at the k-th value keep the lowest feature index: among equal minima the LAST list slot
+// (highest index; the list is in ascending index order) is dropped first.
+template <int CAP, int KMAX>
+__device__ __noinline__ void topk_finalize(uint32_t wbase, uint32_t waddr, float tau, int k,
+                                           float* __restrict__ out_val,
+                                           int32_t* __restrict__ out_idx, bool write) {
+  constexpr int NB = KMAX + kSlack;
+  const float ninf = __uint_as_float(0xff800000u);
+  const float pinf = __uint_as_float(0x7f800000u);
+  if (__any_sync(0xffffffffu, waddr > wbase + static_cast<uint32_t>(k + kSlack) * (kBM * 4)))
+    topk_compact<CAP>(wbase, waddr, tau, k, kSlack);
+  const uint32_t used = waddr - wbase;
+  int surplus = static_cast<int>(used / (kBM * 4)) - k;     // <= kSlack; negative: fewer than k
+  float v[NB];
+#pragma unroll
+  for (int s = 0; s < NB; ++s) {
+    const float x = lds_f32(wbase + s * (kBM * 4));
+    v[s] = (static_cast<uint32_t>(s * (kBM * 4)) < used) ? x : pinf;   // +inf = not a candidate
+  }
+  while (__any_sync(0xffffffffu, surplus > 0)) {
+    float vmin = pinf;
+    int pos = -1;
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+      const bool le = v[s] <= vmin && v[s] != pinf;
+      vmin = le ? v[s] : vmin;
+      pos = le ? s : pos;
+    }
+    if (surplus <= 0) pos = -1;
+#pragma unroll
+    for (int s = 0; s < NB; ++s) v[s] = (s == pos) ? pinf : v[s];
+    --surplus;
+  }
+  if (write) {
+    int w = 0;
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+      if (v[s] != pinf && w < k) {
+        uint32_t ix;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ix) : "r"(wbase + s * (kBM * 4) + CAP * kBM * 4) : "memory");
+        out_val[w] = v[s];
+        out_idx[w] = static_cast<int32_t>(ix);
+        ++w;
+      }
+    }
+    for (; w < k; ++w) {   // fewer than k candidates (split narrower than k, NaN rows): pad
+      out_val[w] = ninf;
+      out_idx[w] = -1;
+    }
+  }
+}
+
+// Work decomposition shared by every role of the GEMM pipeline.
+struct EncodeItems {
+  int total_items, nsplit, tiles_per_split, num_n_tiles, num_kb, ksteps;
+};
+
+// TMA producer (one elected lane): streams A' 128x64 and W' 256x64 boxes through the stage ring.
+template <int STAGES>
+__device__ __forceinline__ void encode_producer_loop(const CUtensorMap* tmap_a,
+                                                     const CUtensorMap* tmap_w, uint8_t* pipe,
+                                                     uint64_t* full_bar, uint64_t* empty_bar,
+                                                     const EncodeItems& it) {
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int item = blockIdx.x; item < it.total_items; item += gridDim.x) {
+    const int m_blk = item / it.nsplit;
+    const int sp = item - m_blk * it.nsplit;
+    const int t0 = sp * it.tiles_per_split;
+    const int t1 = min(t0 + it.tiles_per_split, it.num_n_tiles);
+    for (int nt = t0; nt < t1; ++nt) {
+      for (int kb = 0; kb < it.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[stage], kAStage + kBStage);
+        uint8_t* sa = pipe + stage * (kAStage + kBStage);
+        tma_load_2d(sa, tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+        tma_load_2d(sa + kAStage, tmap_w, &full_bar[stage], kb * kBK, nt * kBN);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  }
+}
+
+// MMA issuer (whole warp; one elected lane issues): 128x256x16 tcgen05.mma into the double-buffered
+// TMEM accumulators.
+template <int STAGES>
+__device__ __forceinline__ void encode_mma_loop(uint8_t* pipe, uint64_t* full_bar,
+                                                uint64_t* empty_bar, uint64_t* tfull_bar,
+                                                uint64_t* tempty_bar, uint32_t tmem_base,
+                                                const EncodeItems& it) {
+  constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN);
+  int stage = 0;
+  uint32_t phase = 0;
+  uint32_t tile = 0;
+  for (int item = blockIdx.x; item < it.total_items; item += gridDim.x) {
+    const int m_blk = item / it.nsplit;
+    const int sp = item - m_blk * it.nsplit;
+    const int t0 = sp * it.tiles_per_split;
+    const int t1 = min(t0 + it.tiles_per_split, it.num_n_tiles);
+    for (int nt = t0; nt < t1; ++nt, ++tile) {
+      const uint32_t as = tile & 1u;
+      const uint32_t aphase = (tile >> 1) & 1u;
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * kBN;
+      for (int kb = 0; kb < it.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(pipe + stage * (kAStage + kBStage));
+          const uint64_t da = umma_desc_sw128_kmajor(sa);
+          const uint64_t db = umma_desc_sw128_kmajor(sa + kAStage);
+          const int nks = min(kBK / 16, it.ksteps - kb * (kBK / 16));
+          for (int ks = 0; ks < nks; ++ks) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * ks), db + static_cast<uint64_t>(2 * ks),
+                      idesc, (kb | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == it.num_kb - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  }
+}
+
 template <int CAP, int STAGES>
 __global__ void __launch_bounds__(256, 1)
 encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -243,6 +381,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int lane = threadIdx.x & 31;
   const int num_kb = ceil_div(ksteps, kBK / 16);
   const int total_items = num_m_blocks * nsplit;
+  const EncodeItems items{total_items, nsplit, tiles_per_split, num_n_tiles, num_kb, ksteps};
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -270,70 +409,10 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int m_blk = item / nsplit;
-        const int sp = item - m_blk * nsplit;
-        const int t0 = sp * tiles_per_split;
-        const int t1 = min(t0 + tiles_per_split, num_n_tiles);
-        for (int nt = t0; nt < t1; ++nt) {
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[stage], kAStage + kBStage);
-            uint8_t* sa = pipe + stage * (kAStage + kBStage);
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
-            tma_load_2d(sa + kAStage, &tmap_w, &full_bar[stage], kb * kBK, nt * kBN);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-        }
-      }
-    }
+    if (elect_one()) encode_producer_loop<STAGES>(&tmap_a, &tmap_w, pipe, full_bar, empty_bar, items);
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN);
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t tile = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int m_blk = item / nsplit;
-      const int sp = item - m_blk * nsplit;
-      const int t0 = sp * tiles_per_split;
-      const int t1 = min(t0 + tiles_per_split, num_n_tiles);
-      for (int nt = t0; nt < t1; ++nt, ++tile) {
-        const uint32_t as = tile & 1u;
-        const uint32_t aphase = (tile >> 1) & 1u;
-        mbar_wait(&tempty_bar[as], aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * kBN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t sa = smem_u32(pipe + stage * (kAStage + kBStage));
-            const uint64_t da = umma_desc_sw128_kmajor(sa);
-            const uint64_t db = umma_desc_sw128_kmajor(sa + kAStage);
-            const int nks = min(kBK / 16, ksteps - kb * (kBK / 16));
-            for (int ks = 0; ks < nks; ++ks) {
-              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * ks), db + static_cast<uint64_t>(2 * ks),
-                        idesc, (kb | ks) != 0 ? 1u : 0u);
-            }
-            umma_commit(&empty_bar[stage]);
-            if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
-          }
-          __syncwarp();
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-      }
-    }
+    encode_mma_loop<STAGES>(pipe, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, items);
   } else if (warp >= 4) {
     // ===================== epilogue: streaming TopK =====================
     const int q = warp - 4;               // TMEM lane quarter this warp may read
@@ -342,7 +421,8 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t* ci = cand_idx + row_in_blk;
     const float neg_inf = __uint_as_float(0xff800000u);
     const uint32_t wbase = smem_u32(cv);                           // list cursor = byte address
-    const uint32_t wlimit = wbase + (CAP - kChunk) * (kBM * 4);    // a full chunk must still fit
+    // the overflow check runs every kCheck values: kCheck more must always fit
+    const uint32_t wlimit = wbase + (CAP - kCheck) * (kBM * 4);
     uint32_t tile = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int m_blk = item / nsplit;
@@ -404,9 +484,14 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   "r"(static_cast<uint32_t>(cbase + j)), "n"(CAP * kBM * 4), "n"(kBM * 4)
                 : "memory");
             waddr = wnext;
+            if ((j + 4) % kCheck == 0) {
+              if (dbg == 2) {
+                if (waddr > wlimit) waddr = wbase;
+              } else if (__any_sync(0xffffffffu, waddr > wlimit)) {
+                topk_compact<CAP>(wbase, waddr, tau, k, kSlack);
+              }
+            }
           }
-          if (dbg == 2) { if (waddr > wlimit) waddr = wbase; return; }
-          if (__any_sync(0xffffffffu, waddr > wlimit)) topk_compact<CAP>(wbase, waddr, tau, k, kSlack);
         };
 
         // Every tile is scanned in full: columns >= F are padding rows of W' (never selected).
@@ -435,21 +520,468 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_arrive(&tempty_bar[as]);
       }
       // ---- end of work item: exact select, write k (val, idx) pairs for this row/split ----
-      topk_compact<CAP>(wbase, waddr, tau, k, 0);
-      const int cnt = static_cast<int>((waddr - wbase) / (kBM * 4));
       const int row = m_blk * kBM + row_in_blk;
-      if (row < B) {
-        const size_t base = (static_cast<size_t>(row) * nsplit + sp) * k;
-        for (int s = 0; s < k; ++s) {
-          if (s < cnt) {
-            out_val[base + s] = cv[s * kBM];
-            out_idx[base + s] = static_cast<int32_t>(ci[s * kBM]);
-          } else {  // split narrower than k columns: pad with never-selected entries
-            out_val[base + s] = neg_inf;
-            out_idx[base + s] = -1;
+      const size_t obase = (static_cast<size_t>(row < B ? row : 0) * nsplit + sp) * k;
+      topk_finalize<CAP, (CAP >= 128 ? 64 : 32)>(wbase, waddr, tau, k, out_val + obase,
+                                                 out_idx + obase, row < B);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================
+// K1, second epilogue organisation: SCANNER + SELECTOR warps (used for k <= 32).
+//
+// In the kernel above one epilogue warp per SM sub-partition does everything and issues only
+// ~0.4 instructions per cycle (fixed-latency dependency stalls; profiles/r1_v3_k1_*.txt), while
+// its list compactions cost as much as the scan itself.  Here each 32-row TMEM lane quarter is
+// served by TWO warps on the same sub-partition that run concurrently:
+//   * the scanner (warps 4-7) reads the accumulators from TMEM and appends every value above its
+//     row threshold tau to a 40-slot FIFO in shared memory - nothing else;
+//   * the selector (warps 8-11) keeps the row's current <= k+8 survivors in REGISTERS, merges
+//     each handed-over FIFO batch into them (bisection select, repack through the FIFO it just
+//     drained), publishes the raised tau back to the scanner, and at the end of the work item
+//     reduces to exactly k and writes the result.
+// Two FIFO buffers per quarter ping-pong between the two warps on mbarriers (full / empty), so
+// scanning batch n+1 overlaps selecting batch n.  A stale (lower) tau in the scanner only lets a
+// few more candidates through: the result is unchanged and exact.
+// Registers: 384 threads; setmaxnreg moves registers from the producer/MMA warpgroup to the
+// selector warpgroup (which holds 80 values + 80 indices per thread).
+// ================================================================================================
+constexpr int kFifo = 40;                          // slots per FIFO buffer (>= k + kSlack)
+constexpr int kFifoBytes = kFifo * kBM * 4;        // one buffer of one array: 20480 B
+constexpr int kFifoIdxOff = 2 * kFifoBytes;        // idx array sits behind both value buffers
+
+template <int STAGES>
+struct Encode2Smem {
+  static constexpr int kPipeBytes = STAGES * (kAStage + kBStage);
+  static constexpr int kFifoTotal = 4 * kFifoBytes;             // 2 buffers x (val + idx)
+  static constexpr int kTauBytes = kBM * 8;                     // {tau, item seq} per row
+  static constexpr int kCntBytes = 2 * kBM * 2;                 // entries per row per buffer (u16)
+  static constexpr int kBarBytes = 256;
+  static_assert((2 * STAGES + 20) * 8 + 8 + 32 <= kBarBytes, "barrier block too small");
+  static constexpr int kTotal = kPipeBytes + kFifoTotal + kTauBytes + kCntBytes + kBarBytes + 1024;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB shared-memory limit");
+};
+
+template <int REGS>
+__device__ __forceinline__ void reg_alloc_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+template <int REGS>
+__device__ __forceinline__ void reg_alloc_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+
+// Predicated append of four (value, index) pairs at cursor w; IOFF = byte offset of the index array.
+template <int IOFF>
+__device__ __forceinline__ uint32_t append4(uint32_t w, float thr, float v0, float v1, float v2,
+                                            float v3, uint32_t i0, uint32_t i1, uint32_t i2,
+                                            uint32_t i3) {
+  uint32_t wn;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, p1, p2, p3;\n\t"
+      ".reg .u32 a1, a2, a3, t0, t1, t2, t3;\n\t"
+      "setp.gt.f32 p0, %2, %6;\n\t"
+      "setp.gt.f32 p1, %3, %6;\n\t"
+      "setp.gt.f32 p2, %4, %6;\n\t"
+      "setp.gt.f32 p3, %5, %6;\n\t"
+      "selp.u32 t0, %12, 0, p0;\n\t"
+      "selp.u32 t1, %12, 0, p1;\n\t"
+      "selp.u32 t2, %12, 0, p2;\n\t"
+      "selp.u32 t3, %12, 0, p3;\n\t"
+      "add.u32 a1, %1, t0;\n\t"
+      "add.u32 a2, a1, t1;\n\t"
+      "add.u32 a3, a2, t2;\n\t"
+      "add.u32 %0, a3, t3;\n\t"
+      "@p0 st.shared.f32 [%1], %2;\n\t"
+      "@p0 st.shared.u32 [%1+%11], %7;\n\t"
+      "@p1 st.shared.f32 [a1], %3;\n\t"
+      "@p1 st.shared.u32 [a1+%11], %8;\n\t"
+      "@p2 st.shared.f32 [a2], %4;\n\t"
+      "@p2 st.shared.u32 [a2+%11], %9;\n\t"
+      "@p3 st.shared.f32 [a3], %5;\n\t"
+      "@p3 st.shared.u32 [a3+%11], %10;\n\t"
+      "}\n"
+      : "=r"(wn)
+      : "r"(w), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(thr), "r"(i0), "r"(i1), "r"(i2), "r"(i3),
+        "n"(IOFF), "n"(kBM * 4)
+      : "memory");
+  return wn;
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Threshold such that k <= count(v > thr) <= k + slack over the N register-resident candidates
+// (-inf entries are padding).  Same bisection as topk_compact.  If the candidates tie across the
+// k-th position beyond the slack, `ties` is set and thr is the tie value: keep everything above it
+// plus the first `tie_left` ties in list order.
+template <int N>
+__device__ __forceinline__ float select_threshold(const float (&v)[N], int total, int k, int slack,
+                                                  float tau, bool& ties, int& tie_left) {
+  const float ninf = __uint_as_float(0xff800000u);
+  const float pinf = __uint_as_float(0x7f800000u);
+  const bool keep_all = total <= k + slack;
+  float vmax = ninf;
+#pragma unroll
+  for (int s = 0; s < N; ++s) vmax = fmaxf(vmax, v[s]);
+  uint32_t lo;
+  if (tau == ninf) {
+    float vmin = pinf;
+#pragma unroll
+    for (int s = 0; s < N; ++s) vmin = fminf(vmin, (v[s] == ninf) ? pinf : v[s]);
+    lo = f2key(vmin) - 1u;
+  } else {
+    lo = f2key(tau);
+  }
+  uint32_t hi = f2key(vmax);
+  bool done = keep_all;
+  int it = 0;
+  while (true) {
+    const bool active = !done && (hi - lo > 1u);
+    if (!__any_sync(0xffffffffu, active)) break;
+    const uint32_t span = hi - lo;
+    const uint32_t step = max(1u, span >> (it < 2 ? 2 : 1));
+    ++it;
+    const uint32_t mid = lo + step;
+    const float midf = key2f(mid);
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+    for (int s = 0; s < N; s += 4) {
+      c0 += (v[s] > midf) ? 1.f : 0.f;
+      c1 += (v[s + 1] > midf) ? 1.f : 0.f;
+      c2 += (v[s + 2] > midf) ? 1.f : 0.f;
+      c3 += (v[s + 3] > midf) ? 1.f : 0.f;
+    }
+    const int c = static_cast<int>((c0 + c1) + (c2 + c3));
+    if (active) {
+      if (c >= k) {
+        lo = mid;
+        done = (c <= k + slack);
+      } else {
+        hi = mid;
+      }
+    }
+  }
+  ties = !done;
+  tie_left = 0;
+  const float thrf = keep_all ? ninf : key2f(done ? lo : hi);
+  if (ties) {
+    int m = 0;
+#pragma unroll
+    for (int s = 0; s < N; ++s) m += (v[s] > thrf) ? 1 : 0;
+    tie_left = k - m;
+  }
+  return thrf;
+}
+
+template <int STAGES, bool DBG>
+__global__ void __launch_bounds__(384, 1)
+encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_w, int B, int F, int k, int ksteps,
+                    int num_m_blocks, int num_n_tiles, int nsplit, int tiles_per_split,
+                    float* __restrict__ out_val, int32_t* __restrict__ out_idx,
+                    unsigned long long* __restrict__ dbg) {
+  using SM = Encode2Smem<STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* pipe = smem;
+  uint8_t* fifo = smem + SM::kPipeBytes;
+  uint8_t* tau_s = fifo + SM::kFifoTotal;
+  uint8_t* cnt_s = tau_s + SM::kTauBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cnt_s + SM::kCntBytes);
+  uint64_t* full_bar = bars;                        // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;              // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;          // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;     // [2]
+  uint64_t* ffull_bar = bars + 2 * STAGES + 4;      // [2 buffers][4 quarters]
+  uint64_t* fempty_bar = bars + 2 * STAGES + 12;    // [2][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
+  uint32_t* meta = tmem_slot + 2;                   // [2][4]: 1 = last hand-over of the work item
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = ceil_div(ksteps, kBK / 16);
+  const int total_items = num_m_blocks * nsplit;
+  const EncodeItems items{total_items, nsplit, tiles_per_split, num_n_tiles, num_kb, ksteps};
+  const float neg_inf = __uint_as_float(0xff800000u);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kBM);
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&ffull_bar[s], 32);
+      mbar_init(&fempty_bar[s], 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kBM * 2; i += blockDim.x) reinterpret_cast<uint32_t*>(tau_s)[i] = 0u;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    reg_alloc_dec<56>();
+    if (warp == 0) {
+      if (elect_one()) encode_producer_loop<STAGES>(&tmap_a, &tmap_w, pipe, full_bar, empty_bar, items);
+    } else if (warp == 1) {
+      encode_mma_loop<STAGES>(pipe, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, items);
+    }
+  } else if (warp < 8) {
+    // ===================== scanner =====================
+    reg_alloc_dec<152>();
+    const int q = warp - 4;
+    const int row_in_blk = q * 32 + lane;
+    const uint32_t fv0 = smem_u32(fifo) + row_in_blk * 4;          // buffer 0, slot 0 of this row
+    const uint32_t tau_addr = smem_u32(tau_s) + row_in_blk * 8;
+    const uint32_t cnt_addr = smem_u32(cnt_s) + row_in_blk * 2;
+    uint32_t fills0 = 0, fills1 = 0, b = 0, seq = 0, tile = 0;
+    unsigned long long d_hand = 0, d_wait_e = 0, d_wait_t = 0;
+    const long long d_t0 = clock64();
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int sp = item - (item / nsplit) * nsplit;
+      const int t0 = sp * tiles_per_split;
+      const int t1 = min(t0 + tiles_per_split, num_n_tiles);
+      ++seq;
+      float tau = neg_inf;
+      mbar_wait_backoff(&fempty_bar[b * 4 + q], ((b ? fills1 : fills0) & 1u) ^ 1u);
+      uint32_t wbase = fv0 + b * kFifoBytes;
+      uint32_t waddr = wbase;
+      uint32_t wlimit = wbase + (kFifo - kCheck) * (kBM * 4);
+
+      auto handoff = [&](uint32_t last) {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(cnt_addr + b * (kBM * 2)),
+                     "h"(static_cast<unsigned short>((waddr - wbase) / (kBM * 4)))
+                     : "memory");
+        if (lane == 0) meta[b * 4 + q] = last;
+        mbar_arrive(&ffull_bar[b * 4 + q]);
+        if (b) ++fills1; else ++fills0;
+        b ^= 1u;
+        ++d_hand;
+        if (!last) {
+          const long long t = DBG ? clock64() : 0;
+          mbar_wait_backoff(&fempty_bar[b * 4 + q], ((b ? fills1 : fills0) & 1u) ^ 1u);
+          if (DBG) d_wait_e += clock64() - t;
+        }
+        wbase = fv0 + b * kFifoBytes;
+        waddr = wbase;
+        wlimit = wbase + (kFifo - kCheck) * (kBM * 4);
+      };
+
+      for (int nt = t0; nt < t1; ++nt, ++tile) {
+        const uint32_t as = tile & 1u;
+        const uint32_t aphase = (tile >> 1) & 1u;
+        {
+          const long long t = DBG ? clock64() : 0;
+          mbar_wait(&tfull_bar[as], aphase);
+          if (DBG) d_wait_t += clock64() - t;
+        }
+        tc_fence_after();
+        const int col0 = nt * kBN;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBN;
+
+        auto process = [&](uint32_t (&r)[16], int cbase) {
+#pragma unroll
+          for (int j = 0; j < kChunk; j += 4) {
+            const uint32_t c = static_cast<uint32_t>(cbase + j);
+            waddr = append4<kFifoIdxOff>(waddr, tau, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]), c,
+                                         c + 1, c + 2, c + 3);
+            if ((j + 4) % kCheck == 0) {
+              if (__any_sync(0xffffffffu, waddr > wlimit)) handoff(0u);
+            }
+          }
+        };
+
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr, ra);
+#pragma unroll 1
+        for (int c4 = 0; c4 < kBN / 64; ++c4) {
+          const uint32_t ta = taddr + c4 * 64;
+          const int cb = col0 + c4 * 64;
+          uint32_t tb, tq;   // the selector's latest threshold for this row (valid for this item only)
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tb), "=r"(tq) : "r"(tau_addr) : "memory");
+          tmem_ld_wait16(ra);
+          tmem_ld16(ta + 16, rb);
+          if (tq == seq) tau = fmaxf(tau, __uint_as_float(tb));
+          process(ra, cb);
+          tmem_ld_wait16(rb);
+          tmem_ld16(ta + 32, ra);
+          process(rb, cb + 16);
+          tmem_ld_wait16(ra);
+          tmem_ld16(ta + 48, rb);
+          process(ra, cb + 32);
+          tmem_ld_wait16(rb);
+          if (c4 + 1 < kBN / 64) tmem_ld16(ta + 64, ra);
+          process(rb, cb + 48);
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+      }
+      handoff(1u);
+    }
+    if (DBG && dbg && lane == 0) {
+      unsigned long long* o = dbg + (static_cast<size_t>(blockIdx.x) * 8 + (warp - 4)) * 8;
+      o[0] = d_hand; o[1] = d_wait_e; o[2] = d_wait_t; o[3] = clock64() - d_t0;
+    }
+  } else {
+    // ===================== selector =====================
+    reg_alloc_inc<232>();
+    const int q = warp - 8;
+    const int row_in_blk = q * 32 + lane;
+    const uint32_t fv0 = smem_u32(fifo) + row_in_blk * 4;
+    const uint32_t tau_addr = smem_u32(tau_s) + row_in_blk * 8;
+    const uint32_t cnt_addr = smem_u32(cnt_s) + row_in_blk * 2;
+    constexpr int N = 2 * kFifo;
+    float v[N];          // [0, kFifo): survivors, [kFifo, N): the batch being merged
+    uint32_t ix[N];
+    uint32_t uses0 = 0, uses1 = 0, b = 0, seq = 0;
+    unsigned long long d_wait_f = 0, d_sel = 0;
+    const long long d_t0 = clock64();
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int m_blk = item / nsplit;
+      const int sp = item - m_blk * nsplit;
+      ++seq;
+      float tau = neg_inf;
+      int scnt = 0;
+#pragma unroll
+      for (int s = 0; s < kFifo; ++s) {
+        v[s] = neg_inf;
+        ix[s] = 0u;
+      }
+      while (true) {
+        {
+          const long long t = DBG ? clock64() : 0;
+          mbar_wait_backoff(&ffull_bar[b * 4 + q], (b ? uses1 : uses0) & 1u);
+          if (DBG) d_wait_f += clock64() - t;
+        }
+        const uint32_t base = fv0 + b * kFifoBytes;
+        unsigned short n16;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(n16) : "r"(cnt_addr + b * (kBM * 2)) : "memory");
+        const int n = static_cast<int>(n16);
+        const uint32_t last = meta[b * 4 + q];
+#pragma unroll
+        for (int s = 0; s < kFifo; ++s) {
+          const float x = lds_f32(base + s * (kBM * 4));
+          v[kFifo + s] = (s < n) ? x : neg_inf;
+          ix[kFifo + s] = lds_u32(base + s * (kBM * 4) + kFifoIdxOff);
+        }
+        const int total = scnt + n;
+        float thr = neg_inf;
+        bool ties = false;
+        int tie_left = 0;
+        if (__any_sync(0xffffffffu, total > k + kSlack)) {
+          thr = select_threshold<N>(v, total, k, kSlack, tau, ties, tie_left);
+          ++d_sel;
+        }
+        // repack the survivors (old ones first: ascending feature index) through the drained FIFO
+        uint32_t w = base;
+        if (!__any_sync(0xffffffffu, ties)) {
+#pragma unroll
+          for (int s = 0; s < N; s += 4)
+            w = append4<kFifoIdxOff>(w, thr, v[s], v[s + 1], v[s + 2], v[s + 3], ix[s], ix[s + 1],
+                                     ix[s + 2], ix[s + 3]);
+        } else {
+#pragma unroll
+          for (int s = 0; s < N; ++s) {
+            const bool tie = ties && (v[s] == thr) && tie_left > 0;
+            tie_left -= tie ? 1 : 0;
+            if (v[s] > thr || tie) {
+              asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.u32 [%0+%3], %2;" ::"r"(w), "f"(v[s]),
+                           "r"(ix[s]), "n"(kFifoIdxOff)
+                           : "memory");
+              w += kBM * 4;
+            }
           }
         }
+        scnt = static_cast<int>((w - base) / (kBM * 4));
+#pragma unroll
+        for (int s = 0; s < kFifo; ++s) {
+          const float x = lds_f32(base + s * (kBM * 4));
+          v[s] = (s < scnt) ? x : neg_inf;
+          ix[s] = lds_u32(base + s * (kBM * 4) + kFifoIdxOff);
+        }
+        if (thr > tau) {
+          tau = thr;
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(tau_addr), "r"(__float_as_uint(tau)),
+                       "r"(seq)
+                       : "memory");
+        }
+        mbar_arrive(&fempty_bar[b * 4 + q]);
+        if (b) ++uses1; else ++uses0;
+        b ^= 1u;
+        if (last) break;
       }
+      // ---- exactly k: drop the surplus by min-extraction (ties: highest index goes first) ----
+      const float pinf = __uint_as_float(0x7f800000u);
+      int surplus = scnt - k;
+#pragma unroll
+      for (int s = 0; s < kFifo; ++s) v[s] = (s < scnt) ? v[s] : pinf;
+      while (__any_sync(0xffffffffu, surplus > 0)) {
+        float vmin = pinf;
+        int pos = -1;
+#pragma unroll
+        for (int s = 0; s < kFifo; ++s) {
+          const bool le = v[s] <= vmin && v[s] != pinf;
+          vmin = le ? v[s] : vmin;
+          pos = le ? s : pos;
+        }
+        if (surplus <= 0) pos = -1;
+#pragma unroll
+        for (int s = 0; s < kFifo; ++s) v[s] = (s == pos) ? pinf : v[s];
+        --surplus;
+      }
+      const int row = m_blk * kBM + row_in_blk;
+      if (row < B) {
+        float* ov = out_val + (static_cast<size_t>(row) * nsplit + sp) * k;
+        int32_t* oi = out_idx + (static_cast<size_t>(row) * nsplit + sp) * k;
+        int w = 0;
+#pragma unroll
+        for (int s = 0; s < kFifo; ++s) {
+          if (v[s] != pinf && w < k) {
+            ov[w] = v[s];
+            oi[w] = static_cast<int32_t>(ix[s]);
+            ++w;
+          }
+        }
+        for (; w < k; ++w) {
+          ov[w] = neg_inf;
+          oi[w] = -1;
+        }
+      }
+    }
+    if (DBG && dbg && lane == 0) {
+      unsigned long long* o = dbg + (static_cast<size_t>(blockIdx.x) * 8 + (warp - 4)) * 8;
+      o[0] = d_sel; o[1] = d_wait_f; o[3] = clock64() - d_t0;
     }
   }
 
@@ -595,9 +1127,50 @@ static int launch_encode(const CUtensorMap& ta, const CUtensorMap& tw, int B, in
   return static_cast<int>(cudaGetLastError());
 }
 
+static unsigned long long* g_encode_dbg_buf = nullptr;   // experiments only: [grid][8 warps][8] counters
+
+template <int STAGES>
+static int launch_encode2(const CUtensorMap& ta, const CUtensorMap& tw, int B, int F, int k,
+                          int ksteps, int num_m_blocks, int num_n_tiles, int nsplit,
+                          int tiles_per_split, float* out_val, int32_t* out_idx, int num_sms,
+                          cudaStream_t stream) {
+  constexpr int smem = Encode2Smem<STAGES>::kTotal;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(encode_topk2_kernel<STAGES, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(encode_topk2_kernel<STAGES, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set[dev] = true;
+  }
+  const int total = num_m_blocks * nsplit;
+  const int grid = total < num_sms ? total : num_sms;
+  if (g_encode_dbg_buf != nullptr)
+    encode_topk2_kernel<STAGES, true><<<grid, 384, smem, stream>>>(
+        ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx,
+        g_encode_dbg_buf);
+  else
+    encode_topk2_kernel<STAGES, false><<<grid, 384, smem, stream>>>(
+        ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx,
+        nullptr);
+  return static_cast<int>(cudaGetLastError());
+}
+
+static int g_encode_variant = 2;   // 1 = single epilogue warp per quarter, 2 = scanner + selector
+
 }  // namespace wsae
 
 using namespace wsae;
+
+extern "C" int wsae_debug_encode_variant(int v) { g_encode_variant = v; return 0; }
+extern "C" int wsae_debug_encode_counters(void* buf) {
+  g_encode_dbg_buf = static_cast<unsigned long long*>(buf);
+  return 0;
+}
 
 // See include/wsae.h for the contract.
 extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int B, int Bp, int F,
@@ -630,7 +1203,10 @@ extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int 
   float* kv = nsplit > 1 ? part_val : out_val;
   int32_t* ki = nsplit > 1 ? part_idx : out_idx;
   const int ksteps = k_used_cols / 16;
-  if (k <= 32)
+  if (k + kSlack <= kFifo && g_encode_variant == 2)
+    rc = launch_encode2<3>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
+                           tiles_per_split, kv, ki, num_sms, stream);
+  else if (k <= 32)
     rc = launch_encode<80, 3>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
                               tiles_per_split, kv, ki, num_sms, stream);
   else
