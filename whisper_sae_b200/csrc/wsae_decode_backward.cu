@@ -31,17 +31,21 @@ struct FusedStats {
   unsigned long long l0_count;
 };
 
-// d += bf16(a.lo) * bf16(b.lo)  /  d += bf16(a.hi) * bf16(b.hi)   (fp32 accumulate, SASS FHFMA.BF16)
-__device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uint32_t b) {
+// acc0 += a.lo*r.lo + a.hi*r.hi ;  acc1 += c.lo*r.lo + c.hi*r.hi   (bf16 x bf16 products, fp32
+// accumulate: SASS FHFMA.BF16 with .H0/.H1 operand selectors, no conversion instructions)
+__device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uint32_t r, uint32_t c) {
   asm("{\n\t"
-      ".reg .b16 a0, a1, b0, b1;\n\t"
+      ".reg .b16 a0, a1, r0, r1, c0, c1;\n\t"
       "mov.b32 {a0, a1}, %2;\n\t"
-      "mov.b32 {b0, b1}, %3;\n\t"
-      "fma.rn.f32.bf16 %0, a0, b0, %0;\n\t"
-      "fma.rn.f32.bf16 %1, a1, b1, %1;\n\t"
+      "mov.b32 {r0, r1}, %3;\n\t"
+      "mov.b32 {c0, c1}, %4;\n\t"
+      "fma.rn.f32.bf16 %0, a0, r0, %0;\n\t"
+      "fma.rn.f32.bf16 %1, c0, r0, %1;\n\t"
+      "fma.rn.f32.bf16 %0, a1, r1, %0;\n\t"
+      "fma.rn.f32.bf16 %1, c1, r1, %1;\n\t"
       "}\n"
       : "+f"(acc0), "+f"(acc1)
-      : "r"(a), "r"(b));
+      : "r"(a), "r"(r), "r"(c));
 }
 
 constexpr int kFusedWarps = 4;
@@ -149,11 +153,9 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
       }
       // ---- partial dots bf16(r) . W_dec[i_j] over this slice ----
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float a0 = 0.f, a1 = 0.f;
-        fhfma2(a0, a1, w[j].x, rb.x);
-        fhfma2(a0, a1, w[j].y, rb.y);
-        part[j] += a0 + a1;
+      for (int j = 0; j < 32; j += 2) {   // two independent accumulation chains per pair of rows
+        fhfma2(part[j], part[j + 1], w[j].x, rb.x, w[j + 1].x);
+        fhfma2(part[j], part[j + 1], w[j].y, rb.y, w[j + 1].y);
       }
     }
     // ---- transpose-reduce: lane j ends up with the sum over lanes of part[j] ----
