@@ -58,6 +58,11 @@ def reduce_step(g_flat: Tensor, stats: Tensor, last_activated: Tensor | None,
         dist.all_reduce(last_activated, op=dist.ReduceOp.MAX, group=group)
 
 
+class _Done:
+    def wait(self) -> None:
+        return None
+
+
 class TorchDistCommunicator:
     """The production communicator: ``torch.distributed`` collectives (NCCL on the GPU box)."""
 
@@ -68,8 +73,17 @@ class TorchDistCommunicator:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
 
-    def reduce_step(self, g_flat: Tensor, stats: Tensor, last_activated: Tensor | None) -> None:
-        reduce_step(g_flat, stats, last_activated, self.group)
+    def all_reduce_sum_async(self, t: Tensor):
+        """Start summing ``t`` over the ranks on the collective's own stream (ordered after the work
+        already queued on the current stream); ``.wait()`` on the handle orders the current stream
+        after it.  Lets the gradient exchange of one weight matrix overlap the GEMM of the next."""
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def reduce_step(self, grads: Tensor | list[Tensor], stats: Tensor, last_activated: Tensor | None) -> None:
+        parts = grads if isinstance(grads, (list, tuple)) else [grads]
+        for g in parts[:-1]:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        reduce_step(parts[-1], stats, last_activated, self.group)
 
 
 class ThreadCommunicator:
@@ -92,24 +106,43 @@ class ThreadCommunicator:
         shared = cls._Shared(world)
         return [cls(shared, r) for r in range(world)]
 
-    def reduce_step(self, g_flat: Tensor, stats: Tensor, last_activated: Tensor | None) -> None:
+    def _exchange(self, tensors: list[Tensor], combine) -> None:
         sh = self.shared
-        if g_flat.is_cuda:
+        if any(t.is_cuda for t in tensors):
             torch.cuda.synchronize()
-        sh.slots[self.rank] = (g_flat.clone(), stats.clone(),
-                               None if last_activated is None else last_activated.clone())
+        sh.slots[self.rank] = [t.clone() for t in tensors]
         sh.barrier.wait()
-        g_flat.zero_()
-        sse = torch.zeros(1, dtype=torch.float64, device=stats.device)
-        l0 = torch.zeros(1, dtype=torch.int64, device=stats.device)
-        for g, st, la in sh.slots:                      # same order on every rank => bit-identical
-            g_flat += g
-            sse += st[:1].view(torch.float64)
-            l0 += st[1:2]
-            if last_activated is not None:
-                torch.maximum(last_activated, la, out=last_activated)
-        stats[:1].view(torch.float64).copy_(sse)
-        stats[1:2].copy_(l0)
-        if g_flat.is_cuda:
+        combine([sh.slots[r] for r in range(self.world)])      # same order on every rank
+        if any(t.is_cuda for t in tensors):
             torch.cuda.synchronize()
         sh.barrier.wait()
+
+    def all_reduce_sum_async(self, t: Tensor):
+        def combine(all_parts):
+            t.zero_()
+            for (p,) in all_parts:
+                t.add_(p)
+        self._exchange([t], combine)
+        return _Done()
+
+    def reduce_step(self, grads: Tensor | list[Tensor], stats: Tensor, last_activated: Tensor | None) -> None:
+        parts = list(grads) if isinstance(grads, (list, tuple)) else [grads]
+        tensors = parts + [stats] + ([last_activated] if last_activated is not None else [])
+
+        def combine(all_parts):
+            for i, g in enumerate(parts):
+                g.zero_()
+                for ap in all_parts:
+                    g.add_(ap[i])
+            sse = torch.zeros(1, dtype=torch.float64, device=stats.device)
+            l0 = torch.zeros(1, dtype=torch.int64, device=stats.device)
+            for ap in all_parts:
+                st = ap[len(parts)]
+                sse += st[:1].view(torch.float64)
+                l0 += st[1:2]
+                if last_activated is not None:
+                    torch.maximum(last_activated, ap[len(parts) + 1], out=last_activated)
+            stats[:1].view(torch.float64).copy_(sse)
+            stats[1:2].copy_(l0)
+
+        self._exchange(tensors, combine)

@@ -100,6 +100,12 @@ class _GraphedStep:
         seg = [self.g_flat[s0:s0 + n] for s0, n in zip(starts, sizes)]
         self.g_b_pre, self.g_b_enc, self.g_b_dec = seg[0], seg[2], seg[4]
         self.g_w_enc, self.g_w_decT = seg[1].view(F, d), seg[3].view(F, d)
+        # data-parallel exchange in three contiguous pieces: dW_enc starts as soon as its GEMM is
+        # done and overlaps the dW_dec GEMM; [b_pre] and [b_enc | W_decT | b_dec] follow
+        self.g_part_w_enc = self.g_flat[starts[1]:starts[2]]
+        self.g_part_head = self.g_flat[:starts[1]]
+        self.g_part_tail = self.g_flat[starts[2]:]
+        self._early = None
         self.grads = [self.g_b_pre, self.g_w_enc, self.g_b_enc, self.g_w_decT, self.g_b_dec]
         self.state = _SparseState()
         self.graph: torch.cuda.CUDAGraph | None = None
@@ -121,8 +127,11 @@ class _GraphedStep:
     def _body(self) -> None:
         self._compute()
         if self.trainer.data_parallel:      # batch-sharded: exchange gradients / stats / fired stamps
-            self.trainer.dp_comm.reduce_step(self.g_flat, self.stats,
-                                             self.trainer.model.feature_last_activated)
+            parts = [self.g_part_head, self.g_part_tail] if self._early is not None else [self.g_flat]
+            self.trainer.dp_comm.reduce_step(parts, self.stats, self.trainer.model.feature_last_activated)
+            if self._early is not None:
+                self._early.wait()
+                self._early = None
         self._update()
 
     def _compute(self) -> None:
@@ -168,6 +177,8 @@ class _GraphedStep:
             # weight gradients on the tensor cores (K4)
             buckets = ops.bucket_by_tile(idx, val, dpre, F)
             ops.wgrad_gemm_(self.g_w_enc, a_packed, B, d, buckets, buckets.dpre, None, 1.0)
+            if self.trainer.data_parallel:     # exchange dW_enc while the dW_dec GEMM runs
+                self._early = self.trainer.dp_comm.all_reduce_sum_async(self.g_part_w_enc)
             ops.wgrad_gemm_(self.g_w_decT, resid_bf, B, d, buckets, buckets.act, self.one, coef)
         ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
         s = self.state
