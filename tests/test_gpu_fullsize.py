@@ -1,0 +1,94 @@
+"""Full-size (BASELINE.json configs[1] bench shape: 75776 x 384 -> 3072, k = 32) checks through
+size-independent properties, with torch-on-GPU as the checker where the CPU oracle would take
+minutes: TopK optimality, exact sparsity, value = recomputed pre-activation, decode/loss identity,
+unit-norm decoder, counter invariants."""
+
+import pytest
+import torch
+
+from oracle import topk_sae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+B, D, F, K = 75776, 384, 3072, 32
+
+
+def _state():
+    torch.manual_seed(42)
+    return O.init_state(D, F)
+
+
+def test_fullsize_topk_is_optimal_and_exact():
+    from whisper_sae_b200 import ops
+
+    st = _state()
+    x = O.synthetic_activations(B, D, seed=1234).cuda()
+    w, b = st["encoder.weight"].cuda(), st["encoder.bias"].cuda()
+    a = ops.pack_activations(x, None, 1)
+    wp = ops.pack_encoder(w, b, 1)
+    idx, val = ops.encode_topk(a, wp, B, F, D, 1, K)
+    torch.cuda.synchronize()
+    assert idx.shape == (B, K) and int(idx.min()) >= 0 and int(idx.max()) < F
+    srt = torch.sort(idx, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                      # k distinct features per row
+    # checker: the same bf16-rounded operands, fp32 accumulate (torch matmul), exact fp32 bias
+    xq, wq = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
+    worst_gap, worst_val = 0.0, 0.0
+    for r0 in range(0, B, 8192):
+        pre = xq[r0:r0 + 8192] @ wq.t() + b
+        scale = pre.abs().max().item()
+        got = pre.gather(1, idx[r0:r0 + 8192].long())
+        worst_val = max(worst_val, ((got - val[r0:r0 + 8192]).abs().max() / scale).item())
+        kth = torch.topk(pre, K + 1, dim=1).values
+        # every selected value >= the true (k+1)-th largest (up to accumulation-order noise) ...
+        worst_gap = max(worst_gap, ((kth[:, K:K + 1] - val[r0:r0 + 8192]).max() / scale).item())
+        # ... and the selected sum equals the optimal top-k sum
+        assert torch.allclose(val[r0:r0 + 8192].sum(1), kth[:, :K].sum(1), rtol=1e-5, atol=1e-4 * scale)
+    assert worst_val <= 2e-6, worst_val            # values = recomputed pre-activations
+    assert worst_gap <= 2e-6, worst_gap            # nothing outside the set beats anything inside
+
+
+def test_fullsize_train_step_invariants(tmp_path):
+    from whisper_sae_b200.config import TrainingConfig
+    from whisper_sae_b200.sae import SAETrainer, TopKSAE
+
+    torch.manual_seed(42)
+    sae = TopKSAE(D, F, k=K, dead_feature_threshold=10_000)
+    cfg = TrainingConfig(batch_size=B, use_amp=True, num_workers=0)
+    tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path)
+    tr.setup_scheduler(1000)
+    x = O.synthetic_activations(2 * B, D, seed=7).cuda()
+    w0 = {n: p.detach().clone() for n, p in sae.named_parameters()}
+
+    def torch_forward(w, xb):
+        """bf16-mode forward with torch ops on the given weights: loss, l0, fired set."""
+        with torch.no_grad():
+            pre = (xb - w["b_pre"]).to(torch.bfloat16).float() @ w["encoder.weight"].to(torch.bfloat16).float().t() \
+                + w["encoder.bias"]
+            v, i = torch.topk(pre, K, dim=1)
+            wd = w["decoder.weight"].t().to(torch.bfloat16).float()       # [F, d] bf16 shadow
+            recon = torch.zeros(B, D, device="cuda")
+            for j in range(K):
+                recon += torch.relu(v[:, j:j + 1]) * wd[i[:, j]]
+            recon += w["decoder.bias"] + w["b_pre"]
+            fired = torch.zeros(F, dtype=torch.bool, device="cuda")
+            fired[i[v > 0]] = True
+            return ((recon - xb) ** 2).mean().item(), float((v > 0).sum()) / B, fired
+
+    loss_ref, l0_ref, fired_ref = torch_forward(w0, x[:B])
+    m1 = tr.train_step(x[:B])
+    assert m1.loss == pytest.approx(loss_ref, rel=1e-4)
+    assert m1.l0 == pytest.approx(l0_ref, abs=1e-3)
+    assert int(sae.step_count) == 1
+    assert torch.equal(sae.feature_last_activated > 0, fired_ref)         # fired set bit-exact
+    assert m1.dead_feature_ratio == 0.0
+    w1 = {n: p.detach().clone() for n, p in sae.named_parameters()}
+    loss2_ref, l02_ref, fired2_ref = torch_forward(w1, x[B:])
+    m2 = tr.train_step(x[B:])                                             # CUDA-graph capture / replay path
+    assert m2.loss == pytest.approx(loss2_ref, rel=1e-4) and int(sae.step_count) == 2
+    assert m2.l0 == pytest.approx(l02_ref, abs=1e-3)
+    assert torch.equal(sae.feature_last_activated == 2, fired2_ref)
+    norms = sae.decoder.weight.norm(dim=0)
+    torch.testing.assert_close(norms, torch.ones(F, device="cuda"), atol=1e-5, rtol=0)
+    for n, p in sae.named_parameters():
+        assert torch.isfinite(p).all() and not torch.equal(p, w0[n]), n
