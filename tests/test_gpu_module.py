@@ -283,3 +283,45 @@ def test_enabled_grad_scaler_path(tmp_path):
     for _ in range(3):
         ma, mb = a.train_step(x), b.train_step(x)
         assert ma.loss == pytest.approx(mb.loss, rel=1e-4)
+
+
+def test_train_layers_script_end_to_end(tmp_path):
+    """scripts/train_layers.py: synthetic cache -> FeatureCache -> SAETrainer.train -> sae_final.pt
+    (the reference CLI's train_layer recipe, scripts/train.py:118-219) on the tiny_test config."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run(
+        [sys.executable, str(root / "scripts" / "train_layers.py"), "--config",
+         str(root / "configs" / "tiny_test.yaml"), "--synthetic-rows", "8192", "--epochs", "2",
+         "--batch-size", "1024", "--output-dir", str(tmp_path / "out"), "--cache-dir", str(tmp_path / "cache")],
+        capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    runs = list((tmp_path / "out").glob("*_encoder_layer0"))
+    assert len(runs) == 1
+    sd = torch.load(runs[0] / "sae_final.pt")
+    assert list(sd) == ["b_pre", "feature_last_activated", "step_count", "encoder.weight", "encoder.bias",
+                        "decoder.weight", "decoder.bias"]
+    assert sd["decoder.weight"].shape == (384, 3072) and int(sd["step_count"]) == 16
+    assert (runs[0] / "metrics.json").exists() and (runs[0] / "final.pt").exists()
+    assert (tmp_path / "cache" / "features" / "whisper-tiny_encoder_layer0.pt").exists()
+
+
+def test_auto_resample_flag(tmp_path):
+    """auto_resample=True calls the reference's (never wired) resampling hook every
+    `resample_dead_every` steps; dead features get re-pointed at high-error inputs."""
+    from whisper_sae_b200.config import TrainingConfig
+    from whisper_sae_b200.sae import SAETrainer, TopKSAE
+
+    torch.manual_seed(0)
+    sae = TopKSAE(64, 512, k=4, dead_feature_threshold=1)
+    cfg = TrainingConfig(batch_size=32, use_amp=False, num_workers=0)
+    tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path, resample_dead_every=3,
+                    resample_batch_size=64, auto_resample=True)
+    x = torch.randn(64, 64)
+    tr.set_resample_dataset(torch.utils.data.TensorDataset(x))
+    for _ in range(6):
+        tr.train_step(x[:32].cuda())
+    assert tr.num_resampled_total > 0

@@ -262,6 +262,7 @@ class SAETrainer:
         grad_scaler: bool = False,
         fused_optimizer: bool | None = None,
         cuda_graph: bool | None = None,
+        auto_resample: bool = False,
         data_parallel: bool = False,
         dp_comm=None,
         global_batch_rows: int | None = None,
@@ -299,6 +300,9 @@ class SAETrainer:
         self._graphs: dict[int, _GraphedStep] = {}
         # batch-sharded data parallel (sae/parallel.py): every rank passes its own row shard to
         # train_step; gradients, stats and fired stamps are all-reduced inside the step
+        # the reference defines _maybe_resample_dead_features but never calls it (training.py:97-134);
+        # auto_resample=True wires it in after every step (off by default: parity)
+        self.auto_resample = bool(auto_resample)
         self.data_parallel = bool(data_parallel)
         self.dp_comm = None
         self.global_batch_rows = global_batch_rows     # default: local rows x world (equal shards)
@@ -400,7 +404,10 @@ class SAETrainer:
             if self.scheduler is not None:
                 self.scheduler.step()
             self.global_step += 1
-            return self._read_metrics(None, batch.shape[0])
+            metrics = self._read_metrics(None, batch.shape[0])
+            if self.auto_resample:
+                self._maybe_resample_dead_features()
+            return metrics
 
         batch = batch.to(self.device, non_blocking=True)
 
@@ -425,6 +432,8 @@ class SAETrainer:
         self.global_step += 1
 
         metrics = self._read_metrics(output, batch.shape[0])
+        if self.auto_resample:
+            self._maybe_resample_dead_features()
         return metrics
 
     def _graph_ok(self, batch: Tensor) -> bool:
