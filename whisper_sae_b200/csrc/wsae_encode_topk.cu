@@ -999,6 +999,9 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // ------------------------------------------------------------------------------------------------
 constexpr int kMergeMaxPerLane = 64;
 
+// PER = candidates per lane (ceil(n / 32) rounded up to an instantiated size): the loops are fully
+// unrolled over registers, so a small merge (12 splits x 32) does not pay for the 64-wide worst case.
+template <int PER>
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict__ part_idx, int B,
                   int n, int k, float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
@@ -1008,10 +1011,10 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
   const float* pv = part_val + static_cast<size_t>(row) * n;
   const int32_t* pi = part_idx + static_cast<size_t>(row) * n;
   const int per = ceil_div(n, 32);  // <= kMergeMaxPerLane (checked on the host)
-  uint32_t key[kMergeMaxPerLane];
+  uint32_t key[PER];
   uint32_t hi = 0;
-#pragma unroll 4
-  for (int t = 0; t < kMergeMaxPerLane; ++t) {
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
     const int p = t * 32 + lane;
     uint32_t kk = 0;
     if (t < per && p < n && pi[p] >= 0) kk = f2key(pv[p]);
@@ -1025,8 +1028,8 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
   while (hi - lo > 1u) {
     const uint32_t mid = lo + ((hi - lo) >> 1);
     int c = 0;
-#pragma unroll 4
-    for (int t = 0; t < kMergeMaxPerLane; ++t) c += (key[t] > mid) ? 1 : 0;
+#pragma unroll
+    for (int t = 0; t < PER; ++t) c += (key[t] > mid) ? 1 : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (c >= k) {
@@ -1043,8 +1046,8 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
   int tie_left = 0;
   if (!exact) {
     int m = 0;
-#pragma unroll 4
-    for (int t = 0; t < kMergeMaxPerLane; ++t) m += (key[t] > hi) ? 1 : 0;
+#pragma unroll
+    for (int t = 0; t < PER; ++t) m += (key[t] > hi) ? 1 : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
     thr = hi;
@@ -1053,7 +1056,9 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
   }
   int base = 0;
   const uint32_t below = (1u << lane) - 1u;
-  for (int t = 0; t < per; ++t) {
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
+    if (t >= per) break;
     const uint32_t kk = key[t];
     const bool gt = kk > thr;
     const bool tie = (kk == tie_key);
@@ -1215,8 +1220,18 @@ extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int 
   if (rc) return rc;
   if (nsplit > 1) {
     const int warps = 8;
-    topk_merge_kernel<<<ceil_div(B, warps), warps * 32, 0, stream>>>(part_val, part_idx, B,
-                                                                    nsplit * k, k, out_val, out_idx);
+    const int per = ceil_div(nsplit * k, 32);
+    const dim3 grid(ceil_div(B, warps)), block(warps * 32);
+#define WSAE_MERGE_CASE(P)                                                                   \
+  topk_merge_kernel<P><<<grid, block, 0, stream>>>(part_val, part_idx, B, nsplit * k, k, out_val, out_idx)
+    if (per <= 2) WSAE_MERGE_CASE(2);
+    else if (per <= 4) WSAE_MERGE_CASE(4);
+    else if (per <= 8) WSAE_MERGE_CASE(8);
+    else if (per <= 12) WSAE_MERGE_CASE(12);
+    else if (per <= 16) WSAE_MERGE_CASE(16);
+    else if (per <= 32) WSAE_MERGE_CASE(32);
+    else WSAE_MERGE_CASE(64);
+#undef WSAE_MERGE_CASE
     rc = static_cast<int>(cudaGetLastError());
   }
   return rc;
