@@ -14,7 +14,8 @@ from ctypes import POINTER, c_double, c_float, c_int, c_int32, c_longlong, c_voi
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libwsae_sm100.so"
+# WSAE_LIB_PATH: load another build of the same library (kernel-tuning experiments only)
+LIB_PATH = Path(os.environ.get("WSAE_LIB_PATH") or _PKG / "lib" / "libwsae_sm100.so")
 CSRC = _PKG / "csrc"
 
 _ERRORS = {

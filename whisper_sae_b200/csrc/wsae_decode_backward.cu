@@ -51,7 +51,7 @@ __device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uin
 constexpr int kFusedWarps = 4;
 
 // bf16 decoder shadow only.  k <= 32, d % 8 == 0.
-__global__ void __launch_bounds__(kFusedWarps * 32, 3)
+__global__ void __launch_bounds__(kFusedWarps * 32, 4)
 decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __restrict__ w_decT,
                        const float* __restrict__ b_dec, const float* __restrict__ b_pre,
                        const int32_t* __restrict__ idx, const float* __restrict__ val,
@@ -225,7 +225,7 @@ extern "C" int wsae_decode_backward(const float* target, const void* w_decT, int
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int blocks = ceil_div(B, kFusedWarps);
-  if (blocks > sms * 3) blocks = sms * 3;
+  if (blocks > sms * 4) blocks = sms * 4;
   const size_t smem = (1 + kFusedWarps) * static_cast<size_t>(round_up(d, 128)) * sizeof(float);
   decode_backward_kernel<<<blocks, kFusedWarps * 32, smem, stream>>>(
       target, static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B,
