@@ -29,7 +29,7 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 101). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 102: + wsae_decode_backward, wsae_adamw_multi, wsae_scatter_rows). */
 int wsae_abi_version(void);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
@@ -169,6 +169,15 @@ typedef struct {
 } wsae_adamw_tensor_t;
 int wsae_adamw_multi(const wsae_adamw_tensor_t* tensors, int count, const float* hyper,
                      const double* grad_sumsq, float renorm_eps, wsae_stream_t stream);
+
+/* ---- experiments only (tools/bench_k1.py); not part of the product path -----------------------
+ * variant: 1 = one epilogue warp per TMEM lane quarter, 2 = scanner + selector warps (default);
+ * mode (variant 1): 0 = product, 1 = release the accumulators unread (GEMM pipeline alone),
+ * 2 = scan without compaction; counters: device buffer u64 [grid][8][8] for the scanner/selector
+ * wait breakdown (NULL = off). */
+int wsae_debug_encode_variant(int variant);
+int wsae_debug_encode_mode(int mode);
+int wsae_debug_encode_counters(void* device_buf);
 
 #ifdef __cplusplus
 }
