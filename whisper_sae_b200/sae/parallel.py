@@ -66,6 +66,8 @@ class _Done:
 class TorchDistCommunicator:
     """The production communicator: ``torch.distributed`` collectives (NCCL on the GPU box)."""
 
+    graph_safe = True        # NCCL collectives can be captured into the step's CUDA graph
+
     def __init__(self, group: dist.ProcessGroup | None = None):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("data_parallel=True needs torch.distributed to be initialised")
@@ -90,6 +92,8 @@ class ThreadCommunicator:
     """In-process stand-in with the same interface: ``world`` threads of ONE process (one GPU, or
     the CPU) rendezvous on a barrier and combine their buffers.  Used to check the batch-sharded
     step against the single-device step where only one GPU is available."""
+
+    graph_safe = False       # host-side rendezvous: the step must be launched eagerly
 
     class _Shared:
         def __init__(self, world: int):

@@ -311,7 +311,12 @@ class SAETrainer:
             self.dp_comm = dp_comm if dp_comm is not None else TorchDistCommunicator()
             if not (is_cuda and self.fused_optimizer) or self.scaler.is_enabled():
                 raise RuntimeError("data_parallel=True needs the fused CUDA step (no GradScaler)")
-            self.cuda_graph = "eager"       # collectives between the kernels: launch them one by one
+            # collectives between the kernels: the step is launched kernel by kernel.  Capturing the
+            # NCCL calls into the step's CUDA graph (WSAE_DP_GRAPH=1, experimental) hung on the
+            # 2-GPU box in round 1 and stays off by default.
+            graph_ok = getattr(self.dp_comm, "graph_safe", False) and \
+                os.environ.get("WSAE_DP_GRAPH", "0") == "1" and self.cuda_graph is not False
+            self.cuda_graph = True if graph_ok else "eager"
 
     # ------------------------------------------------------------------ resampling plumbing
     def set_resample_dataset(self, dataset: torch.utils.data.Dataset) -> None:
