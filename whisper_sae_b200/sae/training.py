@@ -217,6 +217,7 @@ class _GraphedStep:
         h[6] = math.sqrt(1.0 - beta2 ** step_t)
         h[7] = tr.config.gradient_clip
         self.hyper.copy_(h, non_blocking=True)
+        tr.optimizer._opt_called = True    # the fused kernels ARE the optimizer step (lr_scheduler's order check)
         self.calls += 1
         m = tr.model
         m._w_decT()
@@ -381,6 +382,7 @@ class SAETrainer:
         hyper = torch.tensor([lr, beta1, beta2, group["eps"], group["weight_decay"], bc1, bc2s,
                               self.config.gradient_clip], dtype=torch.float32)
         self._hyper.copy_(hyper, non_blocking=True)
+        self.optimizer._opt_called = True
         for p in params:
             state = self.optimizer.state[p]
             # parameter, grad and moments share one dense layout (contiguous or its transpose),
