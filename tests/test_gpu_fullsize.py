@@ -69,7 +69,7 @@ def test_fullsize_train_step_invariants(tmp_path):
             wd = w["decoder.weight"].t().to(torch.bfloat16).float()       # [F, d] bf16 shadow
             recon = torch.zeros(B, D, device="cuda")
             for j in range(K):
-                recon += torch.relu(v[:, j:j + 1]) * wd[i[:, j]]
+                recon += torch.relu(v[:, j:j + 1]).to(torch.bfloat16).float() * wd[i[:, j]]
             recon += w["decoder.bias"] + w["b_pre"]
             fired = torch.zeros(F, dtype=torch.bool, device="cuda")
             fired[i[v > 0]] = True

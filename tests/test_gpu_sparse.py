@@ -43,13 +43,15 @@ def test_decode_mse(B, d, F, k, wdtype):
     state_q = dict(state)
     ref = O.forward(state_q, x, k, training=False)
     w_decT = state["decoder.weight"].t().contiguous()
-    if quant:
+    h = torch.relu(ref.val)
+    if quant:      # bf16 shadow => bf16 x bf16 products (activation rounded too), fp32 accumulation
         w_used = w_decT.to(torch.bfloat16)
         rows = w_used.float()[ref.idx]
+        h = h.to(torch.bfloat16).float()
     else:
         w_used = w_decT
         rows = w_decT[ref.idx]
-    recon = (torch.relu(ref.val).unsqueeze(-1) * rows).sum(1) + state["decoder.bias"] + state["b_pre"]
+    recon = (h.unsqueeze(-1) * rows).sum(1) + state["decoder.bias"] + state["b_pre"]
     resid_ref = recon - x
     stats = torch.zeros(3, dtype=torch.int64, device="cuda")
     last = torch.zeros(F, dtype=torch.int64, device="cuda")
@@ -130,7 +132,8 @@ def test_decode_backward_fused(B, d, F, k, wdtype):
     # force a few selected values non-positive: relu-masked entries must contribute nothing
     val = fwd.val.clone()
     val[::3, 0] = -val[::3, 0].abs()
-    recon = (torch.relu(val).unsqueeze(-1) * state["decoder.weight"].t()[fwd.idx]).sum(1) \
+    h_bf = torch.relu(val).to(torch.bfloat16).float()          # bf16 x bf16 decode products
+    recon = (h_bf.unsqueeze(-1) * state["decoder.weight"].t()[fwd.idx]).sum(1) \
         + state["decoder.bias"] + state["b_pre"]
     resid_ref = recon - x
     grad_out = 0.5

@@ -90,7 +90,9 @@ decode_kernel(const float* __restrict__ target, const WT* __restrict__ w_decT,
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const int32_t f = __shfl_sync(0xffffffffu, my_i, src);
-        const float a = __shfl_sync(0xffffffffu, my_v, src);
+        float a = __shfl_sync(0xffffffffu, my_v, src);
+        // bf16 shadow => bf16 x bf16 product with fp32 accumulation (same as the fused K23 kernel)
+        if (sizeof(WT) == 2) a = __bfloat162float(__float2bfloat16_rn(a));
         const WT* wrow = w_decT + static_cast<size_t>(f) * d;
 #pragma unroll
         for (int c = 0; c < NV; ++c) {
@@ -178,7 +180,8 @@ decode_kernel_generic(const float* __restrict__ target, const WT* __restrict__ w
         const int32_t f = irow[j];
         const float a = vrow[j];
         if (f >= 0 && f < F && a > 0.f)
-          acc = fmaf(a, static_cast<float>(w_decT[static_cast<size_t>(f) * d + col]), acc);
+          acc = fmaf(sizeof(WT) == 2 ? __bfloat162float(__float2bfloat16_rn(a)) : a,
+                     static_cast<float>(w_decT[static_cast<size_t>(f) * d + col]), acc);
       }
       const float r = acc - target[static_cast<size_t>(row) * d + col];
       if (recon_out != nullptr) recon_out[static_cast<size_t>(row) * d + col] = acc;

@@ -16,9 +16,10 @@
 // dependent loop that exposes the load latency.  Here one warp owns one activation row and walks it
 // in slices of 128 columns: lane l owns 4 consecutive columns, so the slice of one decoder row is one
 // coalesced 8-byte load per lane.  The 32 row slices are loaded into REGISTERS with all 32 loads in
-// flight at once, used for the reconstruction (fp32 FMA), and - still in registers - for the 32
-// partial dot products with the residual (FHFMA.BF16: bf16 x bf16 products, fp32 accumulate, no
-// conversion instructions; the residual enters in the same bf16 rounding that K4 consumes).
+// flight at once, used for the reconstruction and - still in registers - for the 32 partial dot
+// products with the residual.  Both are FHFMA.BF16 (bf16 x bf16 products, fp32 accumulate, operand
+// halves picked by .H0/.H1 selectors: no conversion instructions); activation and residual enter
+// in the bf16 rounding that K4's weight-gradient GEMMs consume.
 // Every decoder byte is read from L2 exactly once.  (A first version staged the rows in shared
 // memory with one cp.async.bulk per row: 32 bulk copies of 768 B per activation row saturate the
 // TMA unit at ~45 ns per copy - 4x slower than this form; profiles/r1_k23_notes.md.)
@@ -46,6 +47,22 @@ __device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uin
       "}\n"
       : "+f"(acc0), "+f"(acc1)
       : "r"(a), "r"(r), "r"(c));
+}
+
+// acc.{x,y,z,w} += bf16(w.x.lo, w.x.hi, w.y.lo, w.y.hi) * bf16(h.lo)   (fp32 accumulate)
+__device__ __forceinline__ void fhfma_bcast4(float4& acc, uint2 w, uint32_t h) {
+  asm("{\n\t"
+      ".reg .b16 a0, a1, c0, c1, h0, h1;\n\t"
+      "mov.b32 {a0, a1}, %4;\n\t"
+      "mov.b32 {c0, c1}, %5;\n\t"
+      "mov.b32 {h0, h1}, %6;\n\t"
+      "fma.rn.f32.bf16 %0, a0, h0, %0;\n\t"
+      "fma.rn.f32.bf16 %1, a1, h0, %1;\n\t"
+      "fma.rn.f32.bf16 %2, c0, h0, %2;\n\t"
+      "fma.rn.f32.bf16 %3, c1, h0, %3;\n\t"
+      "}\n"
+      : "+f"(acc.x), "+f"(acc.y), "+f"(acc.z), "+f"(acc.w)
+      : "r"(w.x), "r"(w.y), "r"(h));
 }
 
 constexpr int kFusedWarps = 4;
@@ -95,6 +112,10 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
     const bool fired = (my_i >= 0) && (my_i < F) && (my_v > 0.f);
     if (fired && last_activated != nullptr) last_activated[my_i] = stamp;
     if (!fired) my_v = 0.f;                         // relu; also neutralises invalid entries
+    // bf16 mode: the decoder product is bf16 x bf16 with fp32 accumulation - the activation enters
+    // in bf16 like the weight shadow (the reference's autocast decoder Linear rounds `hidden` to
+    // half precision too; K4's dW_dec GEMM consumes the same bf16(h))
+    const uint32_t my_hb = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(my_v)));
     const uint32_t mask = __ballot_sync(0xffffffffu, fired);
     l0_local += (lane == 0) ? __popc(mask) : 0;
     // element offset (in uint2 units) of each selected decoder row; inactive entries read row 0
@@ -122,12 +143,8 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
       // ---- reconstruction of this slice (fp32) ----
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float h = __shfl_sync(0xffffffffu, my_v, j);
-        const float4 wf = bf16x4_to_float4(w[j]);
-        acc.x = fmaf(h, wf.x, acc.x);
-        acc.y = fmaf(h, wf.y, acc.y);
-        acc.z = fmaf(h, wf.z, acc.z);
-        acc.w = fmaf(h, wf.w, acc.w);
+        const uint32_t hb = __shfl_sync(0xffffffffu, my_hb, j);
+        fhfma_bcast4(acc, w[j], hb);
       }
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok) {
