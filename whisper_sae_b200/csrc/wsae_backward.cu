@@ -158,7 +158,7 @@ backward_sparse_kernel(const float* __restrict__ resid, const float* __restrict_
 // db_pre[c] = db_dec[c] - sum_f db_enc[f] * W_enc[f, c].  One block per chunk of 32 features;
 // thread t owns columns {t, t + blockDim, ...}; features with a zero bias gradient (never selected
 // in this batch) are skipped, so only fired rows of W_enc are read.
-constexpr int kBpreFeat = 32;
+constexpr int kBpreFeat = 8;
 __global__ void __launch_bounds__(256)
 bpre_grad_kernel(const float* __restrict__ d_b_dec, const float* __restrict__ d_b_enc,
                  const float* __restrict__ w_enc, int F, int d, float* __restrict__ d_b_pre) {
