@@ -202,14 +202,15 @@ class _GraphedStep:
         ops.adamw_multi_(entries, self.hyper, self.sumsq, 1e-12)   # clip + AdamW + decoder renorm
 
     def run(self, batch: Tensor) -> None:
+        """Launch first, book-keep afterwards: everything the GPU needs (batch copy, hyper vector,
+        pointer check) is issued before the replay; the optimizer's ``step`` tensors and the grad
+        views are updated while the kernels run (matters at the launch-bound YAML batch sizes)."""
         tr = self.trainer
         self.x.copy_(batch, non_blocking=True)
         group = tr.optimizer.param_groups[0]
-        step_t = 0.0
         for p in self.params:
-            st = tr.optimizer.state[p]
-            st["step"] += 1
-            step_t = float(st["step"])
+            _ensure_adamw_state(tr.optimizer, p)
+        step_t = float(tr.optimizer.state[self.params[0]]["step"]) + 1.0
         beta1, beta2 = group["betas"]
         h = self.hyper_host
         h[0], h[1], h[2], h[3], h[4] = group["lr"], beta1, beta2, group["eps"], group["weight_decay"]
@@ -217,12 +218,8 @@ class _GraphedStep:
         h[6] = math.sqrt(1.0 - beta2 ** step_t)
         h[7] = tr.config.gradient_clip
         self.hyper.copy_(h, non_blocking=True)
-        tr.optimizer._opt_called = True    # the fused kernels ARE the optimizer step (lr_scheduler's order check)
         self.calls += 1
-        m = tr.model
-        m._w_decT()
-        for p in self.params:
-            _ensure_adamw_state(tr.optimizer, p)
+        tr.model._w_decT()
         key = self._pointer_key()
         if key != self._ptrs:      # storage was swapped behind our back (.data = ..., load): re-capture
             self.graph = None
@@ -242,6 +239,10 @@ class _GraphedStep:
                 self.graph = g
             self.graph.replay()
             ops.GPU_LAUNCHES += self.kernels_per_replay
+        # ---- host book-keeping, overlapping the kernels ----
+        for p in self.params:      # torch.optim.AdamW keeps `step` as a CPU float32 tensor per parameter
+            tr.optimizer.state[p]["step"] += 1
+        tr.optimizer._opt_called = True    # the fused kernels ARE the optimizer step (lr_scheduler's order check)
         # expose grads the way autograd would (decoder.weight's grad is the [d, F] transposed view)
         for p, g in zip(self.params, self.grads):
             p.grad = g.t() if p is tr.model.decoder.weight else g
