@@ -4,7 +4,8 @@
     python tools/bench_k1.py [--d 384 --F 3072 --k 32 --batches 16384,65536] [--modes 0,1,2]
 
 modes (experiments, wsae_debug_encode_mode): 0 = product kernel, 1 = GEMM pipeline only (epilogue
-releases the accumulators unread), 2 = scan without compaction (results invalid).
+releases the accumulators unread), 2 = scan without compaction (results invalid; both need
+--variant 1), 3 = scanner + selector kernel with the filter closed (pipeline + bare scan).
 """
 import argparse
 import ctypes
@@ -42,6 +43,10 @@ def main() -> None:
         xs = [ops.pack_activations(torch.randn(B, args.d, device=dev), None, 1) for _ in range(nrot)]
         for mode in [int(s) for s in args.modes.split(",")]:
             lib.wsae_debug_encode_mode(mode)
+            if mode == 3:     # lives in the instrumented build of the scanner + selector kernel
+                lib.wsae_debug_encode_counters.argtypes = [ctypes.c_void_p]
+                dbuf = torch.zeros(148 * 8 * 8, dtype=torch.int64, device=dev)
+                lib.wsae_debug_encode_counters(dbuf.data_ptr())
             for i in range(3):
                 ops.encode_topk(xs[i % nrot], wp, B, args.F, args.d, 1, args.k)
             torch.cuda.synchronize()
@@ -52,6 +57,8 @@ def main() -> None:
             t1.record()
             torch.cuda.synchronize()
             ms = t0.elapsed_time(t1) / args.iters
+            if mode == 3:
+                lib.wsae_debug_encode_counters(None)
             tf = 2.0 * B * args.d * args.F / ms / 1e9
             print(f"B={B} d={args.d} F={args.F} k={args.k} mode={mode}: {ms * 1e3:8.1f} us  "
                   f"{tf:7.1f} TFLOP/s (algorithmic)  {B / ms / 1e3:8.2f} Mrows/s", flush=True)

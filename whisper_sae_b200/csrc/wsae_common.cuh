@@ -116,6 +116,17 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
+// Wait with a short sleep between polls (NS nanoseconds; 0 = tight loop): for the TMA / MMA roles,
+// whose polling would otherwise take issue slots from the epilogue warps on their sub-partition.
+template <int NS>
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (NS > 0) __nanosleep(NS);
+    if (++spins > WSAE_SPIN_LIMIT) __trap();
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — 2D tiled load, completion on an mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -280,7 +280,7 @@ struct EncodeItems {
 };
 
 // TMA producer (one elected lane): streams A' 128x64 and W' 256x64 boxes through the stage ring.
-template <int STAGES>
+template <int STAGES, int NS = 0>
 __device__ __forceinline__ void encode_producer_loop(const CUtensorMap* tmap_a,
                                                      const CUtensorMap* tmap_w, uint8_t* pipe,
                                                      uint64_t* full_bar, uint64_t* empty_bar,
@@ -294,7 +294,7 @@ __device__ __forceinline__ void encode_producer_loop(const CUtensorMap* tmap_a,
     const int t1 = min(t0 + it.tiles_per_split, it.num_n_tiles);
     for (int nt = t0; nt < t1; ++nt) {
       for (int kb = 0; kb < it.num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_wait_sleep<NS>(&empty_bar[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&full_bar[stage], kAStage + kBStage);
         uint8_t* sa = pipe + stage * (kAStage + kBStage);
         tma_load_2d(sa, tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
@@ -310,7 +310,7 @@ __device__ __forceinline__ void encode_producer_loop(const CUtensorMap* tmap_a,
 
 // MMA issuer (whole warp; one elected lane issues): 128x256x16 tcgen05.mma into the double-buffered
 // TMEM accumulators.
-template <int STAGES>
+template <int STAGES, int NS = 0>
 __device__ __forceinline__ void encode_mma_loop(uint8_t* pipe, uint64_t* full_bar,
                                                 uint64_t* empty_bar, uint64_t* tfull_bar,
                                                 uint64_t* tempty_bar, uint32_t tmem_base,
@@ -327,11 +327,11 @@ __device__ __forceinline__ void encode_mma_loop(uint8_t* pipe, uint64_t* full_ba
     for (int nt = t0; nt < t1; ++nt, ++tile) {
       const uint32_t as = tile & 1u;
       const uint32_t aphase = (tile >> 1) & 1u;
-      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      mbar_wait_sleep<NS>(&tempty_bar[as], aphase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * kBN;
       for (int kb = 0; kb < it.num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_sleep<NS>(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(pipe + stage * (kAStage + kBStage));
@@ -554,6 +554,10 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // Registers: 384 threads; setmaxnreg moves registers from the producer/MMA warpgroup to the
 // selector warpgroup (which holds 80 values + 80 indices per thread).
 // ================================================================================================
+#ifndef WSAE_ROLE_SLEEP_NS
+#define WSAE_ROLE_SLEEP_NS 64
+#endif
+constexpr int kRoleSleepNs = WSAE_ROLE_SLEEP_NS;   // poll interval of the TMA / MMA roles (see mbar_wait_sleep)
 constexpr int kFifo = 40;                          // slots per FIFO buffer (>= k + kSlack)
 constexpr int kFifoBytes = kFifo * kBM * 4;        // one buffer of one array: 20480 B
 constexpr int kFifoIdxOff = 2 * kFifoBytes;        // idx array sits behind both value buffers
@@ -580,6 +584,9 @@ __device__ __forceinline__ void reg_alloc_dec() {
 }
 
 // Predicated append of four (value, index) pairs at cursor w; IOFF = byte offset of the index array.
+// (A variant whose four slot addresses are w + prefix sums of the pass flags - one loop-carried add
+// per four values instead of a serial cursor chain - measured SLOWER, 277 vs 260 us: the scanner is
+// not bound by that chain but by issue slots and instruction fetch.)
 template <int IOFF>
 __device__ __forceinline__ uint32_t append4(uint32_t w, float thr, float v0, float v1, float v2,
                                             float v3, uint32_t i0, uint32_t i1, uint32_t i2,
@@ -636,14 +643,26 @@ __device__ __forceinline__ float select_threshold(const float (&v)[N], int total
   const float ninf = __uint_as_float(0xff800000u);
   const float pinf = __uint_as_float(0x7f800000u);
   const bool keep_all = total <= k + slack;
-  float vmax = ninf;
+  float m0 = ninf, m1 = ninf, m2 = ninf, m3 = ninf;     // four independent chains (latency)
 #pragma unroll
-  for (int s = 0; s < N; ++s) vmax = fmaxf(vmax, v[s]);
+  for (int s = 0; s < N; s += 4) {
+    m0 = fmaxf(m0, v[s]);
+    m1 = fmaxf(m1, v[s + 1]);
+    m2 = fmaxf(m2, v[s + 2]);
+    m3 = fmaxf(m3, v[s + 3]);
+  }
+  const float vmax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
   uint32_t lo;
   if (tau == ninf) {
-    float vmin = pinf;
+    float n0 = pinf, n1 = pinf, n2 = pinf, n3 = pinf;
 #pragma unroll
-    for (int s = 0; s < N; ++s) vmin = fminf(vmin, (v[s] == ninf) ? pinf : v[s]);
+    for (int s = 0; s < N; s += 4) {
+      n0 = fminf(n0, (v[s] == ninf) ? pinf : v[s]);
+      n1 = fminf(n1, (v[s + 1] == ninf) ? pinf : v[s + 1]);
+      n2 = fminf(n2, (v[s + 2] == ninf) ? pinf : v[s + 2]);
+      n3 = fminf(n3, (v[s + 3] == ninf) ? pinf : v[s + 3]);
+    }
+    const float vmin = fminf(fminf(n0, n1), fminf(n2, n3));
     lo = f2key(vmin) - 1u;
   } else {
     lo = f2key(tau);
@@ -689,13 +708,40 @@ __device__ __forceinline__ float select_threshold(const float (&v)[N], int total
   return thrf;
 }
 
+// Scanner -> selector hand-over of the FIFO buffer in use (out of line: ~13 calls per work item;
+// inlined at every check site it made the scan loop twice the size of the L0 instruction cache).
+// st: bit 0 = buffer in use, bits 1 / 2 = parity of the number of fills of buffer 0 / 1.
+// Publishes the row's entry count and the `last` flag, arrives on the buffer's full barrier,
+// switches to the other buffer and (unless this was the item's last hand-over) waits until the
+// selector has drained it.  *_q pointers are this lane quarter's entry of the [2][4] arrays.
+template <bool DBG>
+__device__ __noinline__ uint32_t scanner_handoff(uint32_t st, uint32_t nslots, uint32_t last,
+                                                 uint32_t cnt_addr, uint32_t* meta_q,
+                                                 uint64_t* ffull_q, uint64_t* fempty_q, int lane,
+                                                 unsigned long long* waited) {
+  const uint32_t b = st & 1u;
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(cnt_addr + b * (kBM * 2)),
+               "h"(static_cast<unsigned short>(nslots))
+               : "memory");
+  if (lane == 0) meta_q[b * 4] = last;
+  mbar_arrive(&ffull_q[b * 4]);
+  st ^= (2u << b) | 1u;                 // one more fill of buffer b; continue on the other buffer
+  if (!last) {
+    const uint32_t nb = st & 1u;
+    const long long t = DBG ? clock64() : 0;
+    mbar_wait_backoff(&fempty_q[nb * 4], ((st >> (1u + nb)) & 1u) ^ 1u);
+    if (DBG) *waited += clock64() - t;
+  }
+  return st;
+}
+
 template <int STAGES, bool DBG>
 __global__ void __launch_bounds__(384, 1)
 encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_w, int B, int F, int k, int ksteps,
                     int num_m_blocks, int num_n_tiles, int nsplit, int tiles_per_split,
                     float* __restrict__ out_val, int32_t* __restrict__ out_idx,
-                    unsigned long long* __restrict__ dbg) {
+                    unsigned long long* __restrict__ dbg, int mode) {
   using SM = Encode2Smem<STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -752,9 +798,11 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp < 4) {
     reg_alloc_dec<56>();
     if (warp == 0) {
-      if (elect_one()) encode_producer_loop<STAGES>(&tmap_a, &tmap_w, pipe, full_bar, empty_bar, items);
+      if (elect_one())
+        encode_producer_loop<STAGES, kRoleSleepNs>(&tmap_a, &tmap_w, pipe, full_bar, empty_bar, items);
     } else if (warp == 1) {
-      encode_mma_loop<STAGES>(pipe, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, items);
+      encode_mma_loop<STAGES, kRoleSleepNs>(pipe, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base,
+                                            items);
     }
   } else if (warp < 8) {
     // ===================== scanner =====================
@@ -764,7 +812,7 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t fv0 = smem_u32(fifo) + row_in_blk * 4;          // buffer 0, slot 0 of this row
     const uint32_t tau_addr = smem_u32(tau_s) + row_in_blk * 8;
     const uint32_t cnt_addr = smem_u32(cnt_s) + row_in_blk * 2;
-    uint32_t fills0 = 0, fills1 = 0, b = 0, seq = 0, tile = 0;
+    uint32_t st = 0, seq = 0, tile = 0;      // st: bit 0 = FIFO buffer in use, bits 1/2 = fill parities
     unsigned long long d_hand = 0, d_wait_e = 0, d_wait_t = 0;
     const long long d_t0 = clock64();
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -772,30 +820,12 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int t0 = sp * tiles_per_split;
       const int t1 = min(t0 + tiles_per_split, num_n_tiles);
       ++seq;
-      float tau = neg_inf;
-      mbar_wait_backoff(&fempty_bar[b * 4 + q], ((b ? fills1 : fills0) & 1u) ^ 1u);
-      uint32_t wbase = fv0 + b * kFifoBytes;
+      // mode 3 (experiments): nothing passes the filter - times the GEMM pipeline + bare scan
+      float tau = (DBG && mode == 3) ? __uint_as_float(0x7f800000u) : neg_inf;
+      mbar_wait_backoff(&fempty_bar[(st & 1u) * 4 + q], ((st >> (1u + (st & 1u))) & 1u) ^ 1u);
+      uint32_t wbase = fv0 + (st & 1u) * kFifoBytes;
       uint32_t waddr = wbase;
       uint32_t wlimit = wbase + (kFifo - kCheck) * (kBM * 4);
-
-      auto handoff = [&](uint32_t last) {
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(cnt_addr + b * (kBM * 2)),
-                     "h"(static_cast<unsigned short>((waddr - wbase) / (kBM * 4)))
-                     : "memory");
-        if (lane == 0) meta[b * 4 + q] = last;
-        mbar_arrive(&ffull_bar[b * 4 + q]);
-        if (b) ++fills1; else ++fills0;
-        b ^= 1u;
-        ++d_hand;
-        if (!last) {
-          const long long t = DBG ? clock64() : 0;
-          mbar_wait_backoff(&fempty_bar[b * 4 + q], ((b ? fills1 : fills0) & 1u) ^ 1u);
-          if (DBG) d_wait_e += clock64() - t;
-        }
-        wbase = fv0 + b * kFifoBytes;
-        waddr = wbase;
-        wlimit = wbase + (kFifo - kCheck) * (kBM * 4);
-      };
 
       for (int nt = t0; nt < t1; ++nt, ++tile) {
         const uint32_t as = tile & 1u;
@@ -817,17 +847,26 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]), c,
                                          c + 1, c + 2, c + 3);
             if ((j + 4) % kCheck == 0) {
-              if (__any_sync(0xffffffffu, waddr > wlimit)) handoff(0u);
+              if (__any_sync(0xffffffffu, waddr > wlimit)) {
+                st = scanner_handoff<DBG>(st, (waddr - wbase) / (kBM * 4), 0u, cnt_addr, meta + q,
+                                          ffull_bar + q, fempty_bar + q, lane, &d_wait_e);
+                ++d_hand;
+                wbase = fv0 + (st & 1u) * kFifoBytes;
+                waddr = wbase;
+                wlimit = wbase + (kFifo - kCheck) * (kBM * 4);
+              }
             }
           }
         };
 
+        // 32 accumulator columns per loop trip (two tcgen05.ld.x16, double-buffered): with the
+        // hand-over out of line the loop body stays within the ~6 KB L0 instruction cache
         uint32_t ra[16], rb[16];
         tmem_ld16(taddr, ra);
 #pragma unroll 1
-        for (int c4 = 0; c4 < kBN / 64; ++c4) {
-          const uint32_t ta = taddr + c4 * 64;
-          const int cb = col0 + c4 * 64;
+        for (int c2 = 0; c2 < kBN / 32; ++c2) {
+          const uint32_t ta = taddr + c2 * 32;
+          const int cb = col0 + c2 * 32;
           uint32_t tb, tq;   // the selector's latest threshold for this row (valid for this item only)
           asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tb), "=r"(tq) : "r"(tau_addr) : "memory");
           tmem_ld_wait16(ra);
@@ -835,19 +874,15 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (tq == seq) tau = fmaxf(tau, __uint_as_float(tb));
           process(ra, cb);
           tmem_ld_wait16(rb);
-          tmem_ld16(ta + 32, ra);
+          if (c2 + 1 < kBN / 32) tmem_ld16(ta + 32, ra);
           process(rb, cb + 16);
-          tmem_ld_wait16(ra);
-          tmem_ld16(ta + 48, rb);
-          process(ra, cb + 32);
-          tmem_ld_wait16(rb);
-          if (c4 + 1 < kBN / 64) tmem_ld16(ta + 64, ra);
-          process(rb, cb + 48);
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);
       }
-      handoff(1u);
+      st = scanner_handoff<DBG>(st, (waddr - wbase) / (kBM * 4), 1u, cnt_addr, meta + q, ffull_bar + q,
+                                fempty_bar + q, lane, &d_wait_e);
+      ++d_hand;
     }
     if (DBG && dbg && lane == 0) {
       unsigned long long* o = dbg + (static_cast<size_t>(blockIdx.x) * 8 + (warp - 4)) * 8;
@@ -1108,7 +1143,9 @@ static int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint
   return r == CUDA_SUCCESS ? kOk : static_cast<int>(1000 + r);
 }
 
-static int g_encode_dbg = 0;  // experiments only (wsae_debug_encode_mode): 1 = skip epilogue, 2 = no compaction
+// experiments only (wsae_debug_encode_mode): 1 = skip epilogue, 2 = no compaction (both: one-warp
+// epilogue kernel), 3 = scanner filter closed (scanner + selector kernel with the counters buffer set)
+static int g_encode_dbg = 0;
 
 template <int CAP, int STAGES>
 static int launch_encode(const CUtensorMap& ta, const CUtensorMap& tw, int B, int F, int k,
@@ -1157,11 +1194,11 @@ static int launch_encode2(const CUtensorMap& ta, const CUtensorMap& tw, int B, i
   if (g_encode_dbg_buf != nullptr)
     encode_topk2_kernel<STAGES, true><<<grid, 384, smem, stream>>>(
         ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx,
-        g_encode_dbg_buf);
+        g_encode_dbg_buf, g_encode_dbg);
   else
     encode_topk2_kernel<STAGES, false><<<grid, 384, smem, stream>>>(
         ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx,
-        nullptr);
+        nullptr, 0);
   return static_cast<int>(cudaGetLastError());
 }
 
