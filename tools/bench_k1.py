@@ -43,7 +43,7 @@ def main() -> None:
         xs = [ops.pack_activations(torch.randn(B, args.d, device=dev), None, 1) for _ in range(nrot)]
         for mode in [int(s) for s in args.modes.split(",")]:
             lib.wsae_debug_encode_mode(mode)
-            if mode == 3:     # lives in the instrumented build of the scanner + selector kernel
+            if mode >= 3:     # lives in the instrumented build of the scanner + selector kernel
                 lib.wsae_debug_encode_counters.argtypes = [ctypes.c_void_p]
                 dbuf = torch.zeros(148 * 8 * 8, dtype=torch.int64, device=dev)
                 lib.wsae_debug_encode_counters(dbuf.data_ptr())
@@ -57,8 +57,15 @@ def main() -> None:
             t1.record()
             torch.cuda.synchronize()
             ms = t0.elapsed_time(t1) / args.iters
-            if mode == 3:
+            if mode >= 3:
+                torch.cuda.synchronize()
+                dbuf.zero_()
+                ops.encode_topk(xs[0], wp, B, args.F, args.d, 1, args.k)
+                torch.cuda.synchronize()
                 lib.wsae_debug_encode_counters(None)
+                c3 = dbuf.view(148, 8, 8).double()[:, :4]
+                it3 = B / 128 / 148
+                print(f"  mode {mode} scanner: wait-tmem {c3[..., 2].mean() / it3:9.0f} cyc/item  total {c3[..., 3].mean() / it3:9.0f}")
             tf = 2.0 * B * args.d * args.F / ms / 1e9
             print(f"B={B} d={args.d} F={args.F} k={args.k} mode={mode}: {ms * 1e3:8.1f} us  "
                   f"{tf:7.1f} TFLOP/s (algorithmic)  {B / ms / 1e3:8.2f} Mrows/s", flush=True)
@@ -77,6 +84,8 @@ def main() -> None:
                   f"  wait-tmem {sc[..., 2].mean() / items:9.0f}  total {sc[..., 3].mean() / items:9.0f}")
             print(f"  selector: selections/item {se[..., 0].mean() / items:6.1f}  wait-full {se[..., 1].mean() / items:9.0f} cyc/item"
                   f"  total {se[..., 3].mean() / items:9.0f}", flush=True)
+            print(f"  selector sections (cyc/item): load {se[..., 2].mean() / items:8.0f}  select {se[..., 4].mean() / items:8.0f}"
+                  f"  repack {se[..., 5].mean() / items:8.0f}  reload {se[..., 6].mean() / items:8.0f}  final {se[..., 7].mean() / items:8.0f}", flush=True)
         del xs
 
 

@@ -584,13 +584,17 @@ __device__ __forceinline__ void reg_alloc_dec() {
 }
 
 // Predicated append of four (value, index) pairs at cursor w; IOFF = byte offset of the index array.
-// (A variant whose four slot addresses are w + prefix sums of the pass flags - one loop-carried add
-// per four values instead of a serial cursor chain - measured SLOWER, 277 vs 260 us: the scanner is
-// not bound by that chain but by issue slots and instruction fetch.)
+// `slot` is the slot stride (kBM * 4 bytes) passed in a REGISTER that ptxas cannot constant-fold (it
+// comes from a kernel parameter): with an immediate, ptxas rewrites `selp t, 512, 0, p; add a1, a0, t`
+// into `VIADD a1 = a0 + 512; @!p MOV a1 = a0` - two dependent instructions per value on the
+// loop-carried cursor chain, which bounded the scanner at ~15 cycles per value (ncu: `wait` stalls on
+// exactly those pairs).  SEL + IADD keeps one dependent instruction per value.
+// (A variant whose four slot addresses are w + prefix sums of the pass flags measured slower, 277 vs
+// 260 us: ptxas built the prefix sums from the same VIADD/MOV pairs.)
 template <int IOFF>
 __device__ __forceinline__ uint32_t append4(uint32_t w, float thr, float v0, float v1, float v2,
                                             float v3, uint32_t i0, uint32_t i1, uint32_t i2,
-                                            uint32_t i3) {
+                                            uint32_t i3, uint32_t slot) {
   uint32_t wn;
   asm volatile(
       "{\n\t"
@@ -619,7 +623,7 @@ __device__ __forceinline__ uint32_t append4(uint32_t w, float thr, float v0, flo
       "}\n"
       : "=r"(wn)
       : "r"(w), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(thr), "r"(i0), "r"(i1), "r"(i2), "r"(i3),
-        "n"(IOFF), "n"(kBM * 4)
+        "n"(IOFF), "r"(slot)
       : "memory");
   return wn;
 }
@@ -741,7 +745,7 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_w, int B, int F, int k, int ksteps,
                     int num_m_blocks, int num_n_tiles, int nsplit, int tiles_per_split,
                     float* __restrict__ out_val, int32_t* __restrict__ out_idx,
-                    unsigned long long* __restrict__ dbg, int mode) {
+                    unsigned long long* __restrict__ dbg, int mode, uint32_t slot) {
   using SM = Encode2Smem<STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -821,7 +825,7 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int t1 = min(t0 + tiles_per_split, num_n_tiles);
       ++seq;
       // mode 3 (experiments): nothing passes the filter - times the GEMM pipeline + bare scan
-      float tau = (DBG && mode == 3) ? __uint_as_float(0x7f800000u) : neg_inf;
+      float tau = (DBG && mode >= 3) ? __uint_as_float(0x7f800000u) : neg_inf;
       mbar_wait_backoff(&fempty_bar[(st & 1u) * 4 + q], ((st >> (1u + (st & 1u))) & 1u) ^ 1u);
       uint32_t wbase = fv0 + (st & 1u) * kFifoBytes;
       uint32_t waddr = wbase;
@@ -845,7 +849,7 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const uint32_t c = static_cast<uint32_t>(cbase + j);
             waddr = append4<kFifoIdxOff>(waddr, tau, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]), c,
-                                         c + 1, c + 2, c + 3);
+                                         c + 1, c + 2, c + 3, slot);
             if ((j + 4) % kCheck == 0) {
               if (__any_sync(0xffffffffu, waddr > wlimit)) {
                 st = scanner_handoff<DBG>(st, (waddr - wbase) / (kBM * 4), 0u, cnt_addr, meta + q,
@@ -872,10 +876,18 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_ld_wait16(ra);
           tmem_ld16(ta + 16, rb);
           if (tq == seq) tau = fmaxf(tau, __uint_as_float(tb));
-          process(ra, cb);
+          if (DBG && mode == 4) {        // experiments: TMEM reads only (one compare keeps the loads live)
+            if (__uint_as_float(ra[0]) == tau) waddr += 4;
+          } else {
+            process(ra, cb);
+          }
           tmem_ld_wait16(rb);
           if (c2 + 1 < kBN / 32) tmem_ld16(ta + 32, ra);
-          process(rb, cb + 16);
+          if (DBG && mode == 4) {
+            if (__uint_as_float(rb[0]) == tau) waddr += 4;
+          } else {
+            process(rb, cb + 16);
+          }
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);
@@ -900,7 +912,7 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
     float v[N];          // [0, kFifo): survivors, [kFifo, N): the batch being merged
     uint32_t ix[N];
     uint32_t uses0 = 0, uses1 = 0, b = 0, seq = 0;
-    unsigned long long d_wait_f = 0, d_sel = 0;
+    unsigned long long d_wait_f = 0, d_sel = 0, d_t_load = 0, d_t_select = 0, d_t_repack = 0, d_t_reload = 0, d_t_final = 0;
     const long long d_t0 = clock64();
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int m_blk = item / nsplit;
@@ -924,27 +936,33 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
         asm volatile("ld.shared.u16 %0, [%1];" : "=h"(n16) : "r"(cnt_addr + b * (kBM * 2)) : "memory");
         const int n = static_cast<int>(n16);
         const uint32_t last = meta[b * 4 + q];
+        long long tt0 = DBG ? clock64() : 0;
 #pragma unroll
         for (int s = 0; s < kFifo; ++s) {
           const float x = lds_f32(base + s * (kBM * 4));
           v[kFifo + s] = (s < n) ? x : neg_inf;
           ix[kFifo + s] = lds_u32(base + s * (kBM * 4) + kFifoIdxOff);
         }
+        if (DBG) { const long long t = clock64(); d_t_load += t - tt0; tt0 = t; }
         const int total = scnt + n;
         float thr = neg_inf;
         bool ties = false;
         int tie_left = 0;
-        if (__any_sync(0xffffffffu, total > k + kSlack)) {
-          thr = select_threshold<N>(v, total, k, kSlack, tau, ties, tie_left);
+        // the item's last batch is reduced to EXACTLY k (slack 0; ties keep the lowest feature
+        // index), so the survivors re-read below are the result - no separate finalisation pass
+        const int slack = last ? 0 : kSlack;
+        if (__any_sync(0xffffffffu, total > k + slack)) {
+          thr = select_threshold<N>(v, total, k, slack, tau, ties, tie_left);
           ++d_sel;
         }
+        if (DBG) { const long long t = clock64(); d_t_select += t - tt0; tt0 = t; }
         // repack the survivors (old ones first: ascending feature index) through the drained FIFO
         uint32_t w = base;
         if (!__any_sync(0xffffffffu, ties)) {
 #pragma unroll
           for (int s = 0; s < N; s += 4)
             w = append4<kFifoIdxOff>(w, thr, v[s], v[s + 1], v[s + 2], v[s + 3], ix[s], ix[s + 1],
-                                     ix[s + 2], ix[s + 3]);
+                                     ix[s + 2], ix[s + 3], slot);
         } else {
 #pragma unroll
           for (int s = 0; s < N; ++s) {
@@ -959,12 +977,14 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         scnt = static_cast<int>((w - base) / (kBM * 4));
+        if (DBG) { const long long t = clock64(); d_t_repack += t - tt0; tt0 = t; }
 #pragma unroll
         for (int s = 0; s < kFifo; ++s) {
           const float x = lds_f32(base + s * (kBM * 4));
           v[s] = (s < scnt) ? x : neg_inf;
           ix[s] = lds_u32(base + s * (kBM * 4) + kFifoIdxOff);
         }
+        if (DBG) { const long long t = clock64(); d_t_reload += t - tt0; tt0 = t; }
         if (thr > tau) {
           tau = thr;
           asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(tau_addr), "r"(__float_as_uint(tau)),
@@ -976,47 +996,41 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
         b ^= 1u;
         if (last) break;
       }
-      // ---- exactly k: drop the surplus by min-extraction (ties: highest index goes first) ----
-      const float pinf = __uint_as_float(0x7f800000u);
-      int surplus = scnt - k;
-#pragma unroll
-      for (int s = 0; s < kFifo; ++s) v[s] = (s < scnt) ? v[s] : pinf;
-      while (__any_sync(0xffffffffu, surplus > 0)) {
-        float vmin = pinf;
-        int pos = -1;
-#pragma unroll
-        for (int s = 0; s < kFifo; ++s) {
-          const bool le = v[s] <= vmin && v[s] != pinf;
-          vmin = le ? v[s] : vmin;
-          pos = le ? s : pos;
-        }
-        if (surplus <= 0) pos = -1;
-#pragma unroll
-        for (int s = 0; s < kFifo; ++s) v[s] = (s == pos) ? pinf : v[s];
-        --surplus;
-      }
+      // ---- write the row's k (value, index) pairs: v[0 .. scnt) in ascending feature index ----
+      const long long tf0 = DBG ? clock64() : 0;
       const int row = m_blk * kBM + row_in_blk;
       if (row < B) {
         float* ov = out_val + (static_cast<size_t>(row) * nsplit + sp) * k;
         int32_t* oi = out_idx + (static_cast<size_t>(row) * nsplit + sp) * k;
-        int w = 0;
+        if ((k & 3) == 0) {          // 16-byte stores (rows of k * 4 bytes stay 16-byte aligned)
 #pragma unroll
-        for (int s = 0; s < kFifo; ++s) {
-          if (v[s] != pinf && w < k) {
-            ov[w] = v[s];
-            oi[w] = static_cast<int32_t>(ix[s]);
-            ++w;
+          for (int s = 0; s < 32; s += 4) {
+            if (s < k) {
+              // fewer than k candidates (split narrower than k, NaN rows): pad with (-inf, -1)
+              const int4 iv = make_int4(s < scnt ? static_cast<int>(ix[s]) : -1,
+                                        s + 1 < scnt ? static_cast<int>(ix[s + 1]) : -1,
+                                        s + 2 < scnt ? static_cast<int>(ix[s + 2]) : -1,
+                                        s + 3 < scnt ? static_cast<int>(ix[s + 3]) : -1);
+              *reinterpret_cast<float4*>(ov + s) = make_float4(v[s], v[s + 1], v[s + 2], v[s + 3]);
+              *reinterpret_cast<int4*>(oi + s) = iv;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < 32; ++s) {
+            if (s < k) {
+              ov[s] = v[s];
+              oi[s] = s < scnt ? static_cast<int32_t>(ix[s]) : -1;
+            }
           }
         }
-        for (; w < k; ++w) {
-          ov[w] = neg_inf;
-          oi[w] = -1;
-        }
       }
+      if (DBG) d_t_final += clock64() - tf0;
     }
     if (DBG && dbg && lane == 0) {
       unsigned long long* o = dbg + (static_cast<size_t>(blockIdx.x) * 8 + (warp - 4)) * 8;
       o[0] = d_sel; o[1] = d_wait_f; o[3] = clock64() - d_t0;
+      o[2] = d_t_load; o[4] = d_t_select; o[5] = d_t_repack; o[6] = d_t_reload; o[7] = d_t_final;
     }
   }
 
@@ -1194,11 +1208,11 @@ static int launch_encode2(const CUtensorMap& ta, const CUtensorMap& tw, int B, i
   if (g_encode_dbg_buf != nullptr)
     encode_topk2_kernel<STAGES, true><<<grid, 384, smem, stream>>>(
         ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx,
-        g_encode_dbg_buf, g_encode_dbg);
+        g_encode_dbg_buf, g_encode_dbg, static_cast<uint32_t>(kBM * 4));
   else
     encode_topk2_kernel<STAGES, false><<<grid, 384, smem, stream>>>(
         ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx,
-        nullptr, 0);
+        nullptr, 0, static_cast<uint32_t>(kBM * 4));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1245,11 +1259,14 @@ extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int 
   float* kv = nsplit > 1 ? part_val : out_val;
   int32_t* ki = nsplit > 1 ? part_idx : out_idx;
   const int ksteps = k_used_cols / 16;
+#ifndef WSAE_K1_STAGES
+#define WSAE_K1_STAGES 3
+#endif
   if (k + kSlack <= kFifo && g_encode_variant == 2)
-    rc = launch_encode2<3>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
+    rc = launch_encode2<WSAE_K1_STAGES>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
                            tiles_per_split, kv, ki, num_sms, stream);
   else if (k <= 32)
-    rc = launch_encode<80, 3>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
+    rc = launch_encode<80, WSAE_K1_STAGES>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
                               tiles_per_split, kv, ki, num_sms, stream);
   else
     rc = launch_encode<128, 2>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
