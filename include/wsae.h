@@ -29,7 +29,7 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 102: + wsae_decode_backward, wsae_adamw_multi, wsae_scatter_rows). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 103: + wsae_feature_topk_*). */
 int wsae_abi_version(void);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
@@ -169,6 +169,25 @@ typedef struct {
 } wsae_adamw_tensor_t;
 int wsae_adamw_multi(const wsae_adamw_tensor_t* tensors, int count, const float* hyper,
                      const double* grad_sumsq, float renorm_eps, wsae_stream_t stream);
+
+/* ---- Per-feature top-K activating examples (analysis/feature_viz.py:94-158 TopKTracker.update,
+ *      :425-484 collect_top_activations) --------------------------------------------------------
+ * Consumes the sparse code the hot path produces.  Entries i = 0..n-1 are (feat[i], val[i]) with
+ * row(i) = rows ? rows[i] : i / k (k = entries per row of an [B, k] TopK result); an entry counts
+ * when val > 0 (and 0 <= feat < F).  Per feature the K largest values seen so far are kept with
+ * their sample id (sample_ids ? sample_ids[row] : sample_base + row) and position
+ * (pos_ids ? pos_ids[row] : 0): top_val [F,K] descending with -inf = empty, top_sample int64 [F,K],
+ * top_pos int32 [F,K] (-1 = empty), top_count int32 [F].  An entry displaces the current K-th only
+ * if STRICTLY larger (the reference's heap rule), so among equal values the earlier arrival -
+ * earlier call, then lower row - stays.  *total += number of counted entries
+ * (TopKTracker.total_activations).  K <= 32, n < 2^31.  ws: wsae_feature_topk_workspace bytes. */
+int wsae_feature_topk_workspace(long long n, int F, unsigned long long* bytes);
+int wsae_feature_topk_update(const int32_t* feat, const float* val, const int32_t* rows /*nullable*/,
+                             long long n, int k, const long long* sample_ids /*nullable*/,
+                             long long sample_base, const int32_t* pos_ids /*nullable*/, int F, int K,
+                             float* top_val, long long* top_sample, int32_t* top_pos,
+                             int32_t* top_count, unsigned long long* total, void* ws,
+                             unsigned long long ws_bytes, wsae_stream_t stream);
 
 /* ---- experiments only (tools/bench_k1.py); not part of the product path -----------------------
  * variant: 1 = one epilogue warp per TMEM lane quarter, 2 = scanner + selector warps (default);

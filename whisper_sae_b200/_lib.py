@@ -10,7 +10,7 @@ import ctypes
 import os
 import shutil
 import subprocess
-from ctypes import POINTER, c_double, c_float, c_int, c_int32, c_longlong, c_void_p
+from ctypes import POINTER, c_double, c_float, c_int, c_int32, c_longlong, c_ulonglong, c_void_p
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -106,6 +106,12 @@ _SIGNATURES = {
     "wsae_densify_hidden": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
     "wsae_cast_bf16": ([c_void_p, c_void_p, c_longlong, c_void_p], c_int),
     "wsae_sumsq": ([c_void_p, c_longlong, c_void_p, c_void_p], c_int),
+    "wsae_feature_topk_workspace": ([c_longlong, c_int, POINTER(c_ulonglong)], c_int),
+    "wsae_feature_topk_update": (
+        [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_void_p, c_int, c_int,
+         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ulonglong, c_void_p],
+        c_int,
+    ),
     "wsae_fused_adamw": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p],
         c_int,

@@ -385,3 +385,38 @@ def adamw_multi_(entries: list[tuple[Tensor, Tensor, Tensor, Tensor, int]], hype
         a.p, a.g, a.m, a.v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
         a.n, a.row_len, a.reserved = p.numel(), int(row_len), 0
     _run("wsae_adamw_multi", lib.wsae_adamw_multi, arr, len(entries), _ptr(hyper), _ptr(grad_sumsq), float(renorm_eps), _stream())
+
+
+def feature_topk_update(feat: Tensor, val: Tensor, rows: Tensor | None, k: int,
+                        sample_ids: Tensor | None, sample_base: int, pos_ids: Tensor | None,
+                        top_val: Tensor, top_sample: Tensor, top_pos: Tensor, top_count: Tensor,
+                        total: Tensor) -> None:
+    """Merge a batch of (feature, value) entries into the per-feature top-K lists, in place
+    (wsae_feature_topk_update; analysis/feature_viz.py:94-158)."""
+    _need_cuda(feat, val, rows, sample_ids, pos_ids, top_val, top_sample, top_pos, top_count, total)
+    if feat.dtype != torch.int32 or not feat.is_contiguous():
+        raise RuntimeError("feat must be a contiguous int32 tensor")
+    _f32c(val, "val")
+    _f32c(top_val, "top_val")
+    if feat.numel() != val.numel():
+        raise RuntimeError("feat and val must have the same number of entries")
+    if rows is not None and (rows.dtype != torch.int32 or rows.numel() != feat.numel()):
+        raise RuntimeError("rows must be int32 with one entry per (feat, val) pair")
+    if sample_ids is not None and sample_ids.dtype != torch.int64:
+        raise RuntimeError("sample_ids must be int64")
+    if pos_ids is not None and pos_ids.dtype != torch.int32:
+        raise RuntimeError("pos_ids must be int32")
+    if top_sample.dtype != torch.int64 or top_pos.dtype != torch.int32 or top_count.dtype != torch.int32 \
+            or total.dtype != torch.int64:
+        raise RuntimeError("tracker state dtypes: top_sample int64, top_pos int32, top_count int32, total int64")
+    F, K = top_val.shape
+    n = feat.numel()
+    if n == 0:
+        return
+    lib = _lib.load()
+    need = ctypes.c_ulonglong(0)
+    _lib.check(lib.wsae_feature_topk_workspace(n, F, ctypes.byref(need)), "wsae_feature_topk_workspace")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=feat.device)
+    _run("wsae_feature_topk_update", lib.wsae_feature_topk_update, _ptr(feat), _ptr(val), _ptr(rows), n,
+         int(k), _ptr(sample_ids), int(sample_base), _ptr(pos_ids), F, K, _ptr(top_val), _ptr(top_sample),
+         _ptr(top_pos), _ptr(top_count), _ptr(total), _ptr(ws), need.value, _stream(), launches=4)
