@@ -491,7 +491,8 @@ def main() -> None:
         # the launch-bound YAML batch, for the record
         cfg_batch = 128
         tr_small, _ = make_trainer(cfg_batch, dev, layer_seed=rank, use_amp=(args.precision == "bf16"))
-        small = [dev_batches[0][i * cfg_batch:(i + 1) * cfg_batch].contiguous() for i in range(16)]
+        small_rows = synth(16 * cfg_batch, D_MODEL, seed=4321 + rank).to(dev)
+        small = [small_rows[i * cfg_batch:(i + 1) * cfg_batch].contiguous() for i in range(16)]
         sec_small, _ = time_steps(tr_small, small, 100, 10, False)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
