@@ -29,7 +29,7 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 103: + wsae_feature_topk_*). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 104: + wsae_feature_topk_*, wsae_debug_wgrad_cluster). */
 int wsae_abi_version(void);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
@@ -197,6 +197,7 @@ int wsae_feature_topk_update(const int32_t* feat, const float* val, const int32_
 int wsae_debug_encode_variant(int variant);
 int wsae_debug_encode_mode(int mode);
 int wsae_debug_encode_counters(void* device_buf);
+int wsae_debug_wgrad_cluster(int max_cluster_size); /* 1, 2 (default), 4, 8: upper bound for wsae_wgrad_gemm's cluster */
 
 #ifdef __cplusplus
 }

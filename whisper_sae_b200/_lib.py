@@ -55,6 +55,7 @@ _SIGNATURES = {
     "wsae_debug_encode_variant": ([c_int], c_int),
     "wsae_debug_encode_mode": ([c_int], c_int),
     "wsae_debug_encode_counters": ([c_void_p], c_int),
+    "wsae_debug_wgrad_cluster": ([c_int], c_int),
     "wsae_adamw_multi": ([POINTER(AdamwTensor), c_int, c_void_p, c_void_p, c_float, c_void_p], c_int),
     "wsae_abi_version": ([], c_int),
     "wsae_packed_k": ([c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)], c_int),

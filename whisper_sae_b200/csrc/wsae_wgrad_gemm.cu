@@ -11,7 +11,13 @@
 //   * the sparse operand is expanded on the fly: for every (feature tile, 64-row chunk) the builder
 //     warps zero a 128x64 bf16 tile in shared memory and scatter that cell's few entries into it,
 //     in the SWIZZLE_128B K-major layout the MMA expects — S is never dense in HBM;
-//   * fp32 accumulators live in TMEM; split-K CTAs combine with red.global.add.f32.
+//   * fp32 accumulators live in TMEM; split-K CTAs combine with red.global.add.f32;
+//   * the CTAs of a thread-block cluster work on different feature tiles of the SAME row chunks, so
+//     they need the same R tiles: each CTA fetches 1/c of every R tile and TMA-multicasts it into
+//     all c CTAs' shared memory (L2 -> SM traffic / c; without it every one of the F/128 feature
+//     tiles streams all of R from L2: 24 x 58 MB per launch at the bench shape).  A stage is
+//     reusable when the MMAs of ALL c CTAs have read it: the commit is multicast to every CTA's
+//     `empty` barrier, which counts c arrivals.
 // The bucketing (entries grouped by feature tile, then by row chunk) is three small kernels below.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -132,12 +138,16 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // cluster: consecutive blockIdx.x; its CTAs share (n tile, k split) and take adjacent feature tiles
+  const int csize = static_cast<int>(cluster_nctarank());
+  const int crank = static_cast<int>(cluster_ctarank());
+  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
   // work item -> (feature tile, n tile, k split)
-  int item = blockIdx.x;
+  int item = blockIdx.x / csize;
   const int ks = item % ksplit;
   item /= ksplit;
   const int nt = item % n_nt;
-  const int ft = item / n_nt;
+  const int ft = (item / n_nt) * csize + crank;
   const int per = ceil_div(n_chunks, ksplit);
   const int c0 = ks * per;
   const int c1 = min(n_chunks, c0 + per);
@@ -153,7 +163,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&r_full[s], 1);
       mbar_init(&a_full[s], 128);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], static_cast<uint32_t>(csize));   // one commit arrival per CTA of the cluster
     }
     mbar_init(acc_full, 1);
     mbar_fence_init();
@@ -164,6 +174,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();   // peers' barriers are initialised before anything is multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -176,8 +187,16 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
         mbar_wait(&empty[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&r_full[stage], static_cast<uint32_t>(nb_here * kWgRBlock));
         uint8_t* dst = smem + stage * stage_bytes + kWgATile;
-        for (int b = 0; b < nb_here; ++b)   // one swizzled 64x64 block per bulk copy
-          tma_load_2d(dst + b * kWgRBlock, &tmap_r, &r_full[stage], (nb0 + b) * 64, (c0 + c) * kWgRows);
+        if (csize == 1) {
+          for (int b = 0; b < nb_here; ++b)   // one swizzled 64x64 block per bulk copy
+            tma_load_2d(dst + b * kWgRBlock, &tmap_r, &r_full[stage], (nb0 + b) * 64, (c0 + c) * kWgRows);
+        } else {
+          // this CTA's share of the blocks, delivered to every CTA of the cluster (each one's r_full
+          // expects the whole tile: the other blocks arrive from its peers)
+          for (int b = crank; b < nb_here; b += csize)
+            tma_load_2d_multicast(dst + b * kWgRBlock, &tmap_r, &r_full[stage], (nb0 + b) * 64,
+                                  (c0 + c) * kWgRows, cmask);
+        }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -212,7 +231,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
             umma_bf16(tmem_base + 256, da + static_cast<uint64_t>(2 * kk),
                       db2 + static_cast<uint64_t>((kk * 16 * 128) >> 4), idesc2, acc);
         }
-        umma_commit(&empty[stage]);
+        if (csize == 1) umma_commit(&empty[stage]);
+        else umma_commit_multicast(&empty[stage], cmask);
         if (c == nchunk - 1) umma_commit(acc_full);
       }
       __syncwarp();
@@ -223,10 +243,46 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
     }
   } else if (warp >= 4) {
     // ===================== sparse-tile builders, then epilogue =====================
+    // The cell's entries come from global memory through two dependent loads (offsets -> entries,
+    // ~2 L2 latencies).  They are software-pipelined two chunks deep - the offsets of chunk c+2 and
+    // the entries of chunk c+1 are in flight while chunk c's tile is built - otherwise that latency
+    // chain (~1500 cycles per chunk) paces the whole GEMM (tensor pipe 56 % active in round 1).
     const int t = threadIdx.x - 128;  // 0..127
     int stage = 0;
     uint32_t phase = 0;
+    constexpr int kPre = 2;           // entries per thread held in registers (cells hold ~k*64*128/F)
+    auto cell_of = [&](int c) { return static_cast<size_t>(c0 + c) * (n_ft + 1) + ft; };
+    int2 off_next = make_int2(0, 0), off_next2 = make_int2(0, 0);
+    if (nchunk > 0) off_next = make_int2(offsets[cell_of(0)], offsets[cell_of(0) + 1]);
+    if (nchunk > 1) off_next2 = make_int2(offsets[cell_of(1)], offsets[cell_of(1) + 1]);
+    uint32_t m_next[kPre];
+    float v_next[kPre];
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) {
+      const int e = off_next.x + t + j * 128;
+      m_next[j] = (nchunk > 0 && e < off_next.y) ? ent_meta[e] : 0u;
+      v_next[j] = (nchunk > 0 && e < off_next.y) ? ent_val[e] : 0.f;
+    }
     for (int c = 0; c < nchunk; ++c) {
+      // rotate the pipeline registers: this chunk's data was loaded one iteration ago
+      const int2 off = off_next;
+      uint32_t m_cur[kPre];
+      float v_cur[kPre];
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) {
+        m_cur[j] = m_next[j];
+        v_cur[j] = v_next[j];
+      }
+      off_next = off_next2;
+      if (c + 2 < nchunk) off_next2 = make_int2(offsets[cell_of(c + 2)], offsets[cell_of(c + 2) + 1]);
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) {
+        const int e = off_next.x + t + j * 128;
+        const bool ok = (c + 1 < nchunk) && e < off_next.y;
+        m_next[j] = ok ? ent_meta[e] : 0u;
+        v_next[j] = ok ? ent_val[e] : 0.f;
+      }
+
       mbar_wait(&empty[stage], phase ^ 1u);
       uint8_t* a_tile = smem + stage * stage_bytes;
       // zero 16 KB: consecutive threads clear consecutive 16-byte words (conflict-free)
@@ -235,14 +291,15 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
 #pragma unroll
       for (int i = 0; i < 8; ++i) tile4[i * 128 + t] = z;
       named_bar_sync(1, 128);
-      const size_t cell = static_cast<size_t>(c0 + c) * (n_ft + 1) + ft;
-      const int e0 = offsets[cell], e1 = offsets[cell + 1];
-      for (int e = e0 + t; e < e1; e += 128) {
-        const uint32_t m = ent_meta[e];
+      auto put = [&](uint32_t m, float v) {
         const uint32_t row = m & 0xFFu, fl = m >> 8;
-        const uint32_t off = fl * 128u + ((((row >> 3) ^ (fl & 7u)) & 7u) << 4) + ((row & 7u) << 1);
-        *reinterpret_cast<__nv_bfloat16*>(a_tile + off) = __float2bfloat16_rn(ent_val[e]);
-      }
+        const uint32_t o = fl * 128u + ((((row >> 3) ^ (fl & 7u)) & 7u) << 4) + ((row & 7u) << 1);
+        *reinterpret_cast<__nv_bfloat16*>(a_tile + o) = __float2bfloat16_rn(v);
+      };
+#pragma unroll
+      for (int j = 0; j < kPre; ++j)
+        if (off.x + t + j * 128 < off.y) put(m_cur[j], v_cur[j]);
+      for (int e = off.x + t + kPre * 128; e < off.y; e += 128) put(ent_meta[e], ent_val[e]);   // crowded cell
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&a_full[stage]);
       if (++stage == STAGES) {
@@ -282,6 +339,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();   // no CTA leaves while peers may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -303,6 +361,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 wg_encode_fn() {
 }  // namespace wsae
 
 using namespace wsae;
+
+static int g_wgrad_cluster = 2;   // upper bound on the cluster size (wsae_debug_wgrad_cluster: experiments)
+extern "C" int wsae_debug_wgrad_cluster(int c) {
+  if (c != 1 && c != 2 && c != 4 && c != 8) return kBadArg;
+  g_wgrad_cluster = c;
+  return kOk;
+}
 
 extern "C" int wsae_bucket_cells(int B, int F, int* n_chunks, int* n_ft) {
   if (B <= 0 || F <= 0) return kBadArg;
@@ -356,25 +421,59 @@ extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int ksplit = sms / (n_ft * n_nt);
+  const int stage_bytes = kWgATile + nb_tile * kWgRBlock;
+  const int stages = (3 * stage_bytes + 1024 + 256 <= 227 * 1024) ? 3 : 2;
+  const int smem = stages * stage_bytes + 1024 + 256;
+  if (smem > 227 * 1024) return kUnsupported;
+  auto kern = stages == 3 ? wgrad_gemm_kernel<3> : wgrad_gemm_kernel<2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return static_cast<int>(e);
+
+  // cluster size: CTAs of a cluster share their R tiles by TMA multicast.  Largest of {g_wgrad_cluster,
+  // 2, 1} that divides the feature-tile count and that the device can keep resident on (almost) all SMs.
+  int csize = 1, resident = sms;
+  for (int c = g_wgrad_cluster; c >= 2; c >>= 1) {
+    if (n_ft % c != 0) continue;
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(static_cast<unsigned>(sms / c * c));
+    q.blockDim = dim3(256);
+    q.dynamicSmemBytes = static_cast<size_t>(smem);
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = static_cast<unsigned>(c);
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    q.attrs = qa;
+    q.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &q) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    if (nclusters * c >= (sms * 7) / 8) {   // keep >= 7/8 of the SMs busy
+      csize = c;
+      resident = nclusters * c;
+      break;
+    }
+  }
+  int ksplit = resident / (n_ft * n_nt);
   if (ksplit < 1) ksplit = 1;
   if (ksplit > n_chunks) ksplit = n_chunks;
-  const int stage_bytes = kWgATile + nb_tile * kWgRBlock;
   const int grid = n_ft * n_nt * ksplit;
-  cudaError_t e;
-  if (3 * stage_bytes + 1024 + 256 <= 227 * 1024) {
-    const int smem = 3 * stage_bytes + 1024 + 256;
-    e = cudaFuncSetAttribute(wgrad_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    wgrad_gemm_kernel<3><<<grid, 256, smem, stream>>>(tm, F, d, n_chunks, n_ft, n_nt, nb_tile, ksplit,
-                                                      offsets, ent_meta, ent_val, grad_out, alpha, out);
-  } else {
-    const int smem = 2 * stage_bytes + 1024 + 256;
-    if (smem > 227 * 1024) return kUnsupported;
-    e = cudaFuncSetAttribute(wgrad_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    wgrad_gemm_kernel<2><<<grid, 256, smem, stream>>>(tm, F, d, n_chunks, n_ft, n_nt, nb_tile, ksplit,
-                                                      offsets, ent_meta, ent_val, grad_out, alpha, out);
-  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, tm, F, d, n_chunks, n_ft, n_nt, nb_tile, ksplit, offsets, ent_meta,
+                         ent_val, grad_out, alpha, out);
+  if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaGetLastError());
 }
