@@ -80,16 +80,29 @@ bucket_chunk_kernel(const int32_t* __restrict__ idx, const float* __restrict__ v
     if (lane == 0) orow[n_ft] = carry;
   }
   __syncthreads();
+  // grouped entries are staged in shared memory and copied out with coalesced stores (the cursor
+  // positions are scattered over the chunk's 64 * k slots: direct global stores touched one sector
+  // per lane)
+  uint32_t* s_meta = reinterpret_cast<uint32_t*>(s_cell + n_ft);
+  float* s_a = reinterpret_cast<float*>(s_meta + kWgRows * k);
+  float* s_b = s_a + kWgRows * k;
   for (int e = threadIdx.x; e < nrow * k; e += blockDim.x) {
     const int32_t f = idx[g0 + e];
     const float v = val[g0 + e];
     if (f >= 0 && f < F && v > 0.f) {
       const int ft = f / kWgFeat;
-      const int pos = atomicAdd(&s_cell[ft], 1);
-      ent_meta[pos] = static_cast<uint32_t>(e / k) | (static_cast<uint32_t>(f - ft * kWgFeat) << 8);
-      ent_a[pos] = dpre[g0 + e];
-      ent_b[pos] = v;
+      const int pos = atomicAdd(&s_cell[ft], 1) - static_cast<int>(g0);
+      s_meta[pos] = static_cast<uint32_t>(e / k) | (static_cast<uint32_t>(f - ft * kWgFeat) << 8);
+      s_a[pos] = dpre[g0 + e];
+      s_b[pos] = v;
     }
+  }
+  __syncthreads();
+  const int total = offsets[static_cast<size_t>(chunk) * (n_ft + 1) + n_ft] - static_cast<int>(g0);
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    ent_meta[g0 + e] = s_meta[e];
+    ent_a[g0 + e] = s_a[e];
+    ent_b[g0 + e] = s_b[e];
   }
 }
 
@@ -382,8 +395,13 @@ extern "C" int wsae_bucket_by_tile(const int32_t* idx, const float* val, const f
   if (!idx || !val || !dpre || !offsets || !ent_meta || !ent_a || !ent_b) return kBadArg;
   if (B <= 0 || F <= 0 || k <= 0) return kBadArg;
   const int n_chunks = ceil_div(B, kWgRows), n_ft = ceil_div(F, kWgFeat);
-  const size_t smem = static_cast<size_t>(n_ft) * sizeof(int);
-  if (smem > 48 * 1024) return kUnsupported;
+  const size_t smem = static_cast<size_t>(n_ft) * sizeof(int) + static_cast<size_t>(kWgRows) * k * 12;
+  if (smem > 200 * 1024) return kUnsupported;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(bucket_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   bucket_chunk_kernel<<<n_chunks, 256, smem, stream>>>(idx, val, dpre, B, F, k, n_ft, offsets,
                                                        ent_meta, ent_a, ent_b);
   return static_cast<int>(cudaGetLastError());
