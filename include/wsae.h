@@ -29,7 +29,7 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 104: + wsae_feature_topk_*, wsae_debug_wgrad_cluster). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 105: + wsae_feature_topk_*, wsae_debug_wgrad_cluster, wsae_layernorm_rows). */
 int wsae_abi_version(void);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
@@ -188,6 +188,17 @@ int wsae_feature_topk_update(const int32_t* feat, const float* val, const int32_
                              float* top_val, long long* top_sample, int32_t* top_pos,
                              int32_t* top_count, unsigned long long* total, void* ws,
                              unsigned long long ws_bytes, wsae_stream_t stream);
+
+/* ---- Activation extraction: final LayerNorm of hooked Whisper hidden states, flattened
+ *      (sae/hooks.py:85-86,103-104 `layer_norm(hidden_states)`, :213-230 flatten_activations) ----
+ * out[r, :] = (x[r, :] - mean_r) * rsqrt(var_r + eps) * gamma + beta  for r in [0, rows): biased
+ * variance, fp32 arithmetic (torch.nn.LayerNorm); x is [rows, d] with row pitch in_pitch_elems,
+ * in_dtype 0 = float32 / 1 = bfloat16 / 2 = float16; out is float32 with row pitch
+ * out_pitch_elems - pass `matrix + row0 * pitch` to append a batch to a [N, d] activation matrix
+ * (flatten + concatenate of hooks.py / feature_cache.py:283-300).  gamma / beta nullable.  d <= 4096. */
+int wsae_layernorm_rows(const void* x, int in_dtype, long long rows, int d, long long in_pitch_elems,
+                        const float* gamma /*nullable*/, const float* beta /*nullable*/, float eps,
+                        float* out, long long out_pitch_elems, wsae_stream_t stream);
 
 /* ---- experiments only (tools/bench_k1.py); not part of the product path -----------------------
  * variant: 1 = one epilogue warp per TMEM lane quarter, 2 = scanner + selector warps (default);

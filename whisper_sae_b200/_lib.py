@@ -107,6 +107,8 @@ _SIGNATURES = {
     "wsae_densify_hidden": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
     "wsae_cast_bf16": ([c_void_p, c_void_p, c_longlong, c_void_p], c_int),
     "wsae_sumsq": ([c_void_p, c_longlong, c_void_p, c_void_p], c_int),
+    "wsae_layernorm_rows": ([c_void_p, c_int, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_float,
+                             c_void_p, c_longlong, c_void_p], c_int),
     "wsae_feature_topk_workspace": ([c_longlong, c_int, POINTER(c_ulonglong)], c_int),
     "wsae_feature_topk_update": (
         [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_void_p, c_int, c_int,

@@ -420,3 +420,31 @@ def feature_topk_update(feat: Tensor, val: Tensor, rows: Tensor | None, k: int,
     _run("wsae_feature_topk_update", lib.wsae_feature_topk_update, _ptr(feat), _ptr(val), _ptr(rows), n,
          int(k), _ptr(sample_ids), int(sample_base), _ptr(pos_ids), F, K, _ptr(top_val), _ptr(top_sample),
          _ptr(top_pos), _ptr(top_count), _ptr(total), _ptr(ws), need.value, _stream(), launches=4)
+
+
+_LN_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def layernorm_rows_(x: Tensor, gamma: Tensor | None, beta: Tensor | None, eps: float, out: Tensor,
+                    row0: int = 0) -> None:
+    """out[row0 : row0 + n, :] = LayerNorm(x.reshape(n, d)) in fp32 (wsae_layernorm_rows;
+    sae/hooks.py:85-86,213-230: final LayerNorm of hooked hidden states + flatten, appended to the
+    activation matrix ``out``)."""
+    _need_cuda(x, gamma, beta, out)
+    if x.dtype not in _LN_DTYPES:
+        raise RuntimeError(f"unsupported activation dtype {x.dtype}")
+    d = x.shape[-1]
+    x2 = x.reshape(-1, d)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    n = x2.shape[0]
+    _f32c(gamma, "layer_norm.weight")
+    _f32c(beta, "layer_norm.bias")
+    if out.dtype != torch.float32 or out.dim() != 2 or out.shape[1] != d or out.stride(1) != 1:
+        raise RuntimeError("out must be a float32 [N, d] matrix with unit column stride")
+    if row0 < 0 or row0 + n > out.shape[0]:
+        raise RuntimeError(f"rows [{row0}, {row0 + n}) do not fit the [{out.shape[0]}, {d}] activation matrix")
+    lib = _lib.load()
+    dst = out.data_ptr() + row0 * out.stride(0) * 4
+    _run("wsae_layernorm_rows", lib.wsae_layernorm_rows, _ptr(x2), _LN_DTYPES[x.dtype], n, d, x2.stride(0),
+         _ptr(gamma), _ptr(beta), float(eps), dst, out.stride(0), _stream())
