@@ -1,5 +1,5 @@
 """Activation cache (drop-in for the hot-path part of ``whisper_sae.data``)."""
 
-from .feature_cache import CacheMetadata, FeatureCache, ResidentBatches
+from .feature_cache import CacheMetadata, FeatureCache, ResidentBatches, extract_and_cache_features
 
-__all__ = ["CacheMetadata", "FeatureCache", "ResidentBatches"]
+__all__ = ["CacheMetadata", "FeatureCache", "ResidentBatches", "extract_and_cache_features"]

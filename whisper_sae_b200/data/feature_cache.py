@@ -135,3 +135,50 @@ class FeatureCache:
             return ResidentBatches(features, batch_size, shuffle, device)
         return DataLoader(TensorDataset(features), batch_size=batch_size, shuffle=shuffle,
                           num_workers=num_workers, pin_memory=True)
+
+
+def extract_and_cache_features(whisper_model, processor, audio_dataloader, cache: FeatureCache,
+                               encoder_layers: list[int], decoder_layers: list[int],
+                               device: torch.device | str = "cuda",
+                               max_samples: int | None = None) -> None:
+    """Run Whisper over ``audio_dataloader`` and write one cache file per hooked layer
+    (feature_cache.py:200-306; same signature, ``processor`` is unused there too).
+
+    Hooked hidden states are normalised (the model's final LayerNorm) and flattened straight into a
+    growable device matrix per layer (``sae.hooks.ActivationMatrix``); nothing visits the host until
+    ``cache.save`` writes the ``[N, d]`` fp32 tensor in the reference's file format.
+    """
+    from ..sae.hooks import ActivationMatrix, _hidden_of, run_whisper
+
+    whisper_model = whisper_model.to(device)
+    whisper_model.eval()
+    d = whisper_model.config.d_model
+    enc = {layer: ActivationMatrix(d, device) for layer in encoder_layers}
+    dec = {layer: ActivationMatrix(d, device) for layer in decoder_layers}
+    enc_ln, dec_ln = whisper_model.model.encoder.layer_norm, whisper_model.model.decoder.layer_norm
+    handles = []
+    for layer, sink in enc.items():
+        handles.append(whisper_model.model.encoder.layers[layer].register_forward_hook(
+            lambda m, i, o, sink=sink: sink.append(_hidden_of(o).detach(), enc_ln)))
+    for layer, sink in dec.items():
+        handles.append(whisper_model.model.decoder.layers[layer].register_forward_hook(
+            lambda m, i, o, sink=sink: sink.append(_hidden_of(o).detach(), dec_ln)))
+    num_samples = 0
+    target = max_samples if max_samples is not None else float("inf")
+    try:
+        with torch.no_grad():
+            for batch in audio_dataloader:
+                if num_samples >= target:
+                    break
+                if isinstance(batch, (list, tuple)):
+                    batch = batch[0]
+                batch = batch.to(device)
+                run_whisper(whisper_model, batch, bool(decoder_layers))
+                num_samples += batch.shape[0]
+    finally:
+        for h in handles:
+            h.remove()
+    for component, sinks in (("encoder", enc), ("decoder", dec)):
+        for layer, sink in sinks.items():
+            if sink.rows:
+                cache.save(sink.tensor().cpu(), component, layer, num_samples)
