@@ -1061,7 +1061,7 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
   const int32_t* pi = part_idx + static_cast<size_t>(row) * n;
   const int per = ceil_div(n, 32);  // <= kMergeMaxPerLane (checked on the host)
   uint32_t key[PER];
-  uint32_t hi = 0;
+  uint32_t hi = 0, kmin = 0xFFFFFFFFu;
 #pragma unroll
   for (int t = 0; t < PER; ++t) {
     const int p = t * 32 + lane;
@@ -1069,26 +1069,32 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
     if (t < per && p < n && pi[p] >= 0) kk = f2key(pv[p]);
     key[t] = kk;
     hi = max(hi, kk);
+    kmin = min(kmin, kk ? kk : 0xFFFFFFFFu);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-  uint32_t lo = 1u;  // below every valid key (key(-inf) = 0x007fffff), above the empty marker 0
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  // bracket: count(key > lo) >= k, count(key > hi) < k.  lo starts just below the smallest valid key
+  // (the keys of one row cluster in a narrow band: starting at 1 wasted ~8 halvings) unless fewer
+  // than k candidates exist, in which case everything is kept.
+  uint32_t lo = (kmin != 0xFFFFFFFFu && kmin > 1u) ? kmin - 1u : 1u;
   bool exact = false;
   while (hi - lo > 1u) {
     const uint32_t mid = lo + ((hi - lo) >> 1);
-    int c = 0;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;       // four independent counters, one warp-wide REDUX
 #pragma unroll
-    for (int t = 0; t < PER; ++t) c += (key[t] > mid) ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (c >= k) {
-      lo = mid;
-      if (c == k) {
-        exact = true;
-        break;
-      }
-    } else {
-      hi = mid;
+    for (int t = 0; t < PER; t += 4) {
+      c0 += (key[t] > mid) ? 1 : 0;
+      if (t + 1 < PER) c1 += (key[t + 1] > mid) ? 1 : 0;
+      if (t + 2 < PER) c2 += (key[t + 2] > mid) ? 1 : 0;
+      if (t + 3 < PER) c3 += (key[t + 3] > mid) ? 1 : 0;
+    }
+    const int c = __reduce_add_sync(0xffffffffu, (c0 + c1) + (c2 + c3));
+    const bool ge = c >= k;
+    lo = ge ? mid : lo;
+    hi = ge ? hi : mid;
+    if (c == k) {
+      exact = true;
+      break;
     }
   }
   uint32_t thr = lo, tie_key = 0xFFFFFFFFu;
@@ -1097,8 +1103,7 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
     int m = 0;
 #pragma unroll
     for (int t = 0; t < PER; ++t) m += (key[t] > hi) ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    m = __reduce_add_sync(0xffffffffu, m);
     thr = hi;
     tie_key = hi;
     tie_left = k - m;
