@@ -108,7 +108,8 @@ class _GraphedStep:
         self._early = None
         self.grads = [self.g_b_pre, self.g_w_enc, self.g_b_enc, self.g_w_decT, self.g_b_dec]
         self.state = _SparseState()
-        self.graph: torch.cuda.CUDAGraph | None = None
+        self.graph: torch.cuda.CUDAGraph | list | None = None
+        self._mid: dict = {}
         self.kernels_per_replay = 0
         self.calls = 0
         for p in self.params:
@@ -136,6 +137,13 @@ class _GraphedStep:
 
     def _compute(self) -> None:
         """Forward + backward kernels of this rank's rows: fills g_flat, stats[0:2], fired stamps."""
+        self._compute_a()
+        if self._mid["use_gemm"] and self.trainer.data_parallel:   # exchange dW_enc while the dW_dec GEMM runs
+            self._early = self.trainer.dp_comm.all_reduce_sum_async(self.g_part_w_enc)
+        self._compute_b()
+
+    def _compute_a(self) -> None:
+        """Up to and including the dW_enc GEMM (everything the early all-reduce of dW_enc waits for)."""
         m = self.trainer.model
         x = self.x
         B, d = x.shape
@@ -173,17 +181,26 @@ class _GraphedStep:
                 ops.backward_sparse(resid, x, m.b_pre.data, w_used, idx, val, self.one, coef,
                                     d_w_enc=self.g_w_enc, d_w_decT=self.g_w_decT,
                                     d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre)
+        buckets = None
         if use_gemm:
             # weight gradients on the tensor cores (K4)
             buckets = ops.bucket_by_tile(idx, val, dpre, F)
             ops.wgrad_gemm_(self.g_w_enc, a_packed, B, d, buckets, buckets.dpre, None, 1.0)
-            if self.trainer.data_parallel:     # exchange dW_enc while the dW_dec GEMM runs
-                self._early = self.trainer.dp_comm.all_reduce_sum_async(self.g_part_w_enc)
-            ops.wgrad_gemm_(self.g_w_decT, resid_bf, B, d, buckets, buckets.act, self.one, coef)
-        ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
+        else:
+            resid_bf = None
+        self._mid = dict(use_gemm=use_gemm, buckets=buckets, resid_bf=resid_bf, B=B, d=d, coef=coef)
         s = self.state
         s.idx, s.val, s.resid, s.stats, s.w_dec_used, s.rows_total = idx, val, resid, self.stats, w_used, rows_total
         s.d_out = d
+
+    def _compute_b(self) -> None:
+        """The dW_dec GEMM and the b_pre gradient."""
+        m = self.trainer.model
+        mid = self._mid
+        if mid["use_gemm"]:
+            ops.wgrad_gemm_(self.g_w_decT, mid["resid_bf"], mid["B"], mid["d"], mid["buckets"],
+                            mid["buckets"].act, self.one, mid["coef"])
+        ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
 
     def _update(self) -> None:
         """Counters, clip + AdamW + decoder renorm on the (possibly all-reduced) gradient bucket."""
@@ -225,7 +242,35 @@ class _GraphedStep:
             self.graph = None
             self._ptrs = key
             self.calls = 1
-        if self.calls == 1 or tr.cuda_graph == "eager":
+        if self.calls > 1 and tr.cuda_graph == "segments":
+            # data parallel: the kernels between the collectives are three CUDA graphs (compute up to
+            # dW_enc | dW_dec + b_pre gradient | counters + optimizer), the NCCL calls stay eager
+            # between them (capturing them into one graph hung on the 2-GPU box in round 1)
+            if self.graph is None:
+                torch.cuda.synchronize()
+                pool = torch.cuda.graph_pool_handle()
+                before = ops.GPU_LAUNCHES
+                segs = []
+                for part in (self._compute_a, self._compute_b, self._update):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        part()
+                    segs.append(g)
+                self.kernels_per_replay = ops.GPU_LAUNCHES - before
+                ops.GPU_LAUNCHES = before
+                self.graph = segs
+            ga, gb, gc = self.graph
+            comm = tr.dp_comm
+            ga.replay()
+            early = comm.all_reduce_sum_async(self.g_part_w_enc) if self._mid["use_gemm"] else None
+            gb.replay()
+            parts = [self.g_part_head, self.g_part_tail] if early is not None else [self.g_flat]
+            comm.reduce_step(parts, self.stats, tr.model.feature_last_activated)
+            if early is not None:
+                early.wait()
+            gc.replay()
+            ops.GPU_LAUNCHES += self.kernels_per_replay
+        elif self.calls == 1 or tr.cuda_graph in ("eager", "segments"):
             self._body()
         else:
             if self.graph is None:
@@ -318,7 +363,10 @@ class SAETrainer:
             # 2-GPU box in round 1 and stays off by default.
             graph_ok = getattr(self.dp_comm, "graph_safe", False) and \
                 os.environ.get("WSAE_DP_GRAPH", "0") == "1" and self.cuda_graph is not False
-            self.cuda_graph = True if graph_ok else "eager"
+            # default for real process groups: graph the kernel segments, keep the collectives eager
+            seg_ok = getattr(self.dp_comm, "graph_safe", False) and self.cuda_graph is not False and \
+                os.environ.get("WSAE_DP_SEGMENTS", "1") != "0"
+            self.cuda_graph = True if graph_ok else ("segments" if seg_ok else "eager")
 
     # ------------------------------------------------------------------ resampling plumbing
     def set_resample_dataset(self, dataset: torch.utils.data.Dataset) -> None:
