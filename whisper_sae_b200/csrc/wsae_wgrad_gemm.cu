@@ -474,9 +474,23 @@ extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int
       break;
     }
   }
-  int ksplit = resident / (n_ft * n_nt);
-  if (ksplit < 1) ksplit = 1;
-  if (ksplit > n_chunks) ksplit = n_chunks;
+  // split-K factor: fill the resident CTA slots, over up to three waves when one wave would leave
+  // SMs idle (768 -> 6144: 96 (feature, n) tiles on 148 SMs = 65 % in one wave, 97 % as 3 x 96 CTAs)
+  const int base_items = n_ft * n_nt;
+  int ksplit = 1;
+  double best_eff = 0.0;
+  for (int waves = 1; waves <= 3; ++waves) {
+    int ks = (resident * waves) / base_items;
+    if (ks < 1) ks = 1;
+    if (ks > n_chunks) ks = n_chunks;
+    const int g = base_items * ks;
+    const int w = (g + resident - 1) / resident;
+    const double eff = static_cast<double>(g) / (static_cast<double>(w) * resident);
+    if (eff > best_eff + 0.02) {     // prefer fewer waves (less split-K reduction traffic) on near ties
+      best_eff = eff;
+      ksplit = ks;
+    }
+  }
   const int grid = n_ft * n_nt * ksplit;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
