@@ -485,7 +485,7 @@ def main() -> None:
         roof = roofline(prof, args.batch, D_MODEL, HIDDEN, TOPK, peaks, args.precision == "bf16")
         roof["peak_source"] = f"{peak_src} (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"
         roof["traffic"] = NCU_DRAM_TRAFFIC.get((args.workload, args.batch), {}).get(roof["kernel"])
-        roof["traffic_source"] = "profiles/r1_v7_top3_ncu_full.txt (dram bytes per launch)" \
+        roof["traffic_source"] = "profiles/r1_v9_top3_ncu_full.txt (dram bytes per launch)" \
             if roof["traffic"] is not None else None
         shares = {n: round(v["share_of_step"], 4) for n, v in prof.items() if not n.startswith("_")}
         # the launch-bound YAML batch, for the record
