@@ -843,51 +843,104 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int col0 = nt * kBN;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBN;
 
-        auto process = [&](uint32_t (&r)[16], int cbase) {
-#pragma unroll
-          for (int j = 0; j < kChunk; j += 4) {
-            const uint32_t c = static_cast<uint32_t>(cbase + j);
-            waddr = append4<kFifoIdxOff>(waddr, tau, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]), c,
-                                         c + 1, c + 2, c + 3, slot);
-            if ((j + 4) % kCheck == 0) {
-              if (__any_sync(0xffffffffu, waddr > wlimit)) {
-                st = scanner_handoff<DBG>(st, (waddr - wbase) / (kBM * 4), 0u, cnt_addr, meta + q,
-                                          ffull_bar + q, fempty_bar + q, lane, &d_wait_e);
-                ++d_hand;
-                wbase = fv0 + (st & 1u) * kFifoBytes;
-                waddr = wbase;
-                wlimit = wbase + (kFifo - kCheck) * (kBM * 4);
+        // ---- scan of one 128x256 accumulator tile, 32 columns (two tcgen05.ld.x16) per trip ----
+        // A taken branch costs a lone warp ~45-60 cycles (instruction-fetch bubble) and ptxas lays a
+        // rare `if (overflow) handoff();` block inline, i.e. the COMMON path takes a skip-branch at
+        // every overflow check - four per trip, a third of the scan time.  So the hot trip has no
+        // branch at all: an overflow check only folds its vote into `need`, and from then on the
+        // filter is closed (threshold +inf) for the rest of the trip.  The single branch per trip is
+        // the loop back-edge, which also tests `need`; when it falls through, the cold code below
+        // hands the FIFO over and re-scans the groups of that trip that ran with the filter closed.
+        auto scan8 = [&](const uint32_t (&r)[16], int j0, int cbase, float thr) {
+          const uint32_t c = static_cast<uint32_t>(cbase + j0);
+          waddr = append4<kFifoIdxOff>(waddr, thr, __uint_as_float(r[j0]), __uint_as_float(r[j0 + 1]),
+                                       __uint_as_float(r[j0 + 2]), __uint_as_float(r[j0 + 3]), c, c + 1,
+                                       c + 2, c + 3, slot);
+          waddr = append4<kFifoIdxOff>(waddr, thr, __uint_as_float(r[j0 + 4]), __uint_as_float(r[j0 + 5]),
+                                       __uint_as_float(r[j0 + 6]), __uint_as_float(r[j0 + 7]), c + 4,
+                                       c + 5, c + 6, c + 7, slot);
+        };
+        auto handoff = [&]() {
+          st = scanner_handoff<DBG>(st, (waddr - wbase) / (kBM * 4), 0u, cnt_addr, meta + q,
+                                    ffull_bar + q, fempty_bar + q, lane, &d_wait_e);
+          ++d_hand;
+          wbase = fv0 + (st & 1u) * kFifoBytes;
+          waddr = wbase;
+          wlimit = wbase + (kFifo - kCheck) * (kBM * 4);
+        };
+        const float pos_inf = __uint_as_float(0x7f800000u);
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr, ra);
+        int c2 = 0;
+        while (true) {
+          bool need = false;
+          int done = 0;            // groups of 8 columns of the current trip scanned with the filter open
+#pragma unroll 1
+          do {
+            const uint32_t ta = taddr + c2 * 32;
+            const int cb = col0 + c2 * 32;
+            uint32_t tb, tq;   // the selector's latest threshold for this row (valid for this item only)
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tb), "=r"(tq) : "r"(tau_addr) : "memory");
+            tmem_ld_wait16(ra);
+            tmem_ld16(ta + 16, rb);
+            if (tq == seq) tau = fmaxf(tau, __uint_as_float(tb));
+            float thr = tau;
+            done = 0;
+            if (DBG && mode == 4) {        // experiments: TMEM reads only (one compare keeps the loads live)
+              if (__uint_as_float(ra[0]) == tau) waddr += 4;
+              tmem_ld_wait16(rb);
+              if (c2 + 1 < kBN / 32) tmem_ld16(ta + 32, ra);
+              if (__uint_as_float(rb[0]) == tau) waddr += 4;
+            } else {
+              scan8(ra, 0, cb, thr);
+              done += need ? 0 : 1;
+              need = need | __any_sync(0xffffffffu, waddr > wlimit);
+              thr = need ? pos_inf : thr;
+              scan8(ra, 8, cb, thr);
+              done += need ? 0 : 1;
+              need = need | __any_sync(0xffffffffu, waddr > wlimit);
+              thr = need ? pos_inf : thr;
+              tmem_ld_wait16(rb);
+              if (c2 + 1 < kBN / 32) tmem_ld16(ta + 32, ra);
+              scan8(rb, 0, cb + 16, thr);
+              done += need ? 0 : 1;
+              need = need | __any_sync(0xffffffffu, waddr > wlimit);
+              thr = need ? pos_inf : thr;
+              scan8(rb, 8, cb + 16, thr);
+              done += need ? 0 : 1;
+              need = need | __any_sync(0xffffffffu, waddr > wlimit);
+            }
+            ++c2;
+          } while (!need && c2 < kBN / 32);
+          if (!need) break;                                  // tile scanned
+          // ---- cold path: hand the FIFO over, re-scan groups [done, 4) of trip c2 - 1 ----
+          // One hand-over call site, in a loop (a second call site after a re-scan made ptxas fail
+          // register allocation).  Every group re-reads its 16-column chunk into rb and ra (the
+          // prefetched first chunk of the next trip) is fetched again afterwards, so no tcgen05.ld
+          // result is live across the call.
+          {
+            const uint32_t ta = taddr + (c2 - 1) * 32;
+            const int cb = col0 + (c2 - 1) * 32;
+            int g = done;
+            bool over = true;
+            while (over) {
+              handoff();
+              over = false;
+#pragma unroll 1
+              while (g < 4 && !over) {
+                tmem_ld16(ta + (g >> 1) * 16, rb);
+                tmem_ld_wait16(rb);
+                if (g & 1) scan8(rb, 8, cb + (g >> 1) * 16, tau);
+                else scan8(rb, 0, cb + (g >> 1) * 16, tau);
+                over = __any_sync(0xffffffffu, waddr > wlimit);
+                ++g;
               }
             }
           }
-        };
-
-        // 32 accumulator columns per loop trip (two tcgen05.ld.x16, double-buffered): with the
-        // hand-over out of line the loop body stays within the ~6 KB L0 instruction cache
-        uint32_t ra[16], rb[16];
-        tmem_ld16(taddr, ra);
-#pragma unroll 1
-        for (int c2 = 0; c2 < kBN / 32; ++c2) {
-          const uint32_t ta = taddr + c2 * 32;
-          const int cb = col0 + c2 * 32;
-          uint32_t tb, tq;   // the selector's latest threshold for this row (valid for this item only)
-          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tb), "=r"(tq) : "r"(tau_addr) : "memory");
-          tmem_ld_wait16(ra);
-          tmem_ld16(ta + 16, rb);
-          if (tq == seq) tau = fmaxf(tau, __uint_as_float(tb));
-          if (DBG && mode == 4) {        // experiments: TMEM reads only (one compare keeps the loads live)
-            if (__uint_as_float(ra[0]) == tau) waddr += 4;
-          } else {
-            process(ra, cb);
-          }
-          tmem_ld_wait16(rb);
-          if (c2 + 1 < kBN / 32) tmem_ld16(ta + 32, ra);
-          if (DBG && mode == 4) {
-            if (__uint_as_float(rb[0]) == tau) waddr += 4;
-          } else {
-            process(rb, cb + 16);
-          }
+          if (c2 >= kBN / 32) break;
+          tmem_ld16(taddr + c2 * 32, ra);      // (again) the first chunk of the next trip
+          continue;
+          if (c2 >= kBN / 32) break;
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);
