@@ -310,7 +310,7 @@ def roofline(prof: dict, batch: int, d: int, F: int, k: int, peaks: dict, bf16_d
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` of the default
-# workload (tiny, B = 75776, bf16): profiles/r1_v5_top3_ncu_full.txt.  Other shapes: not captured.
+# workload (tiny, B = 75776, bf16): profiles/r1_v9_top3_ncu_full.txt.  Other shapes: not captured.
 NCU_DRAM_TRAFFIC = {("tiny", 75776): {"wsae_encode_topk": 77.59e6, "wsae_decode_backward": 185.92e6,
                                       "wsae_wgrad_gemm": 89.21e6}}
 
