@@ -29,7 +29,7 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 105: + wsae_feature_topk_*, wsae_debug_wgrad_cluster, wsae_layernorm_rows). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 106: + wsae_pack_activations_at, wsae_decode_backward_at). */
 int wsae_abi_version(void);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
@@ -40,6 +40,14 @@ int wsae_abi_version(void);
 int wsae_packed_k(int d, int terms, int* dp_out, int* used_cols_out, int* kp_out);
 int wsae_pack_activations(const float* x, const float* b_pre /*nullable*/, int B, int Bp, int d,
                           int terms, void* a_packed /*bf16 [Bp,Kp]*/, wsae_stream_t stream);
+/* As wsae_pack_activations, but the matrix is named by a device-resident pointer slot: the kernel
+ * reads *x_at when it RUNS, so a captured CUDA graph trains on whichever batch the slot names at
+ * replay time, in place (reference: training.py:170 hands `model(batch)` the batch itself, no
+ * staging copy).  *x_at: 16-byte aligned, B x d fp32.  terms == 1 and d % 8 == 0 only
+ * (WSAE_E_UNSUPPORTED otherwise). */
+int wsae_pack_activations_at(const float* const* x_at, const float* b_pre /*nullable*/, int B,
+                             int Bp, int d, int terms, void* a_packed /*bf16 [Bp,Kp]*/,
+                             wsae_stream_t stream);
 int wsae_pack_encoder(const float* w_enc /*[F,d]*/, const float* b_enc /*[F] nullable*/, int F,
                       int Fp, int d, int terms, void* w_packed /*bf16 [Fp,Kp]*/,
                       wsae_stream_t stream);
@@ -97,6 +105,15 @@ int wsae_decode_backward(const float* target, const void* w_decT, int w_is_bf16,
                          int d, int F, int k, float* resid, void* resid_bf16, void* stats,
                          long long* last_activated, const long long* step_count, float* d_b_enc,
                          float* d_b_dec, float* dpre_val, wsae_stream_t stream);
+/* As wsae_decode_backward, with the target matrix named by a device-resident pointer slot
+ * (*target_at: 16-byte aligned, B x d fp32, read when the kernel runs; see
+ * wsae_pack_activations_at). */
+int wsae_decode_backward_at(const float* const* target_at, const void* w_decT, int w_is_bf16,
+                            const float* b_dec, const float* b_pre /*nullable*/,
+                            const int32_t* idx, const float* val, const float* grad_out /*nullable*/,
+                            float coef, int B, int d, int F, int k, float* resid, void* resid_bf16,
+                            void* stats, long long* last_activated, const long long* step_count,
+                            float* d_b_enc, float* d_b_dec, float* dpre_val, wsae_stream_t stream);
 /* out[idx[b,j], :] += vals[b,j] * (rows[b,:] - center): the encoder weight gradient as a sparse
  * scatter when the input width differs from the decoder width (transcoders); dr % 4 == 0. */
 int wsae_scatter_rows(const float* rows, const float* center /*nullable*/, const int32_t* idx,

@@ -219,6 +219,87 @@ def test_trainer_bf16_within_tolerance(tmp_path):
         assert t.double().abs().sum().item() == pytest.approx(ref["abs_sum"], rel=2e-2)
 
 
+def test_graphed_step_trains_on_device_batches_in_place(tmp_path):
+    """bf16 graph step: device-resident batches are read where they lie (x_slot indirection in K0 /
+    K23, no staging copy); host batches and misaligned / strided device batches go through the
+    staging buffer.  All three feeds must walk the same trajectory."""
+    _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
+    B, d, F, k, steps = 256, 384, 3072, 32, 6
+    x_all = O.synthetic_activations(B * steps, d, 77)
+
+    def run(feed):
+        torch.manual_seed(3)
+        sae = TopKSAE(d, F, k=k)
+        cfg = TrainingConfig(batch_size=B, learning_rate=1e-3, warmup_steps=2, epochs=1, use_amp=True,
+                             num_workers=0)
+        tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path)
+        tr.setup_scheduler(steps)
+        losses = []
+        keep = []
+        for s in range(steps):
+            xb = x_all[s * B:(s + 1) * B]
+            if feed == "device":           # a fresh allocation per step: distinct addresses
+                xb = xb.cuda().clone()
+                keep.append(xb)
+            elif feed == "strided":        # non-contiguous view: must be staged
+                wide = torch.zeros(B, d + 8, device="cuda")
+                wide[:, :d] = xb.cuda()
+                xb = wide[:, :d]
+            elif feed == "misaligned":     # contiguous but only 4-byte aligned: must be staged
+                flat = torch.zeros(B * d + 1, device="cuda")
+                flat[1:] = xb.cuda().reshape(-1)
+                xb = flat[1:].view(B, d)
+                assert xb.data_ptr() % 16 != 0 and xb.is_contiguous()
+            losses.append(tr.train_step(xb).loss)
+        gs = tr._graphs[B]
+        return losses, {n: t.detach().cpu() for n, t in sae.state_dict().items()}, gs
+
+    l_host, p_host, gs_host = run("host")
+    l_dev, p_dev, gs_dev = run("device")
+    assert gs_dev.in_place and gs_dev._x is None, "device batches must not allocate / use the staging buffer"
+    assert gs_host._x is not None
+    assert len({t for t in map(float, l_dev)}) > 1
+    for a, b in zip(l_host, l_dev):
+        assert a == pytest.approx(b, rel=1e-5)
+    for feed in ("strided", "misaligned"):
+        l_o, p_o, gs_o = run(feed)
+        assert gs_o._x is not None
+        for a, b in zip(l_host, l_o):
+            assert a == pytest.approx(b, rel=1e-5)
+    for n in p_host:
+        torch.testing.assert_close(p_dev[n], p_host[n], rtol=1e-4, atol=1e-6)
+
+
+def test_slot_entry_points_match_direct_ones():
+    """wsae_pack_activations_at / wsae_decode_backward_at == the direct-pointer entry points, bit for bit."""
+    from whisper_sae_b200 import ops
+    B, d, F, k = 300, 384, 1024, 32
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, d, generator=g).cuda()
+    b_pre = (0.1 * torch.randn(d, generator=g)).cuda()
+    slot = torch.tensor([x.data_ptr()], dtype=torch.int64, device="cuda")
+    torch.testing.assert_close(ops.pack_activations_at(slot, B, d, b_pre), ops.pack_activations(x, b_pre, 1),
+                               rtol=0, atol=0)
+    w = torch.randn(F, d, generator=g).cuda().to(torch.bfloat16)
+    b_dec = (0.1 * torch.randn(d, generator=g)).cuda()
+    idx = torch.stack([torch.randperm(F, generator=g)[:k] for _ in range(B)]).to(torch.int32).cuda()
+    val = torch.randn(B, k, generator=g).cuda()
+    outs = []
+    for use_slot in (False, True):
+        resid = torch.empty(B, d, device="cuda")
+        stats = torch.zeros(3, dtype=torch.int64, device="cuda")
+        dpre = torch.empty(B, k, device="cuda")
+        ops.decode_backward(slot if use_slot else x, w, b_dec, b_pre, idx, val, None, 1e-3, resid=resid,
+                            resid_bf16=None, stats=stats, last_activated=None, step_count=None,
+                            d_b_enc=None, d_b_dec=None, dpre_val=dpre, target_is_slot=use_slot)
+        outs.append((resid, dpre, stats[1].item()))
+    torch.testing.assert_close(outs[1][0], outs[0][0], rtol=0, atol=0)
+    torch.testing.assert_close(outs[1][1], outs[0][1], rtol=0, atol=0)
+    assert outs[0][2] == outs[1][2]
+    with pytest.raises(RuntimeError):
+        ops.pack_activations_at(slot.to(torch.int32), B, d, b_pre)
+
+
 def test_trainer_bookkeeping_and_checkpoint(tmp_path):
     _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
     cfg = TrainingConfig(batch_size=16, epochs=2, use_amp=False, num_workers=0, checkpoint_every=1)

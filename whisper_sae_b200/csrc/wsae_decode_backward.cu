@@ -76,8 +76,11 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
                        float* __restrict__ resid, __nv_bfloat16* __restrict__ resid_bf16,
                        FusedStats* __restrict__ stats, long long* __restrict__ last_activated,
                        const long long* __restrict__ step_count, float* __restrict__ d_b_enc,
-                       float* __restrict__ d_b_dec, float* __restrict__ dpre_val) {
+                       float* __restrict__ d_b_dec, float* __restrict__ dpre_val,
+                       const float* const* __restrict__ target_at) {
   extern __shared__ __align__(16) float fsm[];   // [dp] bias (b_dec + b_pre), then one [dp] db_dec accumulator per warp
+  pdl_prologue();
+  if (target_at != nullptr) target = *target_at;   // address from a device-resident slot (graph replay)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int dp = round_up(d, 128);
@@ -227,14 +230,15 @@ using namespace wsae;
 
 // See include/wsae.h.  Returns WSAE_E_UNSUPPORTED for shapes the fused kernel does not cover
 // (fp32 decoder, k > 32, d % 8 != 0): callers then use K2 + K3.
-extern "C" int wsae_decode_backward(const float* target, const void* w_decT, int w_is_bf16,
-                                    const float* b_dec, const float* b_pre, const int32_t* idx,
-                                    const float* val, const float* grad_out, float coef, int B,
-                                    int d, int F, int k, float* resid, void* resid_bf16,
-                                    void* stats, long long* last_activated,
-                                    const long long* step_count, float* d_b_enc, float* d_b_dec,
-                                    float* dpre_val, cudaStream_t stream) {
-  if (!target || !w_decT || !b_dec || !idx || !val) return kBadArg;
+static int decode_backward_impl(const float* target, const float* const* target_at,
+                                const void* w_decT, int w_is_bf16, const float* b_dec,
+                                const float* b_pre, const int32_t* idx, const float* val,
+                                const float* grad_out, float coef, int B, int d, int F, int k,
+                                float* resid, void* resid_bf16, void* stats,
+                                long long* last_activated, const long long* step_count,
+                                float* d_b_enc, float* d_b_dec, float* dpre_val,
+                                cudaStream_t stream) {
+  if ((!target && !target_at) || !w_decT || !b_dec || !idx || !val) return kBadArg;
   if (B <= 0 || d <= 0 || F <= 0 || k <= 0) return kBadArg;
   if (!w_is_bf16 || k > 32 || d % 8 != 0 || d > 8192) return kUnsupported;
   if (static_cast<long long>(F) * (d / 4) > 0x7fffffffLL) return kUnsupported;
@@ -244,9 +248,37 @@ extern "C" int wsae_decode_backward(const float* target, const void* w_decT, int
   int blocks = ceil_div(B, kFusedWarps);
   if (blocks > sms * 4) blocks = sms * 4;
   const size_t smem = (1 + kFusedWarps) * static_cast<size_t>(round_up(d, 128)) * sizeof(float);
-  decode_backward_kernel<<<blocks, kFusedWarps * 32, smem, stream>>>(
-      target, static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B,
-      d, F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
-      last_activated, step_count, d_b_enc, d_b_dec, dpre_val);
+  launch_pdl(decode_backward_kernel, blocks, kFusedWarps * 32, smem, stream, target,
+             static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
+             F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
+             last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at);
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int wsae_decode_backward(const float* target, const void* w_decT, int w_is_bf16,
+                                    const float* b_dec, const float* b_pre, const int32_t* idx,
+                                    const float* val, const float* grad_out, float coef, int B,
+                                    int d, int F, int k, float* resid, void* resid_bf16,
+                                    void* stats, long long* last_activated,
+                                    const long long* step_count, float* d_b_enc, float* d_b_dec,
+                                    float* dpre_val, cudaStream_t stream) {
+  if (!target) return kBadArg;
+  return decode_backward_impl(target, nullptr, w_decT, w_is_bf16, b_dec, b_pre, idx, val, grad_out,
+                              coef, B, d, F, k, resid, resid_bf16, stats, last_activated, step_count,
+                              d_b_enc, d_b_dec, dpre_val, stream);
+}
+
+// Same, with the target matrix named by a device-resident pointer slot (*target_at: 16-byte aligned,
+// B x d fp32, read when the kernel runs) - lets a captured graph train on batches in place.
+extern "C" int wsae_decode_backward_at(const float* const* target_at, const void* w_decT,
+                                       int w_is_bf16, const float* b_dec, const float* b_pre,
+                                       const int32_t* idx, const float* val, const float* grad_out,
+                                       float coef, int B, int d, int F, int k, float* resid,
+                                       void* resid_bf16, void* stats, long long* last_activated,
+                                       const long long* step_count, float* d_b_enc, float* d_b_dec,
+                                       float* dpre_val, cudaStream_t stream) {
+  if (!target_at) return kBadArg;
+  return decode_backward_impl(nullptr, target_at, w_decT, w_is_bf16, b_dec, b_pre, idx, val,
+                              grad_out, coef, B, d, F, k, resid, resid_bf16, stats, last_activated,
+                              step_count, d_b_enc, d_b_dec, dpre_val, stream);
 }

@@ -37,6 +37,7 @@ renorm_rows_kernel(float* __restrict__ w, int F, int d, float eps,
 __global__ void __launch_bounds__(1024)
 counters_update_kernel(const long long* __restrict__ last_activated, long long* step_count, int F,
                        long long threshold, int bump, long long* __restrict__ dead_count) {
+  pdl_prologue();
   __shared__ long long s_step;
   __shared__ int s_part[32];
   if (threadIdx.x == 0) {
@@ -76,6 +77,7 @@ densify_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, i
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  pdl_prologue();
   const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(src + i);
@@ -93,6 +95,7 @@ cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
 // out[0] += sum(g^2)  (double accumulator; caller zeroes it).  Grid-stride, float4.
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ out) {
+  pdl_prologue();
   float acc = 0.f;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -183,6 +186,7 @@ __device__ __forceinline__ void adamw_elem(float& pv, float g, float& mv, float&
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const AdamwBatch batch, const float* __restrict__ hyper,
                    const double* __restrict__ grad_sumsq, float renorm_eps) {
+  pdl_prologue();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
   const float bc1 = hyper[5], bc2s = hyper[6], max_norm = hyper[7];
   float clip = 1.f;
@@ -279,7 +283,7 @@ extern "C" int wsae_adamw_multi(const wsae_adamw_tensor_host* tensors, int count
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long cap = static_cast<long long>(sms) * 16;
   const unsigned blocks = static_cast<unsigned>(units < cap ? units : cap);
-  adamw_multi_kernel<<<blocks, 256, 0, stream>>>(b, hyper, grad_sumsq, renorm_eps);
+  launch_pdl(adamw_multi_kernel, blocks, 256, 0, stream, b, hyper, grad_sumsq, renorm_eps);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -296,8 +300,8 @@ extern "C" int wsae_counters_update(const long long* last_activated, long long* 
                                     long long threshold, int bump, long long* dead_count,
                                     cudaStream_t stream) {
   if (!last_activated || !step_count || F <= 0) return kBadArg;
-  counters_update_kernel<<<1, 1024, 0, stream>>>(last_activated, step_count, F, threshold, bump,
-                                                 dead_count);
+  launch_pdl(counters_update_kernel, 1, 1024, 0, stream, last_activated, step_count, F, threshold,
+             bump, dead_count);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -312,8 +316,8 @@ extern "C" int wsae_cast_bf16(const float* src, void* dst, long long n, cudaStre
   if (!src || !dst || n <= 0) return kBadArg;
   const size_t groups = (static_cast<size_t>(n) + 3) / 4;
   const unsigned blocks = static_cast<unsigned>((groups + 255) / 256);
-  cast_bf16_kernel<<<blocks, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst),
-                                               static_cast<size_t>(n));
+  launch_pdl(cast_bf16_kernel, blocks, 256, 0, stream, src, static_cast<__nv_bfloat16*>(dst),
+             static_cast<size_t>(n));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -326,7 +330,7 @@ extern "C" int wsae_sumsq(const float* g, long long n, double* out, cudaStream_t
   if (want < 1) want = 1;
   const size_t cap = static_cast<size_t>(sms) * 8;
   const unsigned blocks = static_cast<unsigned>(want < cap ? want : cap);
-  sumsq_kernel<<<blocks, 256, 0, stream>>>(g, static_cast<size_t>(n), out);
+  launch_pdl(sumsq_kernel, blocks, 256, 0, stream, g, static_cast<size_t>(n), out);
   return static_cast<int>(cudaGetLastError());
 }
 

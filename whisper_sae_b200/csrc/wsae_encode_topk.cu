@@ -770,6 +770,7 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const EncodeItems items{total_items, nsplit, tiles_per_split, num_n_tiles, num_kb, ksteps};
   const float neg_inf = __uint_as_float(0xff800000u);
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
@@ -798,6 +799,7 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // set-up done under the predecessor's tail; global memory (TMA, results) from here on
 
   if (warp < 4) {
     reg_alloc_dec<56>();
@@ -1137,6 +1139,7 @@ template <int PER>
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict__ part_idx, int B,
                   int n, int k, float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -1294,13 +1297,13 @@ static int launch_encode2(const CUtensorMap& ta, const CUtensorMap& tw, int B, i
   const int total = num_m_blocks * nsplit;
   const int grid = total < num_sms ? total : num_sms;
   if (g_encode_dbg_buf != nullptr)
-    encode_topk2_kernel<STAGES, true><<<grid, 384, smem, stream>>>(
-        ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx,
-        g_encode_dbg_buf, g_encode_dbg, static_cast<uint32_t>(kBM * 4));
+    launch_pdl(encode_topk2_kernel<STAGES, true>, grid, 384, smem, stream, ta, tw, B, F, k, ksteps,
+               num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx, g_encode_dbg_buf,
+               g_encode_dbg, static_cast<uint32_t>(kBM * 4));
   else
-    encode_topk2_kernel<STAGES, false><<<grid, 384, smem, stream>>>(
-        ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx,
-        nullptr, 0, static_cast<uint32_t>(kBM * 4));
+    launch_pdl(encode_topk2_kernel<STAGES, false>, grid, 384, smem, stream, ta, tw, B, F, k, ksteps,
+               num_m_blocks, num_n_tiles, nsplit, tiles_per_split, out_val, out_idx, nullptr, 0,
+               static_cast<uint32_t>(kBM * 4));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1365,7 +1368,8 @@ extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int 
     const int per = ceil_div(nsplit * k, 32);
     const dim3 grid(ceil_div(B, warps)), block(warps * 32);
 #define WSAE_MERGE_CASE(P)                                                                   \
-  topk_merge_kernel<P><<<grid, block, 0, stream>>>(part_val, part_idx, B, nsplit * k, k, out_val, out_idx)
+  launch_pdl(topk_merge_kernel<P>, grid, block, 0, stream, part_val, part_idx, B, nsplit * k, k, out_val, \
+             out_idx)
     if (per <= 2) WSAE_MERGE_CASE(2);
     else if (per <= 4) WSAE_MERGE_CASE(4);
     else if (per <= 8) WSAE_MERGE_CASE(8);

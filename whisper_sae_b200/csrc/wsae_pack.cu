@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ src, const float* __restrict__ center,
                  const float* __restrict__ bias, int rows, int rows_p, int d, int dp, int T,
                  int Kp, PieceSchedule sched, __nv_bfloat16* __restrict__ dst) {
+  pdl_prologue();
   const int groups = Kp >> 3;
   const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= static_cast<size_t>(rows_p) * groups) return;
@@ -87,8 +88,13 @@ pack_rows_kernel(const float* __restrict__ src, const float* __restrict__ center
 // two 16-byte loads and one 16-byte store; the bias block and the K padding are written by the same
 // grid.  HBM bound: reads B*d*4, writes Bp*Kp*2 bytes.
 __global__ void __launch_bounds__(256)
-pack_activations_bf16_kernel(const float* __restrict__ x, const float* __restrict__ center, int rows,
-                             int rows_p, int d, int Kp, __nv_bfloat16* __restrict__ dst) {
+pack_activations_bf16_kernel(const float* __restrict__ x, const float* const* __restrict__ x_at,
+                             const float* __restrict__ center, int rows, int rows_p, int d, int Kp,
+                             __nv_bfloat16* __restrict__ dst) {
+  pdl_prologue();
+  // x_at: the matrix's address is read from device memory (a captured graph replays on whichever
+  // batch the slot names - no staging copy of the batch into a graph-owned buffer)
+  if (x_at != nullptr) x = *x_at;
   const int groups = Kp >> 3;
   const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= static_cast<size_t>(rows_p) * groups) return;
@@ -147,8 +153,9 @@ extern "C" int wsae_packed_k(int d, int terms, int* dp_out, int* used_cols_out, 
 }
 
 static int pack_common(int kind, const float* src, const float* center, const float* bias,
-                       int rows, int rows_p, int d, int terms, void* dst, cudaStream_t stream) {
-  if (!src || !dst || rows <= 0 || rows_p < rows) return kBadArg;
+                       int rows, int rows_p, int d, int terms, void* dst, cudaStream_t stream,
+                       const float* const* src_at = nullptr) {
+  if ((!src && !src_at) || !dst || rows <= 0 || rows_p < rows) return kBadArg;
   int dp, used, Kp;
   if (wsae_packed_k(d, terms, &dp, &used, &Kp)) return kBadArg;
   PieceSchedule s;
@@ -156,25 +163,33 @@ static int pack_common(int kind, const float* src, const float* center, const fl
   const size_t total = static_cast<size_t>(rows_p) * (Kp >> 3);
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
-  if (kind == 0 && terms == 1 && d % 8 == 0 &&
-      (reinterpret_cast<uintptr_t>(src) & 15u) == 0 &&
-      (center == nullptr || (reinterpret_cast<uintptr_t>(center) & 15u) == 0))
-    pack_activations_bf16_kernel<<<blocks, threads, 0, stream>>>(
-        src, center, rows, rows_p, d, Kp, static_cast<__nv_bfloat16*>(dst));
+  const bool fast = kind == 0 && terms == 1 && d % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(src) & 15u) == 0 &&
+                    (center == nullptr || (reinterpret_cast<uintptr_t>(center) & 15u) == 0);
+  if (src_at != nullptr && !fast) return kUnsupported;   // the slot form exists for the bf16 path only
+  if (fast)
+    launch_pdl(pack_activations_bf16_kernel, blocks, threads, 0, stream, src, src_at, center, rows,
+               rows_p, d, Kp, static_cast<__nv_bfloat16*>(dst));
   else if (kind == 0)
-    pack_rows_kernel<0><<<blocks, threads, 0, stream>>>(src, center, bias, rows, rows_p, d, dp,
-                                                        terms, Kp, s,
-                                                        static_cast<__nv_bfloat16*>(dst));
+    launch_pdl(pack_rows_kernel<0>, blocks, threads, 0, stream, src, center, bias, rows, rows_p, d,
+               dp, terms, Kp, s, static_cast<__nv_bfloat16*>(dst));
   else
-    pack_rows_kernel<1><<<blocks, threads, 0, stream>>>(src, center, bias, rows, rows_p, d, dp,
-                                                        terms, Kp, s,
-                                                        static_cast<__nv_bfloat16*>(dst));
+    launch_pdl(pack_rows_kernel<1>, blocks, threads, 0, stream, src, center, bias, rows, rows_p, d,
+               dp, terms, Kp, s, static_cast<__nv_bfloat16*>(dst));
   return static_cast<int>(cudaGetLastError());
 }
 
 extern "C" int wsae_pack_activations(const float* x, const float* b_pre, int B, int Bp, int d,
                                      int terms, void* a_packed, cudaStream_t stream) {
   return pack_common(0, x, b_pre, nullptr, B, Bp, d, terms, a_packed, stream);
+}
+
+// Same, with the activation matrix named by a device-resident pointer slot (*x_at must be 16-byte
+// aligned and hold B x d fp32 when the kernel runs).  bf16 single-term packing with d % 8 == 0 only.
+extern "C" int wsae_pack_activations_at(const float* const* x_at, const float* b_pre, int B, int Bp,
+                                        int d, int terms, void* a_packed, cudaStream_t stream) {
+  if (!x_at) return kBadArg;
+  return pack_common(0, nullptr, b_pre, nullptr, B, Bp, d, terms, a_packed, stream, x_at);
 }
 
 extern "C" int wsae_pack_encoder(const float* w_enc, const float* b_enc, int F, int Fp, int d,

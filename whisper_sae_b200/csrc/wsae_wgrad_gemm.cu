@@ -46,6 +46,7 @@ bucket_chunk_kernel(const int32_t* __restrict__ idx, const float* __restrict__ v
                     int* __restrict__ offsets, uint32_t* __restrict__ ent_meta,
                     float* __restrict__ ent_a, float* __restrict__ ent_b) {
   extern __shared__ int s_cell[];  // [n_ft] counts -> cursors
+  pdl_prologue();
   const int chunk = blockIdx.x;
   for (int i = threadIdx.x; i < n_ft; i += blockDim.x) s_cell[i] = 0;
   __syncthreads();
@@ -171,6 +172,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
   const int n_cols = nb_here * 64;
   const uint32_t tmem_cols = n_cols > 256 ? 512u : (n_cols > 128 ? 256u : (n_cols > 64 ? 128u : 64u));
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_r);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -190,6 +192,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
   if (csize > 1) cluster_sync_all();   // peers' barriers are initialised before anything is multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // barriers, TMEM and the descriptor are set up; global memory only from here on
 
   if (warp == 0) {
     // ===================== TMA producer: R tiles =====================
@@ -402,8 +405,8 @@ extern "C" int wsae_bucket_by_tile(const int32_t* idx, const float* val, const f
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  bucket_chunk_kernel<<<n_chunks, 256, smem, stream>>>(idx, val, dpre, B, F, k, n_ft, offsets,
-                                                       ent_meta, ent_a, ent_b);
+  launch_pdl(bucket_chunk_kernel, n_chunks, 256, smem, stream, idx, val, dpre, B, F, k, n_ft, offsets,
+             ent_meta, ent_a, ent_b);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -497,13 +500,15 @@ extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   e = cudaLaunchKernelEx(&cfg, kern, tm, F, d, n_chunks, n_ft, n_nt, nb_tile, ksplit, offsets, ent_meta,
                          ent_val, grad_out, alpha, out);
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -80,11 +80,22 @@ class _GraphedStep:
         self.trainer = trainer
         self.rows = rows
         self.bf16 = bool(trainer.use_amp)
-        self.x = torch.empty((rows, m.input_dim), dtype=torch.float32, device=dev)
-        self.stats = torch.zeros(3, dtype=torch.int64, device=dev)
-        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
-        self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
-        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        # per-step control block, ONE 48-byte H2D copy from pinned memory before every replay:
+        # [hyper f32[8] | x_slot i64 | pad].  x_slot holds the device address of the step's batch:
+        # the kernels that read the activations (K0 pack, K23 target) take it from there when they
+        # RUN, so the captured graph trains on a device-resident batch in place; only batches that
+        # arrive on the host (or misaligned / non-contiguous) are staged into `x`.
+        self.ctl = torch.zeros(48, dtype=torch.uint8, device=dev)
+        self.ctl_host = torch.zeros(48, dtype=torch.uint8).pin_memory()
+        self.hyper = self.ctl[:32].view(torch.float32)
+        self.hyper_host = self.ctl_host[:32].view(torch.float32)
+        self.x_slot = self.ctl[32:40].view(torch.int64)
+        self.x_slot_host = self.ctl_host[32:40].view(torch.int64)
+        d_in, k_sel = m.input_dim, m.k
+        self.in_place = (self.bf16 and d_in % 8 == 0 and ops.wgrad_gemm_supported(d_in)
+                         and ops.decode_backward_supported(d_in, k_sel, True))
+        self._x: Tensor | None = None     # staging buffer, allocated on first use
+        self._live: Tensor | None = None  # the batch the slot names (kept alive until the next step)
         self.one = torch.ones((), dtype=torch.float32, device=dev)
         self.params = [m.b_pre, m.encoder.weight, m.encoder.bias, m.decoder.weight, m.decoder.bias]
         m._w_decT()
@@ -96,7 +107,13 @@ class _GraphedStep:
         for n in sizes:
             starts.append(off)
             off += (n + 15) // 16 * 16
-        self.g_flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        # the step's accumulators share one allocation so ONE memset per step clears them all:
+        # [gradient bucket | stats int64[3] | grad sum-of-squares f64] (tail 64-byte aligned)
+        self.zeroed = torch.zeros(off + 16, dtype=torch.float32, device=dev)
+        self.g_flat = self.zeroed[:off]
+        tail = self.zeroed[off:off + 8].view(torch.int64)
+        self.stats = tail[0:3]
+        self.sumsq = tail[3:4].view(torch.float64)
         seg = [self.g_flat[s0:s0 + n] for s0, n in zip(starts, sizes)]
         self.g_b_pre, self.g_b_enc, self.g_b_dec = seg[0], seg[2], seg[4]
         self.g_w_enc, self.g_w_decT = seg[1].view(F, d), seg[3].view(F, d)
@@ -115,6 +132,13 @@ class _GraphedStep:
         for p in self.params:
             _ensure_adamw_state(trainer.optimizer, p)
         self._ptrs: tuple[int, ...] = ()
+
+    @property
+    def x(self) -> Tensor:
+        if self._x is None:
+            m = self.trainer.model
+            self._x = torch.empty((self.rows, m.input_dim), dtype=torch.float32, device=m.b_pre.device)
+        return self._x
 
     def _pointer_key(self) -> tuple[int, ...]:
         m = self.trainer.model
@@ -145,35 +169,40 @@ class _GraphedStep:
     def _compute_a(self) -> None:
         """Up to and including the dW_enc GEMM (everything the early all-reduce of dW_enc waits for)."""
         m = self.trainer.model
-        x = self.x
-        B, d = x.shape
+        B, d = self.rows, m.input_dim
+        x = None if self.in_place else self.x      # in place: the kernels read the batch through x_slot
+        dev = m.b_pre.device
         F, k = m.hidden_dim, m.k
         terms = 1 if self.bf16 else _fp32_terms()
         w_decT = m.decoder.weight.data.t()
-        self.stats.zero_()
-        a_packed = ops.pack_activations(x, m.b_pre.data, terms)
+        self.zeroed.zero_()
+        if self.in_place:
+            a_packed = ops.pack_activations_at(self.x_slot, B, d, m.b_pre.data)
+        else:
+            a_packed = ops.pack_activations(x, m.b_pre.data, terms)
         w_packed = ops.pack_encoder(m.encoder.weight.data, m.encoder.bias.data, terms)
         idx, val = ops.encode_topk(a_packed, w_packed, B, F, d, terms, k)
         w_used = ops.cast_bf16(w_decT) if self.bf16 else w_decT
         rows_total = m._global_rows or B
         coef = 2.0 / (float(rows_total) * d)
-        self.g_flat.zero_()
-        dpre = torch.empty((B, k), dtype=torch.float32, device=x.device)
+        dpre = torch.empty((B, k), dtype=torch.float32, device=dev)
         use_gemm = self.bf16 and ops.wgrad_gemm_supported(d)
         if use_gemm and ops.decode_backward_supported(d, k, True):
             # K23: decode + MSE + stamps + dv + bias gradients in one pass over the gathered rows
             resid = None          # fp32 residual only on demand (SAEOutput.reconstructed, resampling)
-            resid_bf = torch.empty((B, d), dtype=torch.bfloat16, device=x.device)
-            ops.decode_backward(x, w_used, m.decoder.bias.data, m.b_pre.data, idx, val, self.one, coef,
+            resid_bf = torch.empty((B, d), dtype=torch.bfloat16, device=dev)
+            ops.decode_backward(self.x_slot if self.in_place else x, w_used, m.decoder.bias.data,
+                                m.b_pre.data, idx, val, self.one, coef,
                                 resid=None, resid_bf16=resid_bf, stats=self.stats,
                                 last_activated=m.feature_last_activated, step_count=m.step_count,
-                                d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre)
+                                d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre,
+                                target_is_slot=self.in_place)
         else:
             resid, _ = ops.decode_mse(x, w_used, m.decoder.bias.data, m.b_pre.data, idx, val,
                                       stats=self.stats, last_activated=m.feature_last_activated,
                                       step_count=m.step_count)
             if use_gemm:
-                resid_bf = torch.empty((B, d), dtype=torch.bfloat16, device=x.device)
+                resid_bf = torch.empty((B, d), dtype=torch.bfloat16, device=dev)
                 ops.backward_sparse(resid, None, None, w_used, idx, val, self.one, coef, d_w_enc=None,
                                     d_w_decT=None, d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec,
                                     dpre_val=dpre, resid_bf16=resid_bf)
@@ -208,7 +237,6 @@ class _GraphedStep:
         d = m.input_dim
         ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold, True,
                             self.stats[2:])
-        self.sumsq.zero_()
         ops.sumsq_(self.g_flat, self.sumsq)
         opt_state = self.trainer.optimizer.state
         entries = []
@@ -223,7 +251,15 @@ class _GraphedStep:
         pointer check) is issued before the replay; the optimizer's ``step`` tensors and the grad
         views are updated while the kernels run (matters at the launch-bound YAML batch sizes)."""
         tr = self.trainer
-        self.x.copy_(batch, non_blocking=True)
+        if (self.in_place and batch.is_cuda and batch.device == self.ctl.device
+                and batch.dtype == torch.float32 and batch.is_contiguous()
+                and batch.data_ptr() % 16 == 0):
+            src = batch                      # trained on where it lies
+        else:
+            self.x.copy_(batch, non_blocking=True)
+            src = self.x
+        self._live = src                     # the caller may drop its reference before the replay runs
+        self.x_slot_host[0] = src.data_ptr()
         group = tr.optimizer.param_groups[0]
         for p in self.params:
             _ensure_adamw_state(tr.optimizer, p)
@@ -234,7 +270,7 @@ class _GraphedStep:
         h[5] = 1.0 - beta1 ** step_t
         h[6] = math.sqrt(1.0 - beta2 ** step_t)
         h[7] = tr.config.gradient_clip
-        self.hyper.copy_(h, non_blocking=True)
+        self.ctl.copy_(self.ctl_host, non_blocking=True)
         self.calls += 1
         tr.model._w_decT()
         key = self._pointer_key()
