@@ -29,7 +29,7 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 106: + wsae_pack_activations_at, wsae_decode_backward_at). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 107: + wsae_pack_activations_at, wsae_decode_backward_at, wsae_counters_update_post). */
 int wsae_abi_version(void);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
@@ -158,6 +158,16 @@ int wsae_renorm_decoder(float* w_decT, int F, int d, float eps, void* bf16_shado
 int wsae_counters_update(const long long* last_activated, long long* step_count, int F,
                          long long threshold, int bump, long long* dead_count /*nullable*/,
                          wsae_stream_t stream);
+/* wsae_counters_update, then the step's metrics posted to a host mailbox: mailbox[0..2] = {stats2[0]
+ * (SSE, f64 bits), stats2[1] (L0 count), dead count}, a system-scope fence, mailbox[3] = *seq.
+ * `mailbox` is 4 x int64 of page-locked host memory (device-accessible at the same address under
+ * UVA); `seq` a device int64 the caller bumps per step.  The host polls mailbox[3] instead of
+ * synchronising with the stream: the five `.item()` syncs of sae/training.py:206-214 become one
+ * poll that returns while the rest of the step is still running. */
+int wsae_counters_update_post(const long long* last_activated, long long* step_count, int F,
+                              long long threshold, int bump, long long* dead_count /*nullable*/,
+                              const long long* stats2 /*nullable*/, const long long* seq,
+                              long long* mailbox, wsae_stream_t stream);
 /* hidden[B,F] = scatter(relu(val)) (sae/model.py:115-116) for API callers that need it dense. */
 int wsae_densify_hidden(const int32_t* idx, const float* val, int B, int F, int k, float* hidden,
                         wsae_stream_t stream);

@@ -300,6 +300,31 @@ def test_slot_entry_points_match_direct_ones():
         ops.pack_activations_at(slot.to(torch.int32), B, d, b_pre)
 
 
+def test_counters_update_posts_metrics_to_host_mailbox():
+    """wsae_counters_update_post: same counters as wsae_counters_update, plus {sse bits, l0 count,
+    dead count, seq} in pinned host memory (polled, no stream sync)."""
+    import time
+    from whisper_sae_b200 import ops
+    F, thr = 3072, 5
+    g = torch.Generator().manual_seed(11)
+    last = torch.randint(0, 20, (F,), generator=g).cuda()
+    step = torch.tensor(17, dtype=torch.int64, device="cuda")
+    stats = torch.tensor([torch.tensor(123.5, dtype=torch.float64).view(torch.int64).item(), 4242, -1],
+                         dtype=torch.int64, device="cuda")
+    seq = torch.tensor([9], dtype=torch.int64, device="cuda")
+    mail = torch.zeros(4, dtype=torch.int64).pin_memory()
+    ops.counters_update(last, step, thr, True, stats[2:], post=(stats[:2], seq, mail))
+    mb = mail.numpy()
+    t0 = time.time()
+    while mb[3] != 9:
+        assert time.time() - t0 < 10, "mailbox never posted"
+    want_dead = int(((18 - last.cpu()) > thr).sum())
+    assert step.item() == 18 and stats[2].item() == want_dead
+    assert mb[:1].view("float64")[0] == 123.5 and mb[1] == 4242 and mb[2] == want_dead
+    with pytest.raises(RuntimeError):
+        ops.counters_update(last, step, thr, False, None, post=(stats[:2], seq, torch.zeros(4, dtype=torch.int64)))
+
+
 def test_trainer_bookkeeping_and_checkpoint(tmp_path):
     _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
     cfg = TrainingConfig(batch_size=16, epochs=2, use_amp=False, num_workers=0, checkpoint_every=1)

@@ -111,6 +111,7 @@ _SIGNATURES = {
     ),
     "wsae_renorm_decoder": ([c_void_p, c_int, c_int, c_float, c_void_p, c_void_p], c_int),
     "wsae_counters_update": ([c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p, c_void_p], c_int),
+    "wsae_counters_update_post": ([c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "wsae_densify_hidden": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
     "wsae_cast_bf16": ([c_void_p, c_void_p, c_longlong, c_void_p], c_int),
     "wsae_sumsq": ([c_void_p, c_longlong, c_void_p, c_void_p], c_int),

@@ -34,9 +34,17 @@ renorm_rows_kernel(float* __restrict__ w, int F, int d, float eps,
 }
 
 // Single block: optional step_count bump, then count dead features against the *new* step.
+// Optional mailbox (host-mapped pinned memory, 4 x int64): once the dead count is known the step's
+// metrics are complete - {stats2[0] (SSE, f64 bits), stats2[1] (L0 count), dead count} are posted to
+// the mailbox, then the sequence number *seq_src, behind a system-scope fence.  The host polls the
+// sequence word instead of synchronising with the stream, so it reads the metrics while the rest of
+// the step (weight gradients, optimizer) is still running and has the next step queued before the
+// GPU goes idle.
 __global__ void __launch_bounds__(1024)
 counters_update_kernel(const long long* __restrict__ last_activated, long long* step_count, int F,
-                       long long threshold, int bump, long long* __restrict__ dead_count) {
+                       long long threshold, int bump, long long* __restrict__ dead_count,
+                       const long long* __restrict__ stats2, const long long* __restrict__ seq_src,
+                       long long* mailbox) {
   pdl_prologue();
   __shared__ long long s_step;
   __shared__ int s_part[32];
@@ -53,10 +61,18 @@ counters_update_kernel(const long long* __restrict__ last_activated, long long* 
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
   __syncthreads();
-  if (threadIdx.x == 0 && dead_count != nullptr) {
+  if (threadIdx.x == 0 && (dead_count != nullptr || mailbox != nullptr)) {
     long long t = 0;
     for (int w = 0; w < (blockDim.x >> 5); ++w) t += s_part[w];
-    *dead_count = t;
+    if (dead_count != nullptr) *dead_count = t;
+    if (mailbox != nullptr) {
+      volatile long long* mb = mailbox;
+      mb[0] = stats2 != nullptr ? stats2[0] : 0;
+      mb[1] = stats2 != nullptr ? stats2[1] : 0;
+      mb[2] = t;
+      __threadfence_system();
+      mb[3] = *seq_src;
+    }
   }
 }
 
@@ -301,7 +317,21 @@ extern "C" int wsae_counters_update(const long long* last_activated, long long* 
                                     cudaStream_t stream) {
   if (!last_activated || !step_count || F <= 0) return kBadArg;
   launch_pdl(counters_update_kernel, 1, 1024, 0, stream, last_activated, step_count, F, threshold,
-             bump, dead_count);
+             bump, dead_count, nullptr, nullptr, nullptr);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// wsae_counters_update + the step's metrics posted to a host mailbox (see the kernel's comment).
+// stats2: device {sse f64, l0 u64} (nullable: zeros are posted); seq: device int64; mailbox: 4 x
+// int64 of page-locked host memory, device-accessible at the same address (UVA).
+extern "C" int wsae_counters_update_post(const long long* last_activated, long long* step_count,
+                                         int F, long long threshold, int bump,
+                                         long long* dead_count, const long long* stats2,
+                                         const long long* seq, long long* mailbox,
+                                         cudaStream_t stream) {
+  if (!last_activated || !step_count || F <= 0 || !seq || !mailbox) return kBadArg;
+  launch_pdl(counters_update_kernel, 1, 1024, 0, stream, last_activated, step_count, F, threshold,
+             bump, dead_count, stats2, seq, mailbox);
   return static_cast<int>(cudaGetLastError());
 }
 

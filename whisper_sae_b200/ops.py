@@ -363,11 +363,22 @@ def renorm_decoder_(w_decT: Tensor, eps: float = 1e-12, shadow: Tensor | None = 
 
 
 def counters_update(last_activated: Tensor, step_count: Tensor, threshold: int, bump: bool,
-                    dead_count: Tensor | None) -> None:
+                    dead_count: Tensor | None, *, post: tuple[Tensor | None, Tensor, Tensor] | None = None) -> None:
+    """``post = (stats2, seq, mailbox)``: also post {sse, l0 count, dead count, *seq} to ``mailbox``,
+    a 4 x int64 PINNED HOST tensor the host polls (``stats2`` / ``seq`` are device int64 tensors)."""
     _need_cuda(last_activated, step_count, dead_count)
     if last_activated.dtype != torch.int64 or step_count.dtype != torch.int64:
         raise RuntimeError("dead-feature counters must be int64")
     lib = _lib.load()
+    if post is not None:
+        stats2, seq, mailbox = post
+        _need_cuda(stats2, seq)
+        if mailbox.is_cuda or not mailbox.is_pinned() or mailbox.dtype != torch.int64 or mailbox.numel() < 4:
+            raise RuntimeError("mailbox must be a pinned host int64 tensor of >= 4 elements")
+        if seq.dtype != torch.int64 or (stats2 is not None and (stats2.dtype != torch.int64 or stats2.numel() < 2)):
+            raise RuntimeError("stats2 / seq must be int64 CUDA tensors")
+        _run("wsae_counters_update", lib.wsae_counters_update_post, _ptr(last_activated), _ptr(step_count), last_activated.numel(), int(threshold), int(bump), _ptr(dead_count), _ptr(stats2), _ptr(seq), _ptr(mailbox), _stream())
+        return
     _run("wsae_counters_update", lib.wsae_counters_update, _ptr(last_activated), _ptr(step_count), last_activated.numel(), int(threshold), int(bump), _ptr(dead_count), _stream())
 
 

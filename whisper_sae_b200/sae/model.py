@@ -97,10 +97,11 @@ def _fp32_terms() -> int:
 class _SparseState:
     """Per-forward sparse results shared between the autograd node and the lazy SAEOutput."""
 
-    __slots__ = ("idx", "val", "resid", "stats", "w_dec_used", "rows_total", "d_out")
+    __slots__ = ("idx", "val", "resid", "stats", "w_dec_used", "rows_total", "d_out", "mailbox")
 
     def __init__(self):
         self.idx = self.val = self.resid = self.stats = self.w_dec_used = None
+        self.mailbox = None      # graphed train step: the object whose wait_metrics() yields the stats
         self.rows_total = None
         self.d_out = None
 

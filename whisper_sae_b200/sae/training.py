@@ -81,7 +81,7 @@ class _GraphedStep:
         self.rows = rows
         self.bf16 = bool(trainer.use_amp)
         # per-step control block, ONE 48-byte H2D copy from pinned memory before every replay:
-        # [hyper f32[8] | x_slot i64 | pad].  x_slot holds the device address of the step's batch:
+        # [hyper f32[8] | x_slot i64 | seq i64].  x_slot holds the device address of the step's batch:
         # the kernels that read the activations (K0 pack, K23 target) take it from there when they
         # RUN, so the captured graph trains on a device-resident batch in place; only batches that
         # arrive on the host (or misaligned / non-contiguous) are staged into `x`.
@@ -91,6 +91,14 @@ class _GraphedStep:
         self.hyper_host = self.ctl_host[:32].view(torch.float32)
         self.x_slot = self.ctl[32:40].view(torch.int64)
         self.x_slot_host = self.ctl_host[32:40].view(torch.int64)
+        # seq numbers the steps; the counters kernel posts {sse, l0, dead, seq} to a pinned mailbox as
+        # soon as the metrics are final and SAETrainer._read_metrics polls the sequence word instead
+        # of synchronising with the stream (the reference's five `.item()` calls, training.py:206-214)
+        self.seq_dev = self.ctl[40:48].view(torch.int64)
+        self.seq_host = self.ctl_host[40:48].view(torch.int64)
+        self.mailbox = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.mailbox_np = self.mailbox.numpy()
+        self.seq = 0
         d_in, k_sel = m.input_dim, m.k
         self.in_place = (self.bf16 and d_in % 8 == 0 and ops.wgrad_gemm_supported(d_in)
                          and ops.decode_backward_supported(d_in, k_sel, True))
@@ -210,6 +218,10 @@ class _GraphedStep:
                 ops.backward_sparse(resid, x, m.b_pre.data, w_used, idx, val, self.one, coef,
                                     d_w_enc=self.g_w_enc, d_w_decT=self.g_w_decT,
                                     d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre)
+        if not self.trainer.data_parallel:
+            # the metrics are final once K23 has run: post them now, so the host has them (and the
+            # next step queued) long before the weight-gradient GEMMs and the optimizer finish
+            self._counters()
         buckets = None
         if use_gemm:
             # weight gradients on the tensor cores (K4)
@@ -235,8 +247,8 @@ class _GraphedStep:
         """Counters, clip + AdamW + decoder renorm on the (possibly all-reduced) gradient bucket."""
         m = self.trainer.model
         d = m.input_dim
-        ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold, True,
-                            self.stats[2:])
+        if self.trainer.data_parallel:      # needs the all-reduced stats / fired stamps
+            self._counters()
         ops.sumsq_(self.g_flat, self.sumsq)
         opt_state = self.trainer.optimizer.state
         entries = []
@@ -245,6 +257,23 @@ class _GraphedStep:
             is_dec = p is m.decoder.weight          # feature-major storage: rows = decoder vectors
             entries.append((p.data, g, st["exp_avg"], st["exp_avg_sq"], d if is_dec else 0))
         ops.adamw_multi_(entries, self.hyper, self.sumsq, 1e-12)   # clip + AdamW + decoder renorm
+
+    def _counters(self) -> None:
+        m = self.trainer.model
+        ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold, True,
+                            self.stats[2:], post=(self.stats[:2], self.seq_dev, self.mailbox))
+
+    def wait_metrics(self) -> tuple[float, int, int]:
+        """(sse, l0 count, dead count) of the step launched last: polls the mailbox's sequence word."""
+        mb, seq = self.mailbox_np, self.seq
+        spins = 0
+        while mb[3] != seq:
+            spins += 1
+            if spins > 4_000_000:           # ~1 s: a very long step, or a fault - let CUDA say which
+                torch.cuda.synchronize(self.ctl.device)
+                if mb[3] != seq:
+                    raise RuntimeError("train step finished without posting its metrics")
+        return float(mb[:1].view("float64")[0]), int(mb[1]), int(mb[2])
 
     def run(self, batch: Tensor) -> None:
         """Launch first, book-keep afterwards: everything the GPU needs (batch copy, hyper vector,
@@ -260,6 +289,8 @@ class _GraphedStep:
             src = self.x
         self._live = src                     # the caller may drop its reference before the replay runs
         self.x_slot_host[0] = src.data_ptr()
+        self.seq += 1
+        self.seq_host[0] = self.seq
         group = tr.optimizer.param_groups[0]
         for p in self.params:
             _ensure_adamw_state(tr.optimizer, p)
@@ -327,6 +358,7 @@ class _GraphedStep:
         # expose grads the way autograd would (decoder.weight's grad is the [d, F] transposed view)
         for p, g in zip(self.params, self.grads):
             p.grad = g.t() if p is tr.model.decoder.weight else g
+        self.state.mailbox = self
         tr.model._last_sparse = self.state
 
 
@@ -539,14 +571,19 @@ class SAETrainer:
         lr = self.optimizer.param_groups[0]["lr"]
         st = getattr(self.model, "_last_sparse", None)
         if st is not None and st.stats is not None and (output is None or output.loss.is_cuda):
-            raw = st.stats.cpu()  # the step's single device->host sync (24 bytes)
-            sse = raw[:1].view(torch.float64).item()
+            if output is None and getattr(st, "mailbox", None) is not None:
+                # graphed step: the counters kernel posted the 24 bytes to pinned memory - no stream sync
+                sse, l0_count, dead_count = st.mailbox.wait_metrics()
+            else:
+                raw = st.stats.cpu()  # the step's single device->host sync (24 bytes)
+                sse = raw[:1].view(torch.float64).item()
+                l0_count, dead_count = raw[1].item(), raw[2].item()
             d_out = st.d_out
             loss = float(torch.tensor(sse / (float(st.rows_total) * d_out), dtype=torch.float32))
             l0_rows = st.rows_total if self.data_parallel else rows
-            l0 = float(torch.tensor(raw[1].item() / float(l0_rows), dtype=torch.float32))
+            l0 = float(torch.tensor(l0_count / float(l0_rows), dtype=torch.float32))
             hidden_dim = self.model.feature_last_activated.numel()
-            dead = float(torch.tensor(raw[2].item(), dtype=torch.float32) / hidden_dim)
+            dead = float(torch.tensor(dead_count, dtype=torch.float32) / hidden_dim)
             return TrainingMetrics(loss, loss, 0.0, l0, dead, lr, self.global_step)
         return TrainingMetrics(
             loss=output.loss.item(),
