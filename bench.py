@@ -310,9 +310,9 @@ def roofline(prof: dict, batch: int, d: int, F: int, k: int, peaks: dict, bf16_d
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` of the default
-# workload (tiny, B = 75776, bf16): profiles/r1_v11_top3_ncu_full.txt.  Other shapes: not captured.
-NCU_DRAM_TRAFFIC = {("tiny", 75776): {"wsae_encode_topk": 75.13e6, "wsae_decode_backward": 184.46e6,
-                                      "wsae_wgrad_gemm": 88.98e6}}
+# workload (tiny, B = 75776, bf16): profiles/r1_v12_top3_ncu_full.txt.  Other shapes: not captured.
+NCU_DRAM_TRAFFIC = {("tiny", 75776): {"wsae_encode_topk": 74.24e6, "wsae_decode_backward": 184.51e6,
+                                      "wsae_wgrad_gemm": 90.85e6}}
 
 
 def cpu_oracle_rate(batch: int, seconds_budget: float, threads: int) -> dict:
@@ -485,7 +485,7 @@ def main() -> None:
         roof = roofline(prof, args.batch, D_MODEL, HIDDEN, TOPK, peaks, args.precision == "bf16")
         roof["peak_source"] = f"{peak_src} (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"
         roof["traffic"] = NCU_DRAM_TRAFFIC.get((args.workload, args.batch), {}).get(roof["kernel"])
-        roof["traffic_source"] = "profiles/r1_v11_top3_ncu_full.txt (dram bytes per launch)" \
+        roof["traffic_source"] = "profiles/r1_v12_top3_ncu_full.txt (dram bytes per launch)" \
             if roof["traffic"] is not None else None
         shares = {n: round(v["share_of_step"], 4) for n, v in prof.items() if not n.startswith("_")}
         # the launch-bound YAML batch, for the record
