@@ -23,6 +23,7 @@ import os
 from dataclasses import asdict, dataclass
 from pathlib import Path
 
+import numpy as np
 import torch
 from rich.progress import BarColumn, Progress, SpinnerColumn, TaskProgressColumn, TextColumn
 from torch import Tensor
@@ -99,6 +100,12 @@ class _GraphedStep:
         self.mailbox = torch.zeros(4, dtype=torch.int64).pin_memory()
         self.mailbox_np = self.mailbox.numpy()
         self.seq = 0
+        # numpy views of the pinned control block: a torch index-assignment costs ~5 us each on the
+        # host, which is the critical path once the GPU no longer waits for a stream sync (B = 128)
+        self.hyper_np = self.hyper_host.numpy()
+        self.x_slot_np = self.x_slot_host.numpy()
+        self.seq_np = self.seq_host.numpy()
+        self._step_views: list = []       # (optimizer `step` tensor, its 0-d numpy view) per parameter
         d_in, k_sel = m.input_dim, m.k
         self.in_place = (self.bf16 and d_in % 8 == 0 and ops.wgrad_gemm_supported(d_in)
                          and ops.decode_backward_supported(d_in, k_sel, True))
@@ -132,6 +139,8 @@ class _GraphedStep:
         self.g_part_tail = self.g_flat[starts[2]:]
         self._early = None
         self.grads = [self.g_b_pre, self.g_w_enc, self.g_b_enc, self.g_w_decT, self.g_b_dec]
+        # what autograd would leave in .grad (decoder.weight's grad is the [d, F] transposed view)
+        self._grad_views = [g.t() if p is m.decoder.weight else g for p, g in zip(self.params, self.grads)]
         self.state = _SparseState()
         self.graph: torch.cuda.CUDAGraph | list | None = None
         self._mid: dict = {}
@@ -288,15 +297,15 @@ class _GraphedStep:
             self.x.copy_(batch, non_blocking=True)
             src = self.x
         self._live = src                     # the caller may drop its reference before the replay runs
-        self.x_slot_host[0] = src.data_ptr()
+        self.x_slot_np[0] = src.data_ptr()
         self.seq += 1
-        self.seq_host[0] = self.seq
+        self.seq_np[0] = self.seq
         group = tr.optimizer.param_groups[0]
         for p in self.params:
             _ensure_adamw_state(tr.optimizer, p)
         step_t = float(tr.optimizer.state[self.params[0]]["step"]) + 1.0
         beta1, beta2 = group["betas"]
-        h = self.hyper_host
+        h = self.hyper_np
         h[0], h[1], h[2], h[3], h[4] = group["lr"], beta1, beta2, group["eps"], group["weight_decay"]
         h[5] = 1.0 - beta1 ** step_t
         h[6] = math.sqrt(1.0 - beta2 ** step_t)
@@ -352,12 +361,24 @@ class _GraphedStep:
             self.graph.replay()
             ops.GPU_LAUNCHES += self.kernels_per_replay
         # ---- host book-keeping, overlapping the kernels ----
-        for p in self.params:      # torch.optim.AdamW keeps `step` as a CPU float32 tensor per parameter
-            tr.optimizer.state[p]["step"] += 1
+        # torch.optim.AdamW keeps `step` as a CPU float32 tensor per parameter: bump them through
+        # cached numpy views (re-made when a load_state_dict swapped the tensors)
+        opt_state = tr.optimizer.state
+        if len(self._step_views) != len(self.params) or any(
+                opt_state[p]["step"] is not tv[0] for p, tv in zip(self.params, self._step_views)):
+            self._step_views = []
+            for p in self.params:
+                t = opt_state[p]["step"]
+                self._step_views.append((t, None if t.is_cuda else t.numpy()))
+        for t, view in self._step_views:
+            if view is None:
+                t += 1
+            else:
+                np.add(view, 1, out=view)
         tr.optimizer._opt_called = True    # the fused kernels ARE the optimizer step (lr_scheduler's order check)
-        # expose grads the way autograd would (decoder.weight's grad is the [d, F] transposed view)
-        for p, g in zip(self.params, self.grads):
-            p.grad = g.t() if p is tr.model.decoder.weight else g
+        for p, g in zip(self.params, self._grad_views):   # expose grads the way autograd would
+            if p.grad is not g:
+                p.grad = g
         self.state.mailbox = self
         tr.model._last_sparse = self.state
 
@@ -578,12 +599,13 @@ class SAETrainer:
                 raw = st.stats.cpu()  # the step's single device->host sync (24 bytes)
                 sse = raw[:1].view(torch.float64).item()
                 l0_count, dead_count = raw[1].item(), raw[2].item()
+            # the reference's metrics are fp32 tensors read with .item(): round the same way
             d_out = st.d_out
-            loss = float(torch.tensor(sse / (float(st.rows_total) * d_out), dtype=torch.float32))
+            loss = float(np.float32(sse / (float(st.rows_total) * d_out)))
             l0_rows = st.rows_total if self.data_parallel else rows
-            l0 = float(torch.tensor(l0_count / float(l0_rows), dtype=torch.float32))
+            l0 = float(np.float32(l0_count / float(l0_rows)))
             hidden_dim = self.model.feature_last_activated.numel()
-            dead = float(torch.tensor(dead_count, dtype=torch.float32) / hidden_dim)
+            dead = float(np.float32(dead_count) / np.float32(hidden_dim))
             return TrainingMetrics(loss, loss, 0.0, l0, dead, lr, self.global_step)
         return TrainingMetrics(
             loss=output.loss.item(),
