@@ -236,7 +236,8 @@ def time_steps(tr, batches, steps: int, warmup: int, dist_on: bool) -> tuple[flo
 def time_epoch(tr, host_batches, steps: int, warmup: int, dist_on: bool) -> float:
     """End-to-end seconds for `steps` steps through the public loop `SAETrainer.train_epoch` fed with
     pinned HOST batches: every step's H2D copy (prefetched one batch ahead on a copy stream) and
-    its 24-byte stats readback are inside the timed region."""
+    its metrics readback (32 bytes the counters kernel posts to the pinned host mailbox: sse, l0
+    count, dead count, sequence word) are inside the timed region."""
     n = len(host_batches)
     tr.train_epoch([[host_batches[i % n]] for i in range(warmup)])
     torch.cuda.synchronize()
@@ -500,8 +501,8 @@ def main() -> None:
             "scaling": "strong" if wl["dp"] else "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(args, world),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": args.batch * D_MODEL * 4,
-                    "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * sec_e2e / args.steps},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": args.batch * D_MODEL * 4 + 48,   # batch + control block
+                    "d2h_bytes_per_step": 32, "ms_per_step": 1e3 * sec_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": roof,
