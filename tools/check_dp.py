@@ -16,7 +16,6 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 
 def run(mode: str, steps: int, d: int, F: int, k: int, rows: int, rank: int, world: int):
-    from oracle import topk_sae_oracle as O
     from whisper_sae_b200.config import TrainingConfig
     from whisper_sae_b200.sae import SAETrainer, TopKSAE
     os.environ["WSAE_DP_SEGMENTS"] = "1" if mode == "segments" else "0"
@@ -26,7 +25,10 @@ def run(mode: str, steps: int, d: int, F: int, k: int, rows: int, rank: int, wor
     tr = SAETrainer(sae, cfg, device=f"cuda:{rank}", run_dir=Path(tempfile.mkdtemp()), data_parallel=True)
     tr.setup_scheduler(100)
     assert tr.cuda_graph == ("segments" if mode == "segments" else "eager"), tr.cuda_graph
-    x = O.synthetic_activations(rows * world * steps, d, seed=5).to(f"cuda:{rank}")
+    # SURVEY 8(d) synthetic inputs: row-standardised Gaussians (what the reference's extraction yields)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(rows * world * steps, d, generator=gen)
+    x = ((x - x.mean(1, keepdim=True)) / x.std(1, unbiased=False, keepdim=True)).to(f"cuda:{rank}")
     losses = []
     warm = 4
     for s in range(steps):
