@@ -372,10 +372,13 @@ def run_reference_arm(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        # same config block as the B200 arm at this N; the host trains the N per-GPU units one after
+        # another (reference scripts/train.py:338-342 loops the layers), so its rows/s does not depend on N
+        "config": workload_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{steps} timed train steps of B={batch} rows on the host CPU "
-                                   f"(oracle port of sae/model.py + sae/training.py, torch CPU fp32)"},
+                                   f"(oracle port of sae/model.py + sae/training.py, torch CPU fp32; "
+                                   f"units of an N-GPU job run sequentially at this rate)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
