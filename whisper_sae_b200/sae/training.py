@@ -109,6 +109,15 @@ class _GraphedStep:
         d_in, k_sel = m.input_dim, m.k
         self.in_place = (self.bf16 and d_in % 8 == 0 and ops.wgrad_gemm_supported(d_in)
                          and ops.decode_backward_supported(d_in, k_sel, True))
+        # WSAE_FORK=1 (experiment, single-GPU step only): the small kernels that do not sit on the
+        # K0 -> K1 -> K23 -> K4 chain run on a side stream (a forked branch of the captured graph):
+        # [encoder pack, decoder bf16 cast] next to the activation pack, and [counters + mailbox,
+        # b_pre gradient] next to the bucketing and the two weight-gradient GEMMs.  Their outputs are
+        # pre-allocated, so no allocation ever changes streams.
+        self.fork = os.environ.get("WSAE_FORK", "0") == "1" and not trainer.data_parallel and self.bf16
+        self._side = torch.cuda.Stream(device=dev) if self.fork else None
+        self._w_packed_buf: Tensor | None = None
+        self._w_used_buf: Tensor | None = None
         self._x: Tensor | None = None     # staging buffer, allocated on first use
         self._live: Tensor | None = None  # the batch the slot names (kept alive until the next step)
         self.one = torch.ones((), dtype=torch.float32, device=dev)
@@ -193,13 +202,26 @@ class _GraphedStep:
         terms = 1 if self.bf16 else _fp32_terms()
         w_decT = m.decoder.weight.data.t()
         self.zeroed.zero_()
+        main = torch.cuda.current_stream()
+        if self.fork:
+            if self._w_used_buf is None:
+                self._w_used_buf = torch.empty((F, d), dtype=torch.bfloat16, device=dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                w_packed = self._w_packed_buf = ops.pack_encoder(
+                    m.encoder.weight.data, m.encoder.bias.data, terms, out=self._w_packed_buf)
+                w_used = ops.cast_bf16(w_decT, out=self._w_used_buf)
         if self.in_place:
             a_packed = ops.pack_activations_at(self.x_slot, B, d, m.b_pre.data)
         else:
             a_packed = ops.pack_activations(x, m.b_pre.data, terms)
-        w_packed = ops.pack_encoder(m.encoder.weight.data, m.encoder.bias.data, terms)
+        if self.fork:
+            main.wait_stream(self._side)
+        else:
+            w_packed = ops.pack_encoder(m.encoder.weight.data, m.encoder.bias.data, terms)
         idx, val = ops.encode_topk(a_packed, w_packed, B, F, d, terms, k)
-        w_used = ops.cast_bf16(w_decT) if self.bf16 else w_decT
+        if not self.fork:
+            w_used = ops.cast_bf16(w_decT) if self.bf16 else w_decT
         rows_total = m._global_rows or B
         coef = 2.0 / (float(rows_total) * d)
         dpre = torch.empty((B, k), dtype=torch.float32, device=dev)
@@ -227,7 +249,12 @@ class _GraphedStep:
                 ops.backward_sparse(resid, x, m.b_pre.data, w_used, idx, val, self.one, coef,
                                     d_w_enc=self.g_w_enc, d_w_decT=self.g_w_decT,
                                     d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre)
-        if not self.trainer.data_parallel:
+        if self.fork:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):      # joined in _update, before the gradient norm
+                self._counters()
+                ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
+        elif not self.trainer.data_parallel:
             # the metrics are final once K23 has run: post them now, so the host has them (and the
             # next step queued) long before the weight-gradient GEMMs and the optimizer finish
             self._counters()
@@ -250,7 +277,8 @@ class _GraphedStep:
         if mid["use_gemm"]:
             ops.wgrad_gemm_(self.g_w_decT, mid["resid_bf"], mid["B"], mid["d"], mid["buckets"],
                             mid["buckets"].act, self.one, mid["coef"])
-        ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
+        if not self.fork:
+            ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
 
     def _update(self) -> None:
         """Counters, clip + AdamW + decoder renorm on the (possibly all-reduced) gradient bucket."""
@@ -258,6 +286,8 @@ class _GraphedStep:
         d = m.input_dim
         if self.trainer.data_parallel:      # needs the all-reduced stats / fired stamps
             self._counters()
+        if self.fork:
+            torch.cuda.current_stream().wait_stream(self._side)
         ops.sumsq_(self.g_flat, self.sumsq)
         opt_state = self.trainer.optimizer.state
         entries = []
