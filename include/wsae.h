@@ -10,8 +10,12 @@
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
  *   - return value: 0 ok; <0 argument/shape error (WSAE_E_*); >0 a cudaError_t; >=1000 is
  *     1000 + CUresult from the tensor-map encoder;
- *   - no global mutable state besides per-device function attributes; safe to call from
- *     different host threads on different streams/devices.
+ *   - global state: per-device "function attribute set" flags (written once), the WSAE_PDL
+ *     environment switch (read once) and - EXPERIMENTS ONLY - the process-wide switches behind the
+ *     four wsae_debug_* setters at the end of this header (kernel variant / mode / counter buffer /
+ *     cluster size read by wsae_encode_topk and wsae_wgrad_gemm at launch time).  A process that
+ *     never calls wsae_debug_* may call every other entry point from different host threads on
+ *     different streams/devices; the setters themselves are not thread-safe.
  */
 #ifndef WSAE_H_
 #define WSAE_H_
@@ -184,7 +188,11 @@ int wsae_fused_adamw(float* p, const float* grad, float* m, float* v, long long 
  * [n / row_len, row_len] matrix whose rows are re-normalised to unit L2 norm (clamped at
  * renorm_eps) right after the update: optimizer.step() followed by normalize_decoder_weights()
  * (sae/training.py:193-198, sae/model.py:91-96) in a single pass over the decoder.  `tensors` is a
- * HOST array (copied into the kernel arguments); the pointers inside are device pointers. */
+ * HOST array (copied into the kernel arguments); the pointers inside are device pointers.
+ * flags bit 0 (WSAE_ADAMW_PROJECT_GRAD, rows only; NOT in the reference, default off): before the
+ * update the row's gradient loses its component along the decoder row, g -= (g.w / w.w) w
+ * (BASELINE north_star "gradient projection"); parity tests run with it off. */
+#define WSAE_ADAMW_PROJECT_GRAD 1
 typedef struct {
   float* p;
   const float* g;
@@ -192,7 +200,7 @@ typedef struct {
   float* v;
   long long n;
   int row_len;
-  int reserved;
+  int flags;
 } wsae_adamw_tensor_t;
 int wsae_adamw_multi(const wsae_adamw_tensor_t* tensors, int count, const float* hyper,
                      const double* grad_sumsq, float renorm_eps, wsae_stream_t stream);
@@ -236,6 +244,7 @@ int wsae_debug_encode_variant(int variant);
 int wsae_debug_encode_mode(int mode);
 int wsae_debug_encode_counters(void* device_buf);
 int wsae_debug_wgrad_cluster(int max_cluster_size); /* 1, 2 (default), 4, 8: upper bound for wsae_wgrad_gemm's cluster */
+int wsae_debug_decode_backward_general(int on);     /* 1: wsae_decode_backward always runs its general kernel (A/B against the d % 128 == 0 fast path) */
 
 #ifdef __cplusplus
 }

@@ -133,6 +133,53 @@ def run_dead_case() -> None:
     print("dead_fixed_row: alive", fixture["num_alive"])
 
 
+def resample_pre_state(d: int, F: int, k: int, thr: int, model_seed: int, counter_seed: int,
+                       step_count: int) -> dict:
+    """State before a resample call, reproducible from seeds alone (the GPU tests rebuild it the same
+    way): seeded module init, then a seeded pattern of ``feature_last_activated`` stamps in
+    [0, step_count) so that roughly (1 - thr / step_count) of the features count as dead."""
+    torch.manual_seed(model_seed)
+    model = TopKSAE(d, F, k=k, dead_feature_threshold=thr)
+    g = torch.Generator().manual_seed(counter_seed)
+    with torch.no_grad():
+        model.feature_last_activated.copy_(torch.randint(0, step_count, (F,), generator=g))
+        model.step_count.fill_(step_count)
+    return model
+
+
+def run_resample_case(name: str, d: int, F: int, k: int, thr: int, rows: int, num_resample,
+                      model_seed: int, counter_seed: int, data_seed: int, step_count: int,
+                      train_mode: bool = True) -> None:
+    """model.py:197-257 driven on the live reference module (train mode: the forward inside bumps
+    step_count, :229)."""
+    model = resample_pre_state(d, F, k, thr, model_seed, counter_seed, step_count)
+    model.train(train_mode)
+    dead_before = torch.where(model.get_dead_features())[0]
+    x = synthetic_activations(rows, d, data_seed)
+    ret = model.resample_dead_features(x, num_resample=num_resample)
+    n_cap = len(dead_before) if num_resample is None else min(len(dead_before), num_resample)
+    n_written = min(n_cap, rows)
+    tgt = dead_before[:n_written]
+    sd = model.state_dict()
+    fixture = {
+        "recipe": dict(name=name, d=d, F=F, k=k, thr=thr, rows=rows, num_resample=num_resample,
+                       model_seed=model_seed, counter_seed=counter_seed, data_seed=data_seed,
+                       step_count=step_count, train_mode=train_mode),
+        "torch_version": torch.__version__,
+        "returned": int(ret),
+        "dead_before": dead_before.clone(),
+        "written": tgt.clone(),
+        "encoder_rows": sd["encoder.weight"][tgt].clone(),          # the rewritten rows, in full
+        "decoder_cols_T": sd["decoder.weight"][:, tgt].t().contiguous().clone(),
+        "encoder_bias_written": sd["encoder.bias"][tgt].clone(),
+        "feature_last_activated": sd["feature_last_activated"].clone(),
+        "step_count": int(sd["step_count"]),
+        "after_digest": {n: digest(sd[n]) for n in PARAM_ORDER},
+    }
+    torch.save(fixture, GOLDEN / f"{name}.pt")
+    print(f"{name}: returned {ret}, dead before {len(dead_before)}, rows written {n_written}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     run_case("small_64x256", d=64, F=256, k=8, B=32, steps=6, total_steps=40, lr=1e-3, warmup=4,
@@ -142,3 +189,17 @@ if __name__ == "__main__":
     run_case("mid_128x1024_k32", d=128, F=1024, k=32, B=256, steps=3, total_steps=100, lr=3e-4,
              warmup=10, thr=2, model_seed=5, data_seed=77, full_state=False)
     run_dead_case()
+    # BASELINE configs 3 / 4 (config.py:25-33 whisper-small d=768; :45-50 expansion_factor le=32)
+    run_case("small_768x6144", d=768, F=6144, k=32, B=256, steps=3, total_steps=1000, lr=1e-4,
+             warmup=100, thr=1000, model_seed=42, data_seed=2345, full_state=False)
+    run_case("large_1280x40960", d=1280, F=40960, k=32, B=256, steps=2, total_steps=1000, lr=1e-4,
+             warmup=100, thr=1000, model_seed=42, data_seed=3456, full_state=False)
+    # resample_dead_features (model.py:197-257)
+    run_resample_case("resample_64x256", d=64, F=256, k=8, thr=10, rows=16, num_resample=None,
+                      model_seed=3, counter_seed=4, data_seed=5, step_count=40)
+    run_resample_case("resample_64x256_eval", d=64, F=256, k=8, thr=10, rows=128, num_resample=20,
+                      model_seed=3, counter_seed=4, data_seed=5, step_count=40, train_mode=False)
+    run_resample_case("resample_384x3072", d=384, F=3072, k=32, thr=50, rows=1024, num_resample=64,
+                      model_seed=42, counter_seed=9, data_seed=4567, step_count=100)
+    run_resample_case("resample_1280x40960", d=1280, F=40960, k=32, thr=50, rows=2048, num_resample=32,
+                      model_seed=42, counter_seed=9, data_seed=5678, step_count=100)

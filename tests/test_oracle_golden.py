@@ -7,7 +7,8 @@ import torch
 from oracle import topk_sae_oracle as O
 from tests.conftest import load_golden
 
-CASES = ["small_64x256", "tiny_test_384x3072", "mid_128x1024_k32"]
+# the last two are BASELINE configs 3 / 4 (whisper-small 768->6144, large-v3 1280->40960)
+CASES = ["small_64x256", "tiny_test_384x3072", "mid_128x1024_k32", "small_768x6144", "large_1280x40960"]
 
 
 def _check_digest(t: torch.Tensor, dg: dict, rtol: float, atol: float = 1e-7):
@@ -100,6 +101,39 @@ def test_dead_feature_counters_fixed_row():
     dead = O.dead_features(state, r["thr"])
     assert torch.equal(dead, fx["dead_mask"])
     assert int((~dead).sum()) == fx["num_alive"] == 4
+
+
+RESAMPLE_CASES = ["resample_64x256", "resample_64x256_eval", "resample_384x3072", "resample_1280x40960"]
+
+
+def resample_pre_state(r: dict) -> dict:
+    """The state oracle/make_golden.py's resample cases start from (seeds only)."""
+    torch.manual_seed(r["model_seed"])
+    state = O.init_state(r["d"], r["F"])
+    g = torch.Generator().manual_seed(r["counter_seed"])
+    state["feature_last_activated"] = torch.randint(0, r["step_count"], (r["F"],), generator=g)
+    state["step_count"] = torch.tensor(r["step_count"], dtype=torch.long)
+    return state
+
+
+@pytest.mark.parametrize("name", RESAMPLE_CASES)
+def test_resample_dead_features_matches_reference(name):
+    """model.py:197-257 on the live reference (fixture) vs the oracle restatement."""
+    fx = load_golden(name)
+    r = fx["recipe"]
+    state = resample_pre_state(r)
+    assert torch.equal(torch.where(O.dead_features(state, r["thr"]))[0], fx["dead_before"])
+    x = O.synthetic_activations(r["rows"], r["d"], r["data_seed"])
+    ret = O.resample_dead_features(state, x, r["k"], r["thr"], r["num_resample"], training=r["train_mode"])
+    assert ret == fx["returned"]
+    assert int(state["step_count"]) == fx["step_count"] == r["step_count"] + int(r["train_mode"])
+    assert torch.equal(state["feature_last_activated"], fx["feature_last_activated"])   # bit-exact
+    tgt = fx["written"]
+    torch.testing.assert_close(state["encoder.weight"][tgt], fx["encoder_rows"], rtol=0, atol=0)
+    torch.testing.assert_close(state["decoder.weight"][:, tgt].t(), fx["decoder_cols_T"], rtol=0, atol=0)
+    assert (state["encoder.bias"][tgt] == 0).all()
+    for n in O.PARAM_ORDER:
+        _check_digest(state[n], fx["after_digest"][n], rtol=1e-7)
 
 
 def test_dense_hidden_has_exactly_k_nonzeros():

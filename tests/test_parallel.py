@@ -138,3 +138,37 @@ def test_batch_sharded_step_matches_single_device(tmp_path, use_amp, tol):
             torch.testing.assert_close(p, q, rtol=tol * 10, atol=tol * scale, msg=lambda msg: f"{n}: {msg}")
     for p, q in zip(ranks[0].model.parameters(), ranks[1].model.parameters()):
         assert torch.equal(p, q)          # replicas stay bit-identical without a broadcast
+
+
+@pytest.mark.gpu
+def test_nccl_two_rank_step_matches_golden_and_single_device(tmp_path):
+    """REAL NCCL, two processes on two GPUs (skipped on a one-GPU box): the batch-sharded step vs
+    (a) the live-reference golden traces at 384->3072, 768->6144 and 1280->40960 in fp32-grade mode
+    (losses / weights 1e-5, counters bit-exact) and (b) the single-device bf16 step on the
+    concatenated batch.  tests/_dp_worker.py is the per-rank program."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with `gpurun --gpus 2`)")
+    root = Path(__file__).resolve().parents[1]
+    port = 29500 + os.getpid() % 400
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", str(port), str(root / "tests" / "_dp_worker.py"),
+         str(tmp_path)], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    for rank in range(2):
+        res = json.loads((tmp_path / f"rank{rank}.json").read_text())
+        print(json.dumps(res))
+        by = {r["case"]: r for r in res}
+        for name in ("tiny_test_384x3072", "small_768x6144", "large_1280x40960"):
+            r = by[name]
+            tol = 1e-5 if r["strict"] else 2e-3
+            assert r["loss_rel"] <= tol and r["weight_rel"] <= tol, r
+            assert r["counters_equal"] or not r["strict"], r
+        b = by["bf16_768x6144_vs_single"]
+        assert b["loss_rel"] <= 1e-4 and b["l0_equal"] and b["dead_equal"] and b["counters_equal"], b
+        assert b["weight_rel"] <= 2e-2 and b["replicas_identical"], b

@@ -18,7 +18,8 @@ WANT = [
     "smsp__inst_executed.sum",
     "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-    "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio" ,
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
@@ -44,6 +45,8 @@ def main(path: str) -> None:
         for w in WANT:
             if w in col:
                 print(f"{w:84s} {r[col[w]]:>18s} {units[col[w]]}")
+                if w == "lts__t_sectors.sum":   # 32-byte sectors: the L2 traffic SURVEY 8(d) asks for
+                    print(f"{'lts bytes (= lts__t_sectors.sum x 32 B)':84s} {float(r[col[w]].replace(',', '')) * 32 / 1e6:>18.3f} Mbyte")
 
 
 if __name__ == "__main__":

@@ -48,7 +48,7 @@ class AdamwTensor(ctypes.Structure):
     """wsae_adamw_tensor_t (include/wsae.h)."""
 
     _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p),
-                ("n", c_longlong), ("row_len", c_int), ("reserved", c_int)]
+                ("n", c_longlong), ("row_len", c_int), ("flags", c_int)]
 
 
 _SIGNATURES = {
@@ -56,6 +56,7 @@ _SIGNATURES = {
     "wsae_debug_encode_mode": ([c_int], c_int),
     "wsae_debug_encode_counters": ([c_void_p], c_int),
     "wsae_debug_wgrad_cluster": ([c_int], c_int),
+    "wsae_debug_decode_backward_general": ([c_int], c_int),
     "wsae_adamw_multi": ([POINTER(AdamwTensor), c_int, c_void_p, c_void_p, c_float, c_void_p], c_int),
     "wsae_abi_version": ([], c_int),
     "wsae_packed_k": ([c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)], c_int),

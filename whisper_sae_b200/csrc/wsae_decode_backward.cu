@@ -22,7 +22,7 @@
 // in the bf16 rounding that K4's weight-gradient GEMMs consume.
 // Every decoder byte is read from L2 exactly once.  (A first version staged the rows in shared
 // memory with one cp.async.bulk per row: 32 bulk copies of 768 B per activation row saturate the
-// TMA unit at ~45 ns per copy - 4x slower than this form; profiles/r1_k23_notes.md.)
+// TMA unit at ~45 ns per copy - 0.62 ms against 0.23 ms for this form)
 #include "wsae_common.cuh"
 
 namespace wsae {
@@ -65,10 +65,37 @@ __device__ __forceinline__ void fhfma_bcast4(float4& acc, uint2 w, uint32_t h) {
       : "r"(w.x), "r"(w.y), "r"(h));
 }
 
+// D(16x8, fp32) += A(16x16, bf16, row) * B(16x8, bf16, col): the legacy warp-level tensor-core path
+// (SASS HMMA.16816.F32.BF16).  Used for the k dot products of the fast path below; the tcgen05 / TMEM
+// path is for the dense GEMMs (K1, K4) - here the operands are 32 gathered rows that already sit in
+// registers, the math is 2 % of a GEMM tile and the kernel is bound by the L2 gather, not by FLOPs.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                               uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 constexpr int kFusedWarps = 4;
+constexpr int kDotScratch = 32 * 9;   // floats per warp: 32 dot products x 8 partial sums, stride 9 (bank-conflict free)
 
 // bf16 decoder shadow only.  k <= 32, d % 8 == 0.
-__global__ void __launch_bounds__(kFusedWarps * 32, 4)
+//
+// kFast (d % 128 == 0: every BASELINE width - 384, 768, 1280, 4 x 384): every slice is full, so the
+// gather is 32 unpredicated loads whose address is ONE IMAD.WIDE from a 32-bit row offset (the
+// general form spent 5 instructions per load on bounds predicates, register zeroing and re-loading
+// the base pointer: 25 % of all instructions issued, ncu source page), and the 32 dot products
+// r . W_dec[i_j] run on the tensor pipe: mma.m16n8k16 with A = {w[j].x, w[j'].x, w[j].y, w[j'].y}
+// reads lane l's register as "row (l >> 2), k-columns (l & 3)": the 8 "rows" of the A tile are the
+// eight 16-column blocks of gathered row j (rows 8-15: row j'), and with B = the lane's own bf16
+// residual {rb.x, rb.y} column n of B is block n of the residual - so the DIAGONAL D[g][g] is the
+// partial dot product over block g.  Sixteen HMMA per slice replace 128 FHFMA, the accumulators
+// stay in registers across the slices, and the diagonal is summed through 1.1 KB of shared memory
+// per warp instead of a 31-step shuffle transpose.
+template <bool kFast>
+__global__ void __launch_bounds__(kFusedWarps * 32, kFast ? 3 : 4)
 decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __restrict__ w_decT,
                        const float* __restrict__ b_dec, const float* __restrict__ b_pre,
                        const int32_t* __restrict__ idx, const float* __restrict__ val,
@@ -86,6 +113,7 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
   const int dp = round_up(d, 128);
   float* s_bias = fsm;
   float* s_g = fsm + dp + warp * dp;       // warp-private: plain read-modify-write, no atomics
+  float* s_dot = fsm + (1 + kFusedWarps) * dp;   // fast path: per-warp scratch of the dot-product reduction
   for (int i = threadIdx.x; i < dp; i += blockDim.x) {
     float b = 0.f;
     if (i < d) b = b_dec[i] + (b_pre != nullptr ? b_pre[i] : 0.f);
@@ -124,6 +152,75 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
     // element offset (in uint2 units) of each selected decoder row; inactive entries read row 0
     // with weight 0, so every lane issues the same, fully unrolled load sequence
     const int my_off = fired ? my_i * d4 : 0;
+
+    if (kFast) {
+      // ---------------- fast path: full 128-column slices, dots on the tensor pipe ----------------
+      float acc[16][4];
+#pragma unroll
+      for (int p = 0; p < 16; ++p) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f;
+      const uint2* lane_base = wbase + lane;
+      const float* trow = target + static_cast<size_t>(row) * d + lane * 4;
+      for (int c0 = 0; c0 < d; c0 += 128) {
+        const uint2* sb = lane_base + (c0 >> 2);
+        uint2 w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t off = __shfl_sync(0xffffffffu, static_cast<uint32_t>(my_off), j);
+          w[j] = __ldg(sb + off);
+        }
+        const float4 t = __ldg(reinterpret_cast<const float4*>(trow + c0));
+        float4 a = *reinterpret_cast<const float4*>(s_bias + c0 + lane * 4);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t hb = __shfl_sync(0xffffffffu, my_hb, j);
+          fhfma_bcast4(a, w[j], hb);
+        }
+        float4 r;
+        r.x = a.x - t.x; r.y = a.y - t.y; r.z = a.z - t.z; r.w = a.w - t.w;
+        sse_local = fmaf(r.x, r.x, sse_local);
+        sse_local = fmaf(r.y, r.y, sse_local);
+        sse_local = fmaf(r.z, r.z, sse_local);
+        sse_local = fmaf(r.w, r.w, sse_local);
+        __nv_bfloat162 rlo = __floats2bfloat162_rn(r.x, r.y);
+        __nv_bfloat162 rhi = __floats2bfloat162_rn(r.z, r.w);
+        uint2 rb;
+        rb.x = *reinterpret_cast<uint32_t*>(&rlo);
+        rb.y = *reinterpret_cast<uint32_t*>(&rhi);
+        const size_t o = static_cast<size_t>(row) * d + c0 + lane * 4;
+        if (resid != nullptr) *reinterpret_cast<float4*>(resid + o) = r;
+        if (resid_bf16 != nullptr) *reinterpret_cast<uint2*>(resid_bf16 + o) = rb;
+        float4 gs = *reinterpret_cast<float4*>(s_g + c0 + lane * 4);
+        gs.x += r.x; gs.y += r.y; gs.z += r.z; gs.w += r.w;
+        *reinterpret_cast<float4*>(s_g + c0 + lane * 4) = gs;
+#pragma unroll
+        for (int p = 0; p < 16; ++p)
+          mma_bf16_16816(acc[p], w[2 * p].x, w[2 * p + 1].x, w[2 * p].y, w[2 * p + 1].y, rb.x, rb.y);
+      }
+      // D[g][g] of tile p lives in lane (g, t = g >> 1): register g & 1 for row 2p, 2 + (g & 1) for
+      // row 2p + 1.  The 8 holder lanes park their 32 partial sums in shared memory, lane j adds up
+      // the 8 partials of dot product j.
+      const int g = lane >> 2;
+      float* scr = s_dot + warp * kDotScratch;
+      if ((lane & 3) == (g >> 1)) {
+        const bool odd = (g & 1) != 0;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          scr[(2 * p) * 9 + g] = odd ? acc[p][1] : acc[p][0];
+          scr[(2 * p + 1) * 9 + g] = odd ? acc[p][3] : acc[p][2];
+        }
+      }
+      __syncwarp();
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot += scr[lane * 9 + i];
+      __syncwarp();
+      const float my_dv = fired ? s * dot : 0.f;
+      if (lane < k) {
+        if (dpre_val != nullptr) dpre_val[static_cast<size_t>(row) * k + lane] = my_dv;
+        if (fired && d_b_enc != nullptr) atomicAdd(d_b_enc + my_i, my_dv);
+      }
+      continue;
+    }
 
     float part[32];
 #pragma unroll
@@ -224,9 +321,14 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
   }
 }
 
+// experiments only (wsae_debug_decode_backward_general): 1 = always the general kernel (A/B runs)
+static int g_decode_backward_general = 0;
+
 }  // namespace wsae
 
 using namespace wsae;
+
+extern "C" int wsae_debug_decode_backward_general(int on) { g_decode_backward_general = on; return 0; }
 
 // See include/wsae.h.  Returns WSAE_E_UNSUPPORTED for shapes the fused kernel does not cover
 // (fp32 decoder, k > 32, d % 8 != 0): callers then use K2 + K3.
@@ -245,13 +347,35 @@ static int decode_backward_impl(const float* target, const float* const* target_
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool fast_shape = (d % 128 == 0) && !g_decode_backward_general;
+  const int per_sm = fast_shape ? 3 : 4;
   int blocks = ceil_div(B, kFusedWarps);
-  if (blocks > sms * 4) blocks = sms * 4;
-  const size_t smem = (1 + kFusedWarps) * static_cast<size_t>(round_up(d, 128)) * sizeof(float);
-  launch_pdl(decode_backward_kernel, blocks, kFusedWarps * 32, smem, stream, target,
-             static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
-             F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
-             last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at);
+  if (blocks > sms * per_sm) blocks = sms * per_sm;
+  const size_t smem = ((1 + kFusedWarps) * static_cast<size_t>(round_up(d, 128)) + kFusedWarps * kDotScratch) *
+                      sizeof(float);
+  if (smem > 48 * 1024) {      // d > 2432: opt in to the large dynamic shared-memory carve-out (once per device)
+    static bool attr_set[64] = {};
+    if (dev >= 64 || !attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(decode_backward_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(decode_backward_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      if (dev < 64) attr_set[dev] = true;
+    }
+  }
+  const bool fast = (d % 128 == 0) && !g_decode_backward_general;
+  if (fast)
+    launch_pdl(decode_backward_kernel<true>, blocks, kFusedWarps * 32, smem, stream, target,
+               static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
+               F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
+               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at);
+  else
+    launch_pdl(decode_backward_kernel<false>, blocks, kFusedWarps * 32, smem, stream, target,
+               static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
+               F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
+               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at);
   return static_cast<int>(cudaGetLastError());
 }
 

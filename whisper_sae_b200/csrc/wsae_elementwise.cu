@@ -246,19 +246,76 @@ adamw_multi_kernel(const AdamwBatch batch, const float* __restrict__ hyper,
       const long long row = lu * 8 + warp;
       if (row < rows) {
         const long long base = row * T.row_len;
-        float ss = 0.f;
-        // pass 1: update, store moments, keep the un-normalised weight in place
-        for (int c = lane; c < T.row_len; c += 32) {
-          float pv = T.p[base + c], mv = T.m[base + c], vv = T.v[base + c];
-          adamw_elem(pv, T.g[base + c] * clip, mv, vv, lr, b1, b2, eps, wd, bc2s, step_size);
-          T.p[base + c] = pv; T.m[base + c] = mv; T.v[base + c] = vv;
-          ss = fmaf(pv, pv, ss);
+        const bool project = (T.pad_ & 1) != 0;
+        constexpr int kKeep = 16;                      // float4 per lane held in registers: row_len <= 2048
+        const int nv = T.row_len >> 2;
+        const bool vec = (T.row_len & 3) == 0 && nv <= 32 * kKeep &&
+                         ((reinterpret_cast<uintptr_t>(T.p) | reinterpret_cast<uintptr_t>(T.g) |
+                           reinterpret_cast<uintptr_t>(T.m) | reinterpret_cast<uintptr_t>(T.v)) & 15u) == 0;
+        // optional gradient projection (north_star; NOT in the reference, off by default): remove
+        // the component of the row's gradient along the (unit-norm) decoder row, g -= (g.w) w, so
+        // the step does not spend itself on a length change the renormalisation undoes anyway
+        float gw = 0.f;
+        if (project) {
+          float ww = 0.f;
+          for (int c = lane; c < T.row_len; c += 32) {
+            const float pv = T.p[base + c];
+            gw = fmaf(T.g[base + c], pv, gw);
+            ww = fmaf(pv, pv, ww);
+          }
+          gw = warp_sum(gw) / fmaxf(warp_sum(ww), 1e-30f);
         }
-        ss = warp_sum(ss);
-        const float nrm = fmaxf(sqrtf(ss), renorm_eps);
-        // pass 2 (same lane touches the same addresses: L1-resident): x / max(||x||, eps), the
-        // F.normalize formula
-        for (int c = lane; c < T.row_len; c += 32) T.p[base + c] = T.p[base + c] / nrm;
+        float ss = 0.f;
+        if (vec) {
+          // ONE pass over the row: 16-byte accesses, updated weights stay in registers until the
+          // row norm is known (the scalar form re-read them: 0.68 ms -> see DESIGN for large-v3)
+          float4 keep[kKeep];
+#pragma unroll
+          for (int i = 0; i < kKeep; ++i) {
+            const int c4 = lane + i * 32;
+            if (c4 < nv) {
+              float4 pv = *reinterpret_cast<const float4*>(T.p + base + c4 * 4);
+              float4 g = *reinterpret_cast<const float4*>(T.g + base + c4 * 4);
+              float4 mv = *reinterpret_cast<const float4*>(T.m + base + c4 * 4);
+              float4 vv = *reinterpret_cast<const float4*>(T.v + base + c4 * 4);
+              if (project) { g.x -= gw * pv.x; g.y -= gw * pv.y; g.z -= gw * pv.z; g.w -= gw * pv.w; }
+              adamw_elem(pv.x, g.x * clip, mv.x, vv.x, lr, b1, b2, eps, wd, bc2s, step_size);
+              adamw_elem(pv.y, g.y * clip, mv.y, vv.y, lr, b1, b2, eps, wd, bc2s, step_size);
+              adamw_elem(pv.z, g.z * clip, mv.z, vv.z, lr, b1, b2, eps, wd, bc2s, step_size);
+              adamw_elem(pv.w, g.w * clip, mv.w, vv.w, lr, b1, b2, eps, wd, bc2s, step_size);
+              *reinterpret_cast<float4*>(T.m + base + c4 * 4) = mv;
+              *reinterpret_cast<float4*>(T.v + base + c4 * 4) = vv;
+              keep[i] = pv;
+              ss = fmaf(pv.x, pv.x, ss); ss = fmaf(pv.y, pv.y, ss);
+              ss = fmaf(pv.z, pv.z, ss); ss = fmaf(pv.w, pv.w, ss);
+            }
+          }
+          ss = warp_sum(ss);
+          const float nrm = fmaxf(sqrtf(ss), renorm_eps);     // x / max(||x||, eps): F.normalize
+#pragma unroll
+          for (int i = 0; i < kKeep; ++i) {
+            const int c4 = lane + i * 32;
+            if (c4 < nv) {
+              float4 pv = keep[i];
+              pv.x /= nrm; pv.y /= nrm; pv.z /= nrm; pv.w /= nrm;
+              *reinterpret_cast<float4*>(T.p + base + c4 * 4) = pv;
+            }
+          }
+        } else {
+          // pass 1: update, store moments, keep the un-normalised weight in place
+          for (int c = lane; c < T.row_len; c += 32) {
+            float pv = T.p[base + c], mv = T.m[base + c], vv = T.v[base + c];
+            float g = T.g[base + c];
+            if (project) g -= gw * pv;
+            adamw_elem(pv, g * clip, mv, vv, lr, b1, b2, eps, wd, bc2s, step_size);
+            T.p[base + c] = pv; T.m[base + c] = mv; T.v[base + c] = vv;
+            ss = fmaf(pv, pv, ss);
+          }
+          ss = warp_sum(ss);
+          const float nrm = fmaxf(sqrtf(ss), renorm_eps);
+          // pass 2 (same lane touches the same addresses: L1-resident)
+          for (int c = lane; c < T.row_len; c += 32) T.p[base + c] = T.p[base + c] / nrm;
+        }
       }
     }
   }
@@ -288,7 +345,7 @@ extern "C" int wsae_adamw_multi(const wsae_adamw_tensor_host* tensors, int count
     const wsae_adamw_tensor_host& h = tensors[i];
     if (!h.p || !h.g || !h.m || !h.v || h.n <= 0 || h.row_len < 0) return kBadArg;
     if (h.row_len > 0 && h.n % h.row_len != 0) return kBadArg;
-    b.t[i] = AdamwTensor{h.p, h.g, h.m, h.v, h.n, h.row_len, 0};
+    b.t[i] = AdamwTensor{h.p, h.g, h.m, h.v, h.n, h.row_len, h.reserved};
     b.unit_start[i] = units;
     units += h.row_len == 0 ? (h.n + 1023) / 1024 : (h.n / h.row_len + 7) / 8;
   }

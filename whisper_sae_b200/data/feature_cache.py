@@ -140,21 +140,26 @@ class FeatureCache:
 def extract_and_cache_features(whisper_model, processor, audio_dataloader, cache: FeatureCache,
                                encoder_layers: list[int], decoder_layers: list[int],
                                device: torch.device | str = "cuda",
-                               max_samples: int | None = None) -> None:
+                               max_samples: int | None = None, *,
+                               device_budget_bytes: int = 8 << 30) -> None:
     """Run Whisper over ``audio_dataloader`` and write one cache file per hooked layer
     (feature_cache.py:200-306; same signature, ``processor`` is unused there too).
 
     Hooked hidden states are normalised (the model's final LayerNorm) and flattened straight into a
     growable device matrix per layer (``sae.hooks.ActivationMatrix``); nothing visits the host until
-    ``cache.save`` writes the ``[N, d]`` fp32 tensor in the reference's file format.
+    ``cache.save`` writes the ``[N, d]`` fp32 tensor in the reference's file format - unless the
+    hooked layers together would hold more than ``device_budget_bytes`` on the GPU, in which case full
+    chunks are spilled to pinned host memory as they fill (the reference accumulates on the host).
     """
     from ..sae.hooks import ActivationMatrix, _hidden_of, run_whisper
 
     whisper_model = whisper_model.to(device)
     whisper_model.eval()
     d = whisper_model.config.d_model
-    enc = {layer: ActivationMatrix(d, device) for layer in encoder_layers}
-    dec = {layer: ActivationMatrix(d, device) for layer in decoder_layers}
+    n_sinks = max(1, len(encoder_layers) + len(decoder_layers))
+    cap_rows = max(4096, device_budget_bytes // (n_sinks * d * 4))
+    enc = {layer: ActivationMatrix(d, device, max_device_rows=cap_rows) for layer in encoder_layers}
+    dec = {layer: ActivationMatrix(d, device, max_device_rows=cap_rows) for layer in decoder_layers}
     enc_ln, dec_ln = whisper_model.model.encoder.layer_norm, whisper_model.model.decoder.layer_norm
     handles = []
     for layer, sink in enc.items():

@@ -413,17 +413,22 @@ def fused_adamw_(p: Tensor, grad: Tensor, m: Tensor, v: Tensor, hyper: Tensor,
     _run("wsae_fused_adamw", lib.wsae_fused_adamw, _ptr(p), _ptr(grad), _ptr(m), _ptr(v), p.numel(), _ptr(hyper), _ptr(grad_sumsq), _stream())
 
 
-def adamw_multi_(entries: list[tuple[Tensor, Tensor, Tensor, Tensor, int]], hyper: Tensor,
-                 grad_sumsq: Tensor | None, renorm_eps: float = 1e-12) -> None:
+ADAMW_PROJECT_GRAD = 1     # wsae.h WSAE_ADAMW_PROJECT_GRAD
+
+
+def adamw_multi_(entries: list[tuple], hyper: Tensor, grad_sumsq: Tensor | None,
+                 renorm_eps: float = 1e-12) -> None:
     """Clip + AdamW for several tensors in one launch.  ``entries`` = (param, grad, exp_avg,
-    exp_avg_sq, row_len): row_len > 0 => rows of that length are re-normalised after the update
-    (the feature-major decoder); all four tensors of an entry share one dense layout."""
+    exp_avg_sq, row_len[, flags]): row_len > 0 => rows of that length are re-normalised after the
+    update (the feature-major decoder); flags & ADAMW_PROJECT_GRAD => the row gradient is first
+    projected off the row direction; all four tensors of an entry share one dense layout."""
     lib = _lib.load()
     arr = (_lib.AdamwTensor * len(entries))()
-    for a, (p, g, m, v, row_len) in zip(arr, entries):
+    for a, ent in zip(arr, entries):
+        p, g, m, v, row_len = ent[:5]
         _need_cuda(p, g, m, v)
         a.p, a.g, a.m, a.v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
-        a.n, a.row_len, a.reserved = p.numel(), int(row_len), 0
+        a.n, a.row_len, a.flags = p.numel(), int(row_len), int(ent[5]) if len(ent) > 5 else 0
     _run("wsae_adamw_multi", lib.wsae_adamw_multi, arr, len(entries), _ptr(hyper), _ptr(grad_sumsq), float(renorm_eps), _stream())
 
 
@@ -478,6 +483,11 @@ def layernorm_rows_(x: Tensor, gamma: Tensor | None, beta: Tensor | None, eps: f
     if x2.stride(1) != 1:
         x2 = x2.contiguous()
     n = x2.shape[0]
+    # a half-precision Whisper carries half-precision LayerNorm parameters: the kernel computes in fp32
+    if gamma is not None and gamma.dtype != torch.float32:
+        gamma = gamma.to(torch.float32)
+    if beta is not None and beta.dtype != torch.float32:
+        beta = beta.to(torch.float32)
     _f32c(gamma, "layer_norm.weight")
     _f32c(beta, "layer_norm.bias")
     if out.dtype != torch.float32 or out.dim() != 2 or out.shape[1] != d or out.stride(1) != 1:

@@ -52,34 +52,70 @@ class ActivationCache:
 
 
 class ActivationMatrix:
-    """Growable fp32 ``[N, d]`` device matrix that hooked batches are normalised INTO."""
+    """Growable fp32 ``[N, d]`` matrix that hooked batches are normalised INTO, on the device.
 
-    def __init__(self, d: int, device: torch.device | str, capacity: int = 1 << 16):
+    ``max_device_rows`` bounds the device-resident part: when the next batch would not fit, the rows
+    gathered so far are spilled to pinned host memory (one D2H copy per spill, the reference copies
+    every hooked tensor, hooks.py:90,107) and the device buffer is reused - so a long extraction over
+    many layers (1500 encoder tokens per sample) cannot exhaust HBM.  Growth never keeps an old and a
+    new buffer alive beyond the copy, and never grows past the bound.
+    """
+
+    def __init__(self, d: int, device: torch.device | str, capacity: int = 1 << 16,
+                 max_device_rows: int | None = None):
         self.d = d
-        self.rows = 0
+        self.rows = 0                      # total rows appended (device part + spilled part)
+        self._dev_rows = 0
+        self._max = max_device_rows
+        if max_device_rows is not None:
+            capacity = min(capacity, max_device_rows)
         self._buf = torch.empty((max(capacity, 1), d), dtype=torch.float32, device=device)
+        self._spilled: list[Tensor] = []
+
+    def _spill(self) -> None:
+        if self._dev_rows == 0:
+            return
+        host = torch.empty((self._dev_rows, self.d), dtype=torch.float32, pin_memory=True)
+        host.copy_(self._buf[: self._dev_rows])
+        self._spilled.append(host)
+        self._dev_rows = 0
 
     def _reserve(self, extra: int) -> None:
-        need = self.rows + extra
-        if need > self._buf.shape[0]:
-            grown = torch.empty((max(need, 2 * self._buf.shape[0]), self.d), dtype=torch.float32,
-                                device=self._buf.device)
-            grown[: self.rows].copy_(self._buf[: self.rows])
-            self._buf = grown
+        need = self._dev_rows + extra
+        if need <= self._buf.shape[0]:
+            return
+        if self._max is not None and need > self._max:
+            self._spill()
+            need = extra
+            if need <= self._buf.shape[0]:
+                return
+        cap = max(need, 2 * self._buf.shape[0])
+        if self._max is not None:
+            cap = max(need, min(cap, self._max))
+        grown = torch.empty((cap, self.d), dtype=torch.float32, device=self._buf.device)
+        if self._dev_rows:
+            grown[: self._dev_rows].copy_(self._buf[: self._dev_rows])
+        self._buf = grown
 
     def append(self, hidden: Tensor, layer_norm: nn.LayerNorm | None) -> None:
         """Append ``hidden [..., d]`` (flattened), through ``layer_norm`` if given."""
         n = hidden.numel() // self.d
         self._reserve(n)
+        lo = self._dev_rows
         if layer_norm is None:
-            self._buf[self.rows:self.rows + n].copy_(hidden.reshape(n, self.d))
+            self._buf[lo:lo + n].copy_(hidden.reshape(n, self.d))
         else:
             ops.layernorm_rows_(hidden, layer_norm.weight.detach(), layer_norm.bias.detach(), layer_norm.eps,
-                                self._buf, row0=self.rows)
+                                self._buf, row0=lo)
+        self._dev_rows += n
         self.rows += n
 
     def tensor(self) -> Tensor:
-        return self._buf[: self.rows]
+        """The ``[rows, d]`` matrix: a device view when nothing was spilled, else one host tensor."""
+        if not self._spilled:
+            return self._buf[: self._dev_rows]
+        parts = self._spilled + ([self._buf[: self._dev_rows].cpu()] if self._dev_rows else [])
+        return torch.cat(parts, dim=0)
 
 
 def _hidden_of(output) -> Tensor:

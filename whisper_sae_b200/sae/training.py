@@ -4,8 +4,9 @@
 Same constructor, public attributes, ``train_step`` / ``train_epoch`` / ``train`` /
 ``setup_scheduler`` / checkpoint + metrics file formats.  Differences that are deliberate:
 
-* the five per-step ``.item()`` host syncs (training.py:207-215) become ONE 24-byte readback of
-  the packed stats buffer written by the kernels (SSE as float64, L0 count, dead count);
+* the five per-step ``.item()`` host syncs (training.py:207-215) become ONE poll of a 32-byte pinned
+  host mailbox the counters kernel posts to ({SSE as float64, L0 count, dead count, sequence word});
+  the autograd (non-graphed) path reads the same three numbers with one 24-byte ``stats.cpu()``;
 * ``use_amp`` selects the bf16 tensor-core path instead of fp16 autocast.  bf16 keeps the fp32
   exponent range, so loss scaling is the identity: ``self.scaler`` is still a ``GradScaler``
   (attribute preserved) but constructed disabled unless ``grad_scaler=True`` is passed; the fused
@@ -294,7 +295,8 @@ class _GraphedStep:
         for p, g in zip(self.params, self.grads):
             st = opt_state[p]
             is_dec = p is m.decoder.weight          # feature-major storage: rows = decoder vectors
-            entries.append((p.data, g, st["exp_avg"], st["exp_avg_sq"], d if is_dec else 0))
+            flags = ops.ADAMW_PROJECT_GRAD if (is_dec and self.trainer.project_decoder_grad) else 0
+            entries.append((p.data, g, st["exp_avg"], st["exp_avg_sq"], d if is_dec else 0, flags))
         ops.adamw_multi_(entries, self.hyper, self.sumsq, 1e-12)   # clip + AdamW + decoder renorm
 
     def _counters(self) -> None:
@@ -432,6 +434,7 @@ class SAETrainer:
         data_parallel: bool = False,
         dp_comm=None,
         global_batch_rows: int | None = None,
+        project_decoder_grad: bool = False,
     ):
         self.model = model.to(device)
         self.config = config
@@ -469,6 +472,10 @@ class SAETrainer:
         # the reference defines _maybe_resample_dead_features but never calls it (training.py:97-134);
         # auto_resample=True wires it in after every step (off by default: parity)
         self.auto_resample = bool(auto_resample)
+        # north_star's "gradient projection": remove the component of each decoder row's gradient along
+        # the row before the AdamW step (fused into adamw_multi).  The reference does not do this
+        # (grep finds no projection in sae/training.py), so it is OFF by default and excluded from parity.
+        self.project_decoder_grad = bool(project_decoder_grad)
         self.data_parallel = bool(data_parallel)
         self.dp_comm = None
         self.global_batch_rows = global_batch_rows     # default: local rows x world (equal shards)
@@ -586,7 +593,11 @@ class SAETrainer:
 
         batch = batch.to(self.device, non_blocking=True)
 
-        with torch.amp.autocast("cuda", enabled=self.use_amp):
+        # bf16, not torch's fp16 default: the scaler is disabled unless grad_scaler=True, and models that
+        # do not run through the fused node (ReLUSAE, dense crosscoders, SkipTranscoder.skip) would train
+        # in fp16 without loss scaling otherwise; with an ENABLED scaler the reference's fp16 is kept
+        amp_dtype = torch.float16 if self.scaler.is_enabled() else torch.bfloat16
+        with torch.amp.autocast("cuda", enabled=self.use_amp, dtype=amp_dtype):
             output: SAEOutput = self.model(batch)
 
         self.optimizer.zero_grad()
