@@ -672,7 +672,7 @@ def main() -> None:
     host_batches = [rows[i * args.batch:(i + 1) * args.batch].pin_memory() for i in range(nb)]
     blk_e, _ = time_blocks(epoch_runner(tr, host_batches), args.steps, args.warmup, repeats, dist_on)
     e2e = args.batch * args.steps * world / blk_e["median"]
-    h2d_bytes = args.batch * d * 4 + 48          # batch + control block
+    h2d_bytes = args.batch * d * 4 + 64          # batch + control block
 
     line = None
     side: dict = {}

@@ -33,7 +33,7 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 107: + wsae_pack_activations_at, wsae_decode_backward_at, wsae_counters_update_post). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 108: + wsae_pack_activations_rows_at, wsae_decode_backward_rows_at, adamw flags). */
 int wsae_abi_version(void);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
@@ -52,6 +52,13 @@ int wsae_pack_activations(const float* x, const float* b_pre /*nullable*/, int B
 int wsae_pack_activations_at(const float* const* x_at, const float* b_pre /*nullable*/, int B,
                              int Bp, int d, int terms, void* a_packed /*bf16 [Bp,Kp]*/,
                              wsae_stream_t stream);
+/* Slot form with a row-index indirection: batch row r is row (*rows_at)[r] of the matrix *x_at names
+ * (*rows_at == NULL: identity; indices are int64, as torch.randperm yields them).  Lets the trainer
+ * walk a shuffled epoch over a device-resident activation matrix without materialising each batch
+ * (reference: DataLoader(TensorDataset(features), shuffle=True), data/feature_cache.py:169-197). */
+int wsae_pack_activations_rows_at(const float* const* x_at, const long long* const* rows_at,
+                                  const float* b_pre /*nullable*/, int B, int Bp, int d, int terms,
+                                  void* a_packed /*bf16 [Bp,Kp]*/, wsae_stream_t stream);
 int wsae_pack_encoder(const float* w_enc /*[F,d]*/, const float* b_enc /*[F] nullable*/, int F,
                       int Fp, int d, int terms, void* w_packed /*bf16 [Fp,Kp]*/,
                       wsae_stream_t stream);
@@ -118,6 +125,15 @@ int wsae_decode_backward_at(const float* const* target_at, const void* w_decT, i
                             float coef, int B, int d, int F, int k, float* resid, void* resid_bf16,
                             void* stats, long long* last_activated, const long long* step_count,
                             float* d_b_enc, float* d_b_dec, float* dpre_val, wsae_stream_t stream);
+/* As wsae_decode_backward_at, target row of batch row r = (*target_at)[(*rows_at)[r], :]
+ * (see wsae_pack_activations_rows_at). */
+int wsae_decode_backward_rows_at(const float* const* target_at, const long long* const* rows_at,
+                                 const void* w_decT, int w_is_bf16, const float* b_dec,
+                                 const float* b_pre /*nullable*/, const int32_t* idx, const float* val,
+                                 const float* grad_out /*nullable*/, float coef, int B, int d, int F,
+                                 int k, float* resid, void* resid_bf16, void* stats,
+                                 long long* last_activated, const long long* step_count,
+                                 float* d_b_enc, float* d_b_dec, float* dpre_val, wsae_stream_t stream);
 /* out[idx[b,j], :] += vals[b,j] * (rows[b,:] - center): the encoder weight gradient as a sparse
  * scatter when the input width differs from the decoder width (transcoders); dr % 4 == 0. */
 int wsae_scatter_rows(const float* rows, const float* center /*nullable*/, const int32_t* idx,
@@ -244,7 +260,7 @@ int wsae_debug_encode_variant(int variant);
 int wsae_debug_encode_mode(int mode);
 int wsae_debug_encode_counters(void* device_buf);
 int wsae_debug_wgrad_cluster(int max_cluster_size); /* 1, 2 (default), 4, 8: upper bound for wsae_wgrad_gemm's cluster */
-int wsae_debug_decode_backward_general(int on);     /* 1: wsae_decode_backward always runs its general kernel (A/B against the d % 128 == 0 fast path) */
+int wsae_debug_decode_backward_general(int mode);   /* wsae_decode_backward kernel choice: 0 = per-shape (default), 1 = general, 2 = mma.sync dots, 3 = cp.async staged (A/B runs) */
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""K23 (wsae_decode_backward) alone: fast path (d % 128 == 0: lean gather + mma.sync dots) against the
-general kernel on the same inputs - outputs compared, both timed with CUDA events.
+"""K23 (wsae_decode_backward) alone: the staged kernel (cp.async ring, default for d % 128 == 0), the
+mma.sync variant and the general kernel on the same inputs - outputs compared, all timed with CUDA events.
 
     python tools/bench_k23.py [--shapes 75776x384x3072,75776x768x6144,37888x1280x40960]
 """
@@ -14,9 +14,10 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from whisper_sae_b200 import _lib, ops  # noqa: E402
 
 
-def run(B, d, F, k, general, reps=20):
+def run(B, d, F, k, mode, reps=20):
+    """mode: 0 = the library's per-shape choice, 1 = general (register staged), 2 = mma.sync dots, 3 = staged (cp.async ring)"""
     lib = _lib.load()
-    lib.wsae_debug_decode_backward_general(1 if general else 0)
+    lib.wsae_debug_decode_backward_general(mode)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(B, d, generator=g).cuda()
     w = (torch.randn(F, d, generator=g) / d ** 0.5).cuda().to(torch.bfloat16)
@@ -57,8 +58,10 @@ def main():
     for sh in args.shapes.split(","):
         B, d, F = (int(v) for v in sh.split("x"))
         k = 32
-        t_gen, m_gen, o_gen = run(B, d, F, k, True)
-        t_fast, m_fast, o_fast = run(B, d, F, k, False)
+        t_gen, m_gen, o_gen = run(B, d, F, k, 1)
+        t_mma, m_mma, _ = run(B, d, F, k, 2)
+        t_fast, m_fast, o_fast = run(B, d, F, k, 3)
+        t_auto, _, _ = run(B, d, F, k, 0)
         gather = B * k * d * 2
         errs = []
         for name, a, b in zip(("resid_bf16", "dpre", "stats", "db_enc", "db_dec"), o_fast, o_gen):
@@ -67,8 +70,9 @@ def main():
                 errs.append(f"sse rel {abs(sse_a - sse_b) / abs(sse_b):.1e} l0 {'==' if a[1] == b[1] else '!='}")
             else:
                 errs.append(f"{name} rel-L2 {((a - b).norm() / b.norm().clamp_min(1e-30)).item():.1e}")
-        print(f"B={B} d={d} F={F}: general {t_gen * 1e3:.1f} us (min {m_gen * 1e3:.1f}), fast {t_fast * 1e3:.1f} us "
-              f"(min {m_fast * 1e3:.1f}) = {gather / t_fast / 1e6:.0f} GB/s gathered; " + "; ".join(errs))
+        print(f"B={B} d={d} F={F}: general {t_gen * 1e3:.1f} us (min {m_gen * 1e3:.1f}), mma {t_mma * 1e3:.1f} us, "
+              f"staged {t_fast * 1e3:.1f} us (min {m_fast * 1e3:.1f}) = {gather / t_fast / 1e6:.0f} GB/s gathered; "
+              f"library choice {t_auto * 1e3:.1f} us; staged vs general: " + "; ".join(errs))
 
 
 if __name__ == "__main__":

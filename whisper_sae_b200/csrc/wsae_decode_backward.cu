@@ -104,10 +104,13 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
                        FusedStats* __restrict__ stats, long long* __restrict__ last_activated,
                        const long long* __restrict__ step_count, float* __restrict__ d_b_enc,
                        float* __restrict__ d_b_dec, float* __restrict__ dpre_val,
-                       const float* const* __restrict__ target_at) {
+                       const float* const* __restrict__ target_at,
+                       const long long* const* __restrict__ rows_at) {
   extern __shared__ __align__(16) float fsm[];   // [dp] bias (b_dec + b_pre), then one [dp] db_dec accumulator per warp
   pdl_prologue();
   if (target_at != nullptr) target = *target_at;   // address from a device-resident slot (graph replay)
+  // batch row r is row (*rows_at)[r] of the target matrix (0 / null = identity): wsae_pack.cu
+  const long long* perm = rows_at != nullptr ? *rows_at : nullptr;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int dp = round_up(d, 128);
@@ -159,7 +162,8 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
 #pragma unroll
       for (int p = 0; p < 16; ++p) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f;
       const uint2* lane_base = wbase + lane;
-      const float* trow = target + static_cast<size_t>(row) * d + lane * 4;
+      const size_t srow = perm != nullptr ? static_cast<size_t>(__ldg(perm + row)) : static_cast<size_t>(row);
+      const float* trow = target + srow * d + lane * 4;
       for (int c0 = 0; c0 < d; c0 += 128) {
         const uint2* sb = lane_base + (c0 >> 2);
         uint2 w[32];
@@ -238,7 +242,10 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
         if (ok) w[j] = __ldg(wbase + off + (col >> 2));
       }
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) t = __ldg(reinterpret_cast<const float4*>(target + static_cast<size_t>(row) * d + col));
+      if (ok) {
+        const size_t srow = perm != nullptr ? static_cast<size_t>(__ldg(perm + row)) : static_cast<size_t>(row);
+        t = __ldg(reinterpret_cast<const float4*>(target + srow * d + col));
+      }
       float4 acc = *reinterpret_cast<const float4*>(s_bias + col);
       // ---- reconstruction of this slice (fp32) ----
 #pragma unroll
@@ -321,8 +328,257 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
   }
 }
 
+// ================================================================================================
+// K23, staged form (d % 128 == 0, d >= 128 * (STAGES - 1)): the gather runs AHEAD of the math.
+//
+// ncu + tools/l2_gather_bench (profiles/r2_l2_gather.json): a pure gather of the same 1.86 GB of
+// decoder rows runs at 14-16 TB/s out of L2, the register-staged kernel above at 8.3 TB/s with the
+// issue slots 62 % busy - each warp loads a slice (32 rows x 256 B), waits ~2000 cycles for the loaded
+// L2 queue to drain, computes, and only then asks for the next slice, so the memory system idles
+// while the warps compute and the warps idle while it works.  Here every warp owns a ring of STAGES
+// shared-memory slice buffers (8 KB each) filled by cp.async (LDGSTS.128: L2 -> shared memory, no
+// registers): while slice q is multiplied out of registers, slices q+1 .. q+STAGES-1 - of this
+// activation row or the next - are already in flight.  16 cp.async per slice (lanes 0-15 copy the
+// 256-byte slice of one gathered row, lanes 16-31 the next), one LDS.64 per gathered row and lane to
+// bring the staged slice into the same register layout the general kernel uses; the arithmetic
+// (FHFMA.BF16 reconstruction and dot products, transpose-reduce, stats, stamps) is unchanged, so the
+// results are bit-identical to the general kernel.
+// ================================================================================================
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kSliceBytes = 32 * 256;   // one staged slice: 32 gathered rows x 128 bf16 columns
+
+template <int STAGES>
+__global__ void __launch_bounds__(kFusedWarps * 32, STAGES == 2 ? 3 : 2)
+decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloat16* __restrict__ w_decT,
+                              const float* __restrict__ b_dec, const float* __restrict__ b_pre,
+                              const int32_t* __restrict__ idx, const float* __restrict__ val,
+                              const float* __restrict__ grad_out, float coef, int B, int d, int F, int k,
+                              float* __restrict__ resid, __nv_bfloat16* __restrict__ resid_bf16,
+                              FusedStats* __restrict__ stats, long long* __restrict__ last_activated,
+                              const long long* __restrict__ step_count, float* __restrict__ d_b_enc,
+                              float* __restrict__ d_b_dec, float* __restrict__ dpre_val,
+                              const float* const* __restrict__ target_at,
+                              const long long* const* __restrict__ rows_at, int dbg) {
+  extern __shared__ __align__(16) float fsm[];   // [d] bias, [warps][d] db_dec partials, then the slice rings
+  pdl_prologue();
+  if (target_at != nullptr) target = *target_at;
+  const long long* perm = rows_at != nullptr ? *rows_at : nullptr;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float* s_bias = fsm;
+  float* s_g = fsm + d + warp * d;
+  const uint32_t ring = smem_u32(fsm + (1 + kFusedWarps) * d) + warp * (STAGES * kSliceBytes);
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    s_bias[i] = b_dec[i] + (b_pre != nullptr ? b_pre[i] : 0.f);
+#pragma unroll
+    for (int w = 0; w < kFusedWarps; ++w) fsm[d + w * d + i] = 0.f;
+  }
+  __syncthreads();
+
+  const float s = coef * (grad_out != nullptr ? *grad_out : 1.f);
+  const long long stamp = (last_activated != nullptr && step_count != nullptr) ? (*step_count + 1) : 0;
+  const int warp_global = blockIdx.x * kFusedWarps + warp;
+  const int warp_stride = gridDim.x * kFusedWarps;
+  const int nsl = d >> 7;                      // slices per activation row
+  const int row_bytes = d * 2;
+  const char* wbytes = reinterpret_cast<const char*>(w_decT);
+  // copy role of this lane: rows 2i + (lane >> 4), 16-byte chunk (lane & 15) of the slice
+  const int cp_half = lane >> 4;
+  const uint32_t cp_dst = (lane >> 4) * 256u + (lane & 15) * 16u;
+  const int cp_col = (lane & 15) * 16;
+
+  // (index, value) of a row's k entries, one per lane: byte offset of the gathered decoder row and
+  // the bf16 activation; invalid / non-positive entries gather row 0 with weight 0
+  auto load_meta = [&](int row, int32_t& mi, float& mv) {
+    mi = -1;
+    mv = 0.f;
+    if (row < B && lane < k) {
+      mi = __ldg(idx + static_cast<size_t>(row) * k + lane);
+      mv = __ldg(val + static_cast<size_t>(row) * k + lane);
+    }
+  };
+  auto issue_slice = [&](uint32_t off_bytes, int sl, int stage) {     // off_bytes: this lane's entry
+    const uint32_t dst0 = ring + stage * kSliceBytes + cp_dst;
+    const char* src0 = wbytes + sl * 256 + cp_col;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t off = __shfl_sync(0xffffffffu, off_bytes, 2 * i + cp_half);
+      cp_async_16(dst0 + i * 512, src0 + off);
+    }
+  };
+
+  float sse_local = 0.f;
+  unsigned int l0_local = 0;
+
+  int row = warp_global;
+  int32_t cur_i, nxt_i;
+  float cur_v, nxt_v;
+  load_meta(row, cur_i, cur_v);
+  load_meta(row + warp_stride, nxt_i, nxt_v);
+  // Entries that did not fire (value <= 0) still gather THEIR row (weight 0); invalid indices gather a
+  // row that differs per (activation row, lane).  Sending them all to row 0, as the register-staged
+  // kernel does, is harmless there (L1 serves it) but cp.async bypasses L1: with half of the entries
+  // inactive every SM hammered the same few L2 sectors and the kernel ran 10x slower (2.7 ms).
+  auto row_offset = [&](int32_t mi, int row_) -> uint32_t {
+    const uint32_t f = (mi >= 0 && mi < F) ? static_cast<uint32_t>(mi)
+                                           : (static_cast<uint32_t>(row_) * 37u + static_cast<uint32_t>(lane)) % static_cast<uint32_t>(F);
+    return f * static_cast<uint32_t>(row_bytes);
+  };
+  bool cur_f = (cur_i >= 0) && (cur_i < F) && (cur_v > 0.f);
+  uint32_t cur_off = row_offset(cur_i, row);
+  bool nxt_f = (nxt_i >= 0) && (nxt_i < F) && (nxt_v > 0.f);
+  uint32_t nxt_off = row_offset(nxt_i, row + warp_stride);
+
+  // prologue: slices 0 .. STAGES-2 of the flattened (row, slice) sequence (nsl >= STAGES - 1: they
+  // belong to the first row)
+#pragma unroll
+  for (int q = 0; q < STAGES - 1; ++q) {
+    if (row < B) issue_slice(cur_off, q, q);
+    cp_async_commit();
+  }
+  int stage = 0;                               // stage holding the slice about to be computed
+
+  for (; row < B; row += warp_stride) {
+    const bool fired = cur_f;
+    const int32_t my_i = cur_i;
+    if (fired && last_activated != nullptr && !(dbg & 4)) last_activated[my_i] = stamp;
+    const float my_v = fired ? cur_v : 0.f;
+    const uint32_t my_hb = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(my_v)));
+    const uint32_t mask = __ballot_sync(0xffffffffu, fired);
+    l0_local += (lane == 0) ? __popc(mask) : 0;
+    const size_t srow = perm != nullptr ? static_cast<size_t>(__ldg(perm + row)) : static_cast<size_t>(row);
+    const float* trow = target + srow * d + lane * 4;
+    int32_t nn_i = -1;     // metadata two rows ahead: requested after the first slice's copies are
+    float nn_v = 0.f;      // out (not at the top of the row, where ptxas made the target address wait
+                           // for it: 11 % of all stall samples), consumed when this row is done
+
+    float part[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) part[j] = 0.f;
+
+    for (int sl = 0; sl < nsl; ++sl) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!(dbg & 1)) t = __ldg(reinterpret_cast<const float4*>(trow + sl * 128));
+      cp_async_wait<STAGES - 2>();             // slice (row, sl) has landed (this lane's copies)
+      __syncwarp();                            // ... and every other lane's; the stage consumed last is free
+      {   // keep the ring full: slice sl + STAGES - 1 of this row, or of the next one
+        const int ps = sl + STAGES - 1;
+        int pstage = stage + STAGES - 1;
+        if (pstage >= STAGES) pstage -= STAGES;
+        if (ps < nsl) issue_slice(cur_off, ps, pstage);
+        else if (row + warp_stride < B) issue_slice(nxt_off, ps - nsl, pstage);
+        cp_async_commit();
+      }
+      if (sl == 0) load_meta(row + 2 * warp_stride, nn_i, nn_v);
+      const uint32_t sbase = ring + stage * kSliceBytes + lane * 8;
+      uint2 w[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[j].x), "=r"(w[j].y) : "r"(sbase + j * 256));
+      float4 acc = *reinterpret_cast<const float4*>(s_bias + sl * 128 + lane * 4);
+      if (dbg & 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc.x += __uint_as_float(w[j].x ^ w[j].y);
+      } else if (dbg & 128) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) fhfma_bcast4(acc, w[j], my_hb);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t hb = __shfl_sync(0xffffffffu, my_hb, j);
+          fhfma_bcast4(acc, w[j], hb);
+        }
+      }
+      float4 r;
+      r.x = acc.x - t.x; r.y = acc.y - t.y; r.z = acc.z - t.z; r.w = acc.w - t.w;
+      sse_local = fmaf(r.x, r.x, sse_local);
+      sse_local = fmaf(r.y, r.y, sse_local);
+      sse_local = fmaf(r.z, r.z, sse_local);
+      sse_local = fmaf(r.w, r.w, sse_local);
+      __nv_bfloat162 rlo = __floats2bfloat162_rn(r.x, r.y);
+      __nv_bfloat162 rhi = __floats2bfloat162_rn(r.z, r.w);
+      uint2 rb;
+      rb.x = *reinterpret_cast<uint32_t*>(&rlo);
+      rb.y = *reinterpret_cast<uint32_t*>(&rhi);
+      const size_t o = static_cast<size_t>(row) * d + sl * 128 + lane * 4;
+      if (!(dbg & 2)) {
+        if (resid != nullptr) *reinterpret_cast<float4*>(resid + o) = r;
+        if (resid_bf16 != nullptr) *reinterpret_cast<uint2*>(resid_bf16 + o) = rb;
+      }
+      if (!(dbg & 16)) {
+        float4 gs = *reinterpret_cast<float4*>(s_g + sl * 128 + lane * 4);
+        gs.x += r.x; gs.y += r.y; gs.z += r.z; gs.w += r.w;
+        *reinterpret_cast<float4*>(s_g + sl * 128 + lane * 4) = gs;
+      }
+      if (!(dbg & 64)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          fhfma2(part[j], part[j + 1], w[j].x, rb.x, w[j + 1].x);
+          fhfma2(part[j], part[j + 1], w[j].y, rb.y, w[j + 1].y);
+        }
+      }
+      if (++stage == STAGES) stage = 0;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = upper ? part[i] : part[i + off];
+        const float keep = upper ? part[i + off] : part[i];
+        part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    const float my_dv = fired ? s * part[0] : 0.f;
+    if (lane < k && !(dbg & 8)) {
+      if (dpre_val != nullptr) dpre_val[static_cast<size_t>(row) * k + lane] = my_dv;
+      if (fired && d_b_enc != nullptr) atomicAdd(d_b_enc + my_i, my_dv);
+    }
+    // rotate the metadata window
+    cur_i = nxt_i; cur_v = nxt_v; cur_f = nxt_f; cur_off = nxt_off;
+    nxt_i = nn_i; nxt_v = nn_v;
+    nxt_f = (nxt_i >= 0) && (nxt_i < F) && (nxt_v > 0.f);
+    nxt_off = row_offset(nxt_i, row + 2 * warp_stride);
+  }
+  cp_async_wait<0>();
+
+  __shared__ float s_sse[kFusedWarps];
+  __shared__ unsigned int s_l0[kFusedWarps];
+  const float wsum = warp_sum(sse_local);
+  if (lane == 0) {
+    s_sse[warp] = wsum;
+    s_l0[warp] = l0_local;
+  }
+  __syncthreads();
+  if (d_b_dec != nullptr)
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kFusedWarps; ++w) t += fsm[d + w * d + i];
+      atomicAdd(d_b_dec + i, s * t);
+    }
+  if (threadIdx.x == 0 && stats != nullptr) {
+    double tsum = 0.0;
+    unsigned long long c = 0;
+    for (int w = 0; w < kFusedWarps; ++w) {
+      tsum += static_cast<double>(s_sse[w]);
+      c += s_l0[w];
+    }
+    atomicAdd(&stats->sse, tsum);
+    atomicAdd(&stats->l0_count, c);
+  }
+}
+
 // experiments only (wsae_debug_decode_backward_general): 1 = always the general kernel (A/B runs)
-static int g_decode_backward_general = 0;
+static int g_decode_backward_general = 0;   // 0 = per-shape choice (see the launcher), 1 = general, 2 = mma, 3 = staged
 
 }  // namespace wsae
 
@@ -333,7 +589,7 @@ extern "C" int wsae_debug_decode_backward_general(int on) { g_decode_backward_ge
 // See include/wsae.h.  Returns WSAE_E_UNSUPPORTED for shapes the fused kernel does not cover
 // (fp32 decoder, k > 32, d % 8 != 0): callers then use K2 + K3.
 static int decode_backward_impl(const float* target, const float* const* target_at,
-                                const void* w_decT, int w_is_bf16, const float* b_dec,
+                                const long long* const* rows_at, const void* w_decT, int w_is_bf16, const float* b_dec,
                                 const float* b_pre, const int32_t* idx, const float* val,
                                 const float* grad_out, float coef, int B, int d, int F, int k,
                                 float* resid, void* resid_bf16, void* stats,
@@ -347,7 +603,7 @@ static int decode_backward_impl(const float* target, const float* const* target_
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const bool fast_shape = (d % 128 == 0) && !g_decode_backward_general;
+  const bool fast_shape = (d % 128 == 0) && ((g_decode_backward_general & 0xff) == 2 || (g_decode_backward_general & 0xff) == 0);
   const int per_sm = fast_shape ? 3 : 4;
   int blocks = ceil_div(B, kFusedWarps);
   if (blocks > sms * per_sm) blocks = sms * per_sm;
@@ -365,17 +621,71 @@ static int decode_backward_impl(const float* target, const float* const* target_
       if (dev < 64) attr_set[dev] = true;
     }
   }
-  const bool fast = (d % 128 == 0) && !g_decode_backward_general;
+  const auto wd = static_cast<const __nv_bfloat16*>(w_decT);
+  const auto rbf = static_cast<__nv_bfloat16*>(resid_bf16);
+  const auto st = static_cast<FusedStats*>(stats);
+  // staged kernel: full slices, ring depth 3 (2 when the shared memory of two resident blocks would
+  // not fit), byte offsets of the gathered rows in 32 bits
+  const int mode = g_decode_backward_general & 0xff;
+  const int dbg = g_decode_backward_general >> 8;
+  // Kernel choice (tools/bench_k23.py, same box, B = 75776 / 37888, k = 32):
+  //   d = 384:  staged 213 us | mma 232 us | general 239 us   -> staged where THREE blocks fit an SM
+  //   d = 768:  staged 490 us | mma 411 us | general 430 us   -> mma (the ring leaves room for 8 warps only)
+  //   d = 1280: staged 387 us | mma 352 us | general 367 us   -> mma
+  //   d % 128 != 0: general
+  // mode (wsae_debug_decode_backward_general): 0 = this choice, 1 = general, 2 = mma, 3 = staged
+  const bool staged_fits3 =
+      3 * ((1 + kFusedWarps) * static_cast<size_t>(d) * sizeof(float) + kFusedWarps * 2 * kSliceBytes + 1024) <= 227 * 1024;
+  if (((mode == 0 && staged_fits3) || mode == 3) && d % 128 == 0 &&
+      static_cast<long long>(F) * d * 2 <= 0xffffffffLL) {
+    const size_t base = (1 + kFusedWarps) * static_cast<size_t>(d) * sizeof(float);
+    // ring depth 2 leaves room for three resident blocks (12 warps per SM) at d = 384: measured
+    // faster than depth 3 with two blocks (tools/bench_k23.py); WSAE_K23_STAGES overrides
+    static const int want_stages = [] {
+      const char* e = std::getenv("WSAE_K23_STAGES");
+      return (e && e[0] == '3') ? 3 : 2;
+    }();
+    int stages = want_stages;
+    if (2 * (base + kFusedWarps * 3 * kSliceBytes + 1024) > 227 * 1024 || d < 256) stages = 2;
+    const size_t smem_s = base + static_cast<size_t>(kFusedWarps) * stages * kSliceBytes;
+    static bool attr_staged[64] = {};
+    if (dev >= 64 || !attr_staged[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(decode_backward_staged_kernel<3>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(decode_backward_staged_kernel<2>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      if (dev < 64) attr_staged[dev] = true;
+    }
+    if (smem_s <= 220 * 1024) {
+      int per = static_cast<int>((227 * 1024) / (smem_s + 1024));
+      if (per > (stages == 2 ? 3 : 2)) per = stages == 2 ? 3 : 2;
+      if (per < 1) per = 1;
+      int nblk = ceil_div(B, kFusedWarps);
+      if (nblk > sms * per) nblk = sms * per;
+      if (stages == 3)
+        launch_pdl(decode_backward_staged_kernel<3>, nblk, kFusedWarps * 32, smem_s, stream, target, wd, b_dec,
+                   b_pre, idx, val, grad_out, coef, B, d, F, k, resid, rbf, st, last_activated, step_count,
+                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, dbg);
+      else
+        launch_pdl(decode_backward_staged_kernel<2>, nblk, kFusedWarps * 32, smem_s, stream, target, wd, b_dec,
+                   b_pre, idx, val, grad_out, coef, B, d, F, k, resid, rbf, st, last_activated, step_count,
+                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, dbg);
+      return static_cast<int>(cudaGetLastError());
+    }
+  }
+  const bool fast = (d % 128 == 0) && (mode == 2 || mode == 0);
   if (fast)
     launch_pdl(decode_backward_kernel<true>, blocks, kFusedWarps * 32, smem, stream, target,
                static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
                F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
-               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at);
+               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at);
   else
     launch_pdl(decode_backward_kernel<false>, blocks, kFusedWarps * 32, smem, stream, target,
                static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
                F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
-               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at);
+               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -387,7 +697,7 @@ extern "C" int wsae_decode_backward(const float* target, const void* w_decT, int
                                     const long long* step_count, float* d_b_enc, float* d_b_dec,
                                     float* dpre_val, cudaStream_t stream) {
   if (!target) return kBadArg;
-  return decode_backward_impl(target, nullptr, w_decT, w_is_bf16, b_dec, b_pre, idx, val, grad_out,
+  return decode_backward_impl(target, nullptr, nullptr, w_decT, w_is_bf16, b_dec, b_pre, idx, val, grad_out,
                               coef, B, d, F, k, resid, resid_bf16, stats, last_activated, step_count,
                               d_b_enc, d_b_dec, dpre_val, stream);
 }
@@ -402,7 +712,24 @@ extern "C" int wsae_decode_backward_at(const float* const* target_at, const void
                                        const long long* step_count, float* d_b_enc, float* d_b_dec,
                                        float* dpre_val, cudaStream_t stream) {
   if (!target_at) return kBadArg;
-  return decode_backward_impl(nullptr, target_at, w_decT, w_is_bf16, b_dec, b_pre, idx, val,
+  return decode_backward_impl(nullptr, target_at, nullptr, w_decT, w_is_bf16, b_dec, b_pre, idx, val,
+                              grad_out, coef, B, d, F, k, resid, resid_bf16, stats, last_activated,
+                              step_count, d_b_enc, d_b_dec, dpre_val, stream);
+}
+
+// Slot form with a row-index indirection: target row of batch row r = (*target_at)[(*rows_at)[r], :]
+// (*rows_at == 0: identity).  See wsae_pack_activations_rows_at.
+extern "C" int wsae_decode_backward_rows_at(const float* const* target_at,
+                                            const long long* const* rows_at, const void* w_decT,
+                                            int w_is_bf16, const float* b_dec, const float* b_pre,
+                                            const int32_t* idx, const float* val,
+                                            const float* grad_out, float coef, int B, int d, int F,
+                                            int k, float* resid, void* resid_bf16, void* stats,
+                                            long long* last_activated, const long long* step_count,
+                                            float* d_b_enc, float* d_b_dec, float* dpre_val,
+                                            cudaStream_t stream) {
+  if (!target_at || !rows_at) return kBadArg;
+  return decode_backward_impl(nullptr, target_at, rows_at, w_decT, w_is_bf16, b_dec, b_pre, idx, val,
                               grad_out, coef, B, d, F, k, resid, resid_bf16, stats, last_activated,
                               step_count, d_b_enc, d_b_dec, dpre_val, stream);
 }

@@ -199,6 +199,10 @@ __device__ __forceinline__ void adamw_elem(float& pv, float g, float& mv, float&
   pv -= step_size * (mv / denom);
 }
 
+// KEEP = float4 per lane of a decoder row held in registers between the update and the renorm
+// (row_len <= 128 * KEEP); the launcher picks the smallest that fits: a 16-deep predicated loop costs
+// a d = 384 row more than it saves (0.022 -> 0.030 ms at 384 -> 3072 when it was the only form).
+template <int KEEP>
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const AdamwBatch batch, const float* __restrict__ hyper,
                    const double* __restrict__ grad_sumsq, float renorm_eps) {
@@ -247,7 +251,7 @@ adamw_multi_kernel(const AdamwBatch batch, const float* __restrict__ hyper,
       if (row < rows) {
         const long long base = row * T.row_len;
         const bool project = (T.pad_ & 1) != 0;
-        constexpr int kKeep = 16;                      // float4 per lane held in registers: row_len <= 2048
+        constexpr int kKeep = KEEP;
         const int nv = T.row_len >> 2;
         const bool vec = (T.row_len & 3) == 0 && nv <= 32 * kKeep &&
                          ((reinterpret_cast<uintptr_t>(T.p) | reinterpret_cast<uintptr_t>(T.g) |
@@ -356,7 +360,14 @@ extern "C" int wsae_adamw_multi(const wsae_adamw_tensor_host* tensors, int count
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long cap = static_cast<long long>(sms) * 16;
   const unsigned blocks = static_cast<unsigned>(units < cap ? units : cap);
-  launch_pdl(adamw_multi_kernel, blocks, 256, 0, stream, b, hyper, grad_sumsq, renorm_eps);
+  int max_row = 0;
+  for (int i = 0; i < count; ++i) max_row = tensors[i].row_len > max_row ? tensors[i].row_len : max_row;
+  if (max_row <= 512)
+    launch_pdl(adamw_multi_kernel<4>, blocks, 256, 0, stream, b, hyper, grad_sumsq, renorm_eps);
+  else if (max_row <= 1024)
+    launch_pdl(adamw_multi_kernel<8>, blocks, 256, 0, stream, b, hyper, grad_sumsq, renorm_eps);
+  else
+    launch_pdl(adamw_multi_kernel<16>, blocks, 256, 0, stream, b, hyper, grad_sumsq, renorm_eps);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -89,12 +89,16 @@ pack_rows_kernel(const float* __restrict__ src, const float* __restrict__ center
 // grid.  HBM bound: reads B*d*4, writes Bp*Kp*2 bytes.
 __global__ void __launch_bounds__(256)
 pack_activations_bf16_kernel(const float* __restrict__ x, const float* const* __restrict__ x_at,
+                             const long long* const* __restrict__ rows_at,
                              const float* __restrict__ center, int rows, int rows_p, int d, int Kp,
                              __nv_bfloat16* __restrict__ dst) {
   pdl_prologue();
   // x_at: the matrix's address is read from device memory (a captured graph replays on whichever
-  // batch the slot names - no staging copy of the batch into a graph-owned buffer)
+  // batch the slot names - no staging copy of the batch into a graph-owned buffer).  rows_at: slot
+  // with the address of an int64 row-index array (0 = identity): batch row r is matrix row
+  // (*rows_at)[r], so a shuffled batch of a resident activation matrix is never materialised.
   if (x_at != nullptr) x = *x_at;
+  const long long* perm = rows_at != nullptr ? *rows_at : nullptr;
   const int groups = Kp >> 3;
   const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= static_cast<size_t>(rows_p) * groups) return;
@@ -103,7 +107,8 @@ pack_activations_bf16_kernel(const float* __restrict__ x, const float* const* __
   uint4 out = make_uint4(0u, 0u, 0u, 0u);
   if (r < rows) {
     if (c0 < d) {
-      const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * d + c0);
+      const size_t sr = perm != nullptr ? static_cast<size_t>(__ldg(perm + r)) : static_cast<size_t>(r);
+      const float4* src = reinterpret_cast<const float4*>(x + sr * d + c0);
       float4 a = __ldcs(src), b = __ldcs(src + 1);        // streamed once: do not keep in L2/L1
       if (center != nullptr) {
         const float4 ca = __ldg(reinterpret_cast<const float4*>(center + c0));
@@ -154,7 +159,7 @@ extern "C" int wsae_packed_k(int d, int terms, int* dp_out, int* used_cols_out, 
 
 static int pack_common(int kind, const float* src, const float* center, const float* bias,
                        int rows, int rows_p, int d, int terms, void* dst, cudaStream_t stream,
-                       const float* const* src_at = nullptr) {
+                       const float* const* src_at = nullptr, const long long* const* rows_at = nullptr) {
   if ((!src && !src_at) || !dst || rows <= 0 || rows_p < rows) return kBadArg;
   int dp, used, Kp;
   if (wsae_packed_k(d, terms, &dp, &used, &Kp)) return kBadArg;
@@ -168,8 +173,8 @@ static int pack_common(int kind, const float* src, const float* center, const fl
                     (center == nullptr || (reinterpret_cast<uintptr_t>(center) & 15u) == 0);
   if (src_at != nullptr && !fast) return kUnsupported;   // the slot form exists for the bf16 path only
   if (fast)
-    launch_pdl(pack_activations_bf16_kernel, blocks, threads, 0, stream, src, src_at, center, rows,
-               rows_p, d, Kp, static_cast<__nv_bfloat16*>(dst));
+    launch_pdl(pack_activations_bf16_kernel, blocks, threads, 0, stream, src, src_at, rows_at, center,
+               rows, rows_p, d, Kp, static_cast<__nv_bfloat16*>(dst));
   else if (kind == 0)
     launch_pdl(pack_rows_kernel<0>, blocks, threads, 0, stream, src, center, bias, rows, rows_p, d,
                dp, terms, Kp, s, static_cast<__nv_bfloat16*>(dst));
@@ -190,6 +195,15 @@ extern "C" int wsae_pack_activations_at(const float* const* x_at, const float* b
                                         int d, int terms, void* a_packed, cudaStream_t stream) {
   if (!x_at) return kBadArg;
   return pack_common(0, nullptr, b_pre, nullptr, B, Bp, d, terms, a_packed, stream, x_at);
+}
+
+// Slot form with a row-index indirection: batch row r = (*x_at)[(*rows_at)[r], :]; *rows_at == 0 means
+// identity.  (reference: the DataLoader's shuffled TensorDataset batch, data/feature_cache.py:169-197.)
+extern "C" int wsae_pack_activations_rows_at(const float* const* x_at, const long long* const* rows_at,
+                                             const float* b_pre, int B, int Bp, int d, int terms,
+                                             void* a_packed, cudaStream_t stream) {
+  if (!x_at || !rows_at) return kBadArg;
+  return pack_common(0, nullptr, b_pre, nullptr, B, Bp, d, terms, a_packed, stream, x_at, rows_at);
 }
 
 extern "C" int wsae_pack_encoder(const float* w_enc, const float* b_enc, int F, int Fp, int d,

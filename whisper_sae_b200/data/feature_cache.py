@@ -58,15 +58,65 @@ class CacheMetadata:
         return cls(**json.loads(json_str))
 
 
+class IndexedBatch:
+    """A batch named by reference: rows ``rows`` (int64, device) of the resident ``features`` matrix.
+
+    What the reference's ``DataLoader(TensorDataset(features), shuffle=True)`` materialises per step
+    (feature_cache.py:169-197) - here the graphed train step reads the rows where they lie (K0 and
+    K23 take the matrix address and the index array from device slots: ``wsae_pack_activations_rows_at``,
+    ``wsae_decode_backward_rows_at``), so a shuffled epoch costs no gather pass (233 MB of HBM traffic
+    per 75 776-row batch at d = 384).  ``materialize()`` gives the plain tensor for every other consumer.
+    """
+
+    __slots__ = ("features", "rows")
+
+    def __init__(self, features: Tensor, rows: Tensor):
+        if features.dim() != 2 or rows.dim() != 1 or rows.dtype != torch.int64:
+            raise ValueError("IndexedBatch needs a [N, d] matrix and a 1-d int64 row-index tensor")
+        self.features = features
+        self.rows = rows
+
+    @property
+    def shape(self) -> torch.Size:
+        return torch.Size((self.rows.shape[0], self.features.shape[1]))
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.features.dtype
+
+    @property
+    def device(self) -> torch.device:
+        return self.features.device
+
+    @property
+    def is_cuda(self) -> bool:
+        return self.features.is_cuda
+
+    def dim(self) -> int:
+        return 2
+
+    def __len__(self) -> int:
+        return self.rows.shape[0]
+
+    def materialize(self) -> Tensor:
+        return self.features.index_select(0, self.rows)
+
+    def to(self, *args, **kwargs) -> Tensor:
+        return self.materialize().to(*args, **kwargs)
+
+
 class ResidentBatches:
-    """Batches cut from a resident [N, d] matrix by a device-side permutation each epoch."""
+    """Batches cut from a resident [N, d] matrix by a device-side permutation each epoch.  On a CUDA
+    device a shuffled batch is an :class:`IndexedBatch` (matrix + slice of the permutation): the train
+    step gathers the rows inside its own kernels instead of an ``index_select`` pass per batch."""
 
     def __init__(self, features: Tensor, batch_size: int, shuffle: bool, device: torch.device | str,
-                 drop_last: bool = False, seed: int | None = None):
+                 drop_last: bool = False, seed: int | None = None, indexed: bool | None = None):
         self.features = features.to(device)
         self.batch_size = batch_size
         self.shuffle = shuffle
         self.drop_last = drop_last
+        self.indexed = self.features.is_cuda if indexed is None else bool(indexed)
         self._gen = torch.Generator(device=self.features.device)
         if seed is not None:
             self._gen.manual_seed(seed)
@@ -75,13 +125,18 @@ class ResidentBatches:
         n = self.features.shape[0]
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
-    def __iter__(self) -> Iterator[list[Tensor]]:
+    def __iter__(self) -> Iterator[list]:
         n = self.features.shape[0]
         order = (torch.randperm(n, device=self.features.device, generator=self._gen)
                  if self.shuffle else None)
         for i in range(len(self)):
             lo, hi = i * self.batch_size, min(n, (i + 1) * self.batch_size)
-            rows = self.features[lo:hi] if order is None else self.features.index_select(0, order[lo:hi])
+            if order is None:
+                rows = self.features[lo:hi]
+            elif self.indexed:
+                rows = IndexedBatch(self.features, order[lo:hi])
+            else:
+                rows = self.features.index_select(0, order[lo:hi])
             yield [rows]  # same 1-element list a TensorDataset loader yields
 
 

@@ -116,13 +116,25 @@ def pack_activations(x: Tensor, b_pre: Tensor | None, terms: int, out: Tensor | 
 
 
 def pack_activations_at(x_at: Tensor, B: int, d: int, b_pre: Tensor | None,
-                        out: Tensor | None = None) -> Tensor:
+                        out: Tensor | None = None, rows_at: Tensor | None = None) -> Tensor:
     """``pack_activations`` (bf16, one term) of the ``[B, d]`` fp32 matrix whose device address the
-    int64 slot ``x_at`` holds WHEN THE KERNEL RUNS (graph replay on batches in place)."""
-    _need_cuda(x_at, b_pre)
+    int64 slot ``x_at`` holds WHEN THE KERNEL RUNS (graph replay on batches in place).  ``rows_at``:
+    a second int64 slot holding the address of an int64 row-index array (0 = identity): batch row r is
+    row ``rows[r]`` of the matrix (shuffled batches of a resident matrix, never materialised)."""
+    _need_cuda(x_at, b_pre, rows_at)
     _f32c(b_pre, "b_pre")
     if x_at.dtype != torch.int64 or x_at.numel() != 1:
         raise RuntimeError("x_at must be a one-element int64 CUDA tensor holding a device address")
+    if rows_at is not None:
+        if rows_at.dtype != torch.int64 or rows_at.numel() != 1:
+            raise RuntimeError("rows_at must be a one-element int64 CUDA tensor holding a device address")
+        ps = packed_shape(d, 1)
+        Bp = _round_up(B, 128)
+        if out is None or out.shape != (Bp, ps.kp):
+            out = torch.empty((Bp, ps.kp), dtype=torch.bfloat16, device=x_at.device)
+        lib = _lib.load()
+        _run("wsae_pack_activations", lib.wsae_pack_activations_rows_at, _ptr(x_at), _ptr(rows_at), _ptr(b_pre), B, Bp, d, 1, _ptr(out), _stream())
+        return out
     ps = packed_shape(d, 1)
     Bp = _round_up(B, 128)
     if out is None or out.shape != (Bp, ps.kp):
@@ -246,7 +258,7 @@ def decode_backward(target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: Tensor
                     resid: Tensor | None, resid_bf16: Tensor | None, stats: Tensor | None,
                     last_activated: Tensor | None, step_count: Tensor | None,
                     d_b_enc: Tensor | None, d_b_dec: Tensor | None, dpre_val: Tensor | None,
-                    target_is_slot: bool = False) -> None:
+                    target_is_slot: bool = False, rows_at: Tensor | None = None) -> None:
     """K23: sparse decode + MSE + L0 + fired stamps + dv / bias gradients in one pass.
     ``target_is_slot``: ``target`` is a one-element int64 tensor holding the device address of the
     ``[B, d]`` fp32 target, read when the kernel runs (see ``pack_activations_at``)."""
@@ -259,6 +271,11 @@ def decode_backward(target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: Tensor
         if not w_decT.is_contiguous() or w_decT.dtype != torch.bfloat16:
             raise RuntimeError("w_decT must be contiguous [F, d] bfloat16")
         lib = _lib.load()
+        if rows_at is not None:
+            if rows_at.dtype != torch.int64 or rows_at.numel() != 1 or not rows_at.is_cuda:
+                raise RuntimeError("rows_at must be a one-element int64 CUDA tensor holding a device address")
+            _run("wsae_decode_backward", lib.wsae_decode_backward_rows_at, _ptr(target), _ptr(rows_at), _ptr(w_decT), 1, _ptr(b_dec), _ptr(b_pre), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(resid), _ptr(resid_bf16), _ptr(stats), _ptr(last_activated), _ptr(step_count), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _stream())
+            return
         _run("wsae_decode_backward", lib.wsae_decode_backward_at, _ptr(target), _ptr(w_decT), 1, _ptr(b_dec), _ptr(b_pre), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(resid), _ptr(resid_bf16), _ptr(stats), _ptr(last_activated), _ptr(step_count), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _stream())
         return
     _f32c(target, "target")

@@ -34,6 +34,7 @@ from torch.utils.data import DataLoader
 
 from .. import ops
 from ..config import TrainingConfig
+from ..data.feature_cache import IndexedBatch
 from .model import SAEOutput, TopKSAE, _fp32_terms, _SparseState
 
 
@@ -82,13 +83,13 @@ class _GraphedStep:
         self.trainer = trainer
         self.rows = rows
         self.bf16 = bool(trainer.use_amp)
-        # per-step control block, ONE 48-byte H2D copy from pinned memory before every replay:
-        # [hyper f32[8] | x_slot i64 | seq i64].  x_slot holds the device address of the step's batch:
+        # per-step control block, ONE 64-byte H2D copy from pinned memory before every replay:
+        # [hyper f32[8] | x_slot i64 | seq i64 | rows_slot i64 | pad].  x_slot holds the device address of the step's batch:
         # the kernels that read the activations (K0 pack, K23 target) take it from there when they
         # RUN, so the captured graph trains on a device-resident batch in place; only batches that
         # arrive on the host (or misaligned / non-contiguous) are staged into `x`.
-        self.ctl = torch.zeros(48, dtype=torch.uint8, device=dev)
-        self.ctl_host = torch.zeros(48, dtype=torch.uint8).pin_memory()
+        self.ctl = torch.zeros(64, dtype=torch.uint8, device=dev)
+        self.ctl_host = torch.zeros(64, dtype=torch.uint8).pin_memory()
         self.hyper = self.ctl[:32].view(torch.float32)
         self.hyper_host = self.ctl_host[:32].view(torch.float32)
         self.x_slot = self.ctl[32:40].view(torch.int64)
@@ -98,6 +99,10 @@ class _GraphedStep:
         # of synchronising with the stream (the reference's five `.item()` calls, training.py:206-214)
         self.seq_dev = self.ctl[40:48].view(torch.int64)
         self.seq_host = self.ctl_host[40:48].view(torch.int64)
+        # rows_slot: address of an int64 row-index array (0 = identity): an IndexedBatch of a resident
+        # activation matrix is gathered INSIDE K0 / K23 (wsae_*_rows_at), never materialised
+        self.rows_slot = self.ctl[48:56].view(torch.int64)
+        self.rows_slot_np = self.ctl_host[48:56].view(torch.int64).numpy()
         self.mailbox = torch.zeros(4, dtype=torch.int64).pin_memory()
         self.mailbox_np = self.mailbox.numpy()
         self.seq = 0
@@ -213,7 +218,7 @@ class _GraphedStep:
                     m.encoder.weight.data, m.encoder.bias.data, terms, out=self._w_packed_buf)
                 w_used = ops.cast_bf16(w_decT, out=self._w_used_buf)
         if self.in_place:
-            a_packed = ops.pack_activations_at(self.x_slot, B, d, m.b_pre.data)
+            a_packed = ops.pack_activations_at(self.x_slot, B, d, m.b_pre.data, rows_at=self.rows_slot)
         else:
             a_packed = ops.pack_activations(x, m.b_pre.data, terms)
         if self.fork:
@@ -236,7 +241,8 @@ class _GraphedStep:
                                 resid=None, resid_bf16=resid_bf, stats=self.stats,
                                 last_activated=m.feature_last_activated, step_count=m.step_count,
                                 d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre,
-                                target_is_slot=self.in_place)
+                                target_is_slot=self.in_place,
+                                rows_at=self.rows_slot if self.in_place else None)
         else:
             resid, _ = ops.decode_mse(x, w_used, m.decoder.bias.data, m.b_pre.data, idx, val,
                                       stats=self.stats, last_activated=m.feature_last_activated,
@@ -321,7 +327,19 @@ class _GraphedStep:
         pointer check) is issued before the replay; the optimizer's ``step`` tensors and the grad
         views are updated while the kernels run (matters at the launch-bound YAML batch sizes)."""
         tr = self.trainer
-        if (self.in_place and batch.is_cuda and batch.device == self.ctl.device
+        rows_ptr = 0
+        if isinstance(batch, IndexedBatch):
+            f, r = batch.features, batch.rows
+            if (self.in_place and f.is_cuda and f.device == self.ctl.device and f.dtype == torch.float32
+                    and f.is_contiguous() and f.data_ptr() % 16 == 0 and r.is_cuda and r.is_contiguous()
+                    and r.device == f.device):
+                src, rows_ptr = f, r.data_ptr()      # rows gathered inside K0 / K23
+                self._live_rows = r
+            else:
+                batch = batch.materialize()
+        if rows_ptr:
+            pass
+        elif (self.in_place and batch.is_cuda and batch.device == self.ctl.device
                 and batch.dtype == torch.float32 and batch.is_contiguous()
                 and batch.data_ptr() % 16 == 0):
             src = batch                      # trained on where it lies
@@ -330,6 +348,7 @@ class _GraphedStep:
             src = self.x
         self._live = src                     # the caller may drop its reference before the replay runs
         self.x_slot_np[0] = src.data_ptr()
+        self.rows_slot_np[0] = rows_ptr
         self.seq += 1
         self.seq_np[0] = self.seq
         group = tr.optimizer.param_groups[0]
@@ -574,6 +593,8 @@ class SAETrainer:
         self.model.train()
         if isinstance(batch, (tuple, list)):
             batch = batch[0]
+        if isinstance(batch, IndexedBatch) and not self._graph_ok(batch):
+            batch = batch.materialize()      # only the graphed step gathers rows inside its kernels
         if self.data_parallel:
             if not self._graph_ok(batch):
                 raise RuntimeError("data_parallel=True supports the fused TopKSAE step only")
