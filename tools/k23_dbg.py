@@ -1,8 +1,9 @@
-import os, sys, subprocess
+import sys
 from pathlib import Path
-root = Path(__file__).resolve().parent.parent
-for st in ("2", "3"):
-    env = dict(os.environ, WSAE_K23_STAGES=st)
-    out = subprocess.run([sys.executable, str(root / "tools" / "bench_k23.py"), "--shapes", "75776x384x3072,75776x768x6144,37888x1280x40960"],
-                         env=env, capture_output=True, text=True)
-    print(f"--- WSAE_K23_STAGES={st}\n{out.stdout}{out.stderr[-500:]}", flush=True)
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import tools.bench_k23 as K
+K.ALL_FIRED = True
+for shape in ((75776, 384, 3072), (75776, 768, 6144), (37888, 1280, 40960)):
+    for mode in (1, 2, 3, 0):
+        t, m, _ = K.run(*shape, 32, mode, reps=8)
+        print(f"all fired {shape}, mode={mode}: {t*1e3:.1f} us (min {m*1e3:.1f})", flush=True)

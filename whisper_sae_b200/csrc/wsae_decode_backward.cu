@@ -105,7 +105,7 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
                        const long long* __restrict__ step_count, float* __restrict__ d_b_enc,
                        float* __restrict__ d_b_dec, float* __restrict__ dpre_val,
                        const float* const* __restrict__ target_at,
-                       const long long* const* __restrict__ rows_at) {
+                       const long long* const* __restrict__ rows_at, int stamp_words) {
   extern __shared__ __align__(16) float fsm[];   // [dp] bias (b_dec + b_pre), then one [dp] db_dec accumulator per warp
   pdl_prologue();
   if (target_at != nullptr) target = *target_at;   // address from a device-resident slot (graph replay)
@@ -117,6 +117,11 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
   float* s_bias = fsm;
   float* s_g = fsm + dp + warp * dp;       // warp-private: plain read-modify-write, no atomics
   float* s_dot = fsm + (1 + kFusedWarps) * dp;   // fast path: per-warp scratch of the dot-product reduction
+  // fired-feature bitmap of this block (stamp_words = ceil(F / 32), 0 = stamp straight to global memory):
+  // 2.4 M scattered 8-byte stamp stores per launch, issued next to as many RED.ADDs on d_b_enc, cost the
+  // staged kernel 78 us of 301 (tools/k23_dbg.py); one coalesced pass per block writes them instead
+  uint32_t* s_fired = reinterpret_cast<uint32_t*>(s_dot + kFusedWarps * kDotScratch);
+  for (int i = threadIdx.x; i < stamp_words; i += blockDim.x) s_fired[i] = 0u;
   for (int i = threadIdx.x; i < dp; i += blockDim.x) {
     float b = 0.f;
     if (i < d) b = b_dec[i] + (b_pre != nullptr ? b_pre[i] : 0.f);
@@ -144,7 +149,10 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
       my_v = val[static_cast<size_t>(row) * k + lane];
     }
     const bool fired = (my_i >= 0) && (my_i < F) && (my_v > 0.f);
-    if (fired && last_activated != nullptr) last_activated[my_i] = stamp;
+    if (fired && last_activated != nullptr) {
+      if (stamp_words > 0) atomicOr(&s_fired[my_i >> 5], 1u << (my_i & 31));
+      else last_activated[my_i] = stamp;
+    }
     if (!fired) my_v = 0.f;                         // relu; also neutralises invalid entries
     // bf16 mode: the decoder product is bf16 x bf16 with fp32 accumulation - the activation enters
     // in bf16 like the weight shadow (the reference's autocast decoder Linear rounds `hidden` to
@@ -309,6 +317,9 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
     s_l0[warp] = l0_local;
   }
   __syncthreads();
+  if (stamp_words > 0 && last_activated != nullptr)
+    for (int f = threadIdx.x; f < F; f += blockDim.x)
+      if ((s_fired[f >> 5] >> (f & 31)) & 1u) last_activated[f] = stamp;
   if (d_b_dec != nullptr)
     for (int i = threadIdx.x; i < d; i += blockDim.x) {
       float t = 0.f;
@@ -366,8 +377,8 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
                               const long long* __restrict__ step_count, float* __restrict__ d_b_enc,
                               float* __restrict__ d_b_dec, float* __restrict__ dpre_val,
                               const float* const* __restrict__ target_at,
-                              const long long* const* __restrict__ rows_at, int dbg) {
-  extern __shared__ __align__(16) float fsm[];   // [d] bias, [warps][d] db_dec partials, then the slice rings
+                              const long long* const* __restrict__ rows_at, int stamp_words, int dbg) {
+  extern __shared__ __align__(16) float fsm[];   // [d] bias, [warps][d] db_dec partials, the slice rings, the fired bitmap
   pdl_prologue();
   if (target_at != nullptr) target = *target_at;
   const long long* perm = rows_at != nullptr ? *rows_at : nullptr;
@@ -376,6 +387,9 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
   float* s_bias = fsm;
   float* s_g = fsm + d + warp * d;
   const uint32_t ring = smem_u32(fsm + (1 + kFusedWarps) * d) + warp * (STAGES * kSliceBytes);
+  uint32_t* s_fired = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(fsm + (1 + kFusedWarps) * d) +
+                                                  kFusedWarps * STAGES * kSliceBytes);
+  for (int i = threadIdx.x; i < stamp_words; i += blockDim.x) s_fired[i] = 0u;
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     s_bias[i] = b_dec[i] + (b_pre != nullptr ? b_pre[i] : 0.f);
 #pragma unroll
@@ -449,7 +463,10 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
   for (; row < B; row += warp_stride) {
     const bool fired = cur_f;
     const int32_t my_i = cur_i;
-    if (fired && last_activated != nullptr && !(dbg & 4)) last_activated[my_i] = stamp;
+    if (fired && last_activated != nullptr && !(dbg & 4)) {
+      if (stamp_words > 0) atomicOr(&s_fired[my_i >> 5], 1u << (my_i & 31));
+      else last_activated[my_i] = stamp;
+    }
     const float my_v = fired ? cur_v : 0.f;
     const uint32_t my_hb = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(my_v)));
     const uint32_t mask = __ballot_sync(0xffffffffu, fired);
@@ -558,6 +575,9 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
     s_l0[warp] = l0_local;
   }
   __syncthreads();
+  if (stamp_words > 0 && last_activated != nullptr)
+    for (int f = threadIdx.x; f < F; f += blockDim.x)
+      if ((s_fired[f >> 5] >> (f & 31)) & 1u) last_activated[f] = stamp;
   if (d_b_dec != nullptr)
     for (int i = threadIdx.x; i < d; i += blockDim.x) {
       float t = 0.f;
@@ -603,12 +623,14 @@ static int decode_backward_impl(const float* target, const float* const* target_
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const bool fast_shape = (d % 128 == 0) && ((g_decode_backward_general & 0xff) == 2 || (g_decode_backward_general & 0xff) == 0);
+  const bool fast_shape = (d % 128 == 0) && ((g_decode_backward_general & 0xff) == 2 || ((g_decode_backward_general & 0xff) == 0 && d <= 1024));
   const int per_sm = fast_shape ? 3 : 4;
   int blocks = ceil_div(B, kFusedWarps);
   if (blocks > sms * per_sm) blocks = sms * per_sm;
+  // fired bitmap in shared memory (F <= 65536: 8 KB), else stamps go straight to global memory
+  const int stamp_words = (last_activated != nullptr && F <= 65536) ? ceil_div(F, 32) : 0;
   const size_t smem = ((1 + kFusedWarps) * static_cast<size_t>(round_up(d, 128)) + kFusedWarps * kDotScratch) *
-                      sizeof(float);
+                          sizeof(float) + static_cast<size_t>(stamp_words) * 4;
   if (smem > 48 * 1024) {      // d > 2432: opt in to the large dynamic shared-memory carve-out (once per device)
     static bool attr_set[64] = {};
     if (dev >= 64 || !attr_set[dev]) {
@@ -629,16 +651,18 @@ static int decode_backward_impl(const float* target, const float* const* target_
   const int mode = g_decode_backward_general & 0xff;
   const int dbg = g_decode_backward_general >> 8;
   // Kernel choice (tools/bench_k23.py, same box, B = 75776 / 37888, k = 32):
-  //   d = 384:  staged 213 us | mma 232 us | general 239 us   -> staged where THREE blocks fit an SM
-  //   d = 768:  staged 490 us | mma 411 us | general 430 us   -> mma (the ring leaves room for 8 warps only)
-  //   d = 1280: staged 387 us | mma 352 us | general 367 us   -> mma
+  // every selected value positive, as K1 hands them over in training (profiles/r2_k23_variants.txt):
+  //   d = 384:  staged 226 us | mma 256 us | general 259 us   -> staged where THREE blocks fit an SM
+  //   d = 768:  staged 541 us | mma 451 us | general 461 us   -> mma (the ring leaves room for 8 warps only)
+  //   d = 1280: staged 434 us | mma 451 us | general 444 us   -> general (F = 40960: decoder > L2 share)
   //   d % 128 != 0: general
   // mode (wsae_debug_decode_backward_general): 0 = this choice, 1 = general, 2 = mma, 3 = staged
   const bool staged_fits3 =
-      3 * ((1 + kFusedWarps) * static_cast<size_t>(d) * sizeof(float) + kFusedWarps * 2 * kSliceBytes + 1024) <= 227 * 1024;
+      3 * ((1 + kFusedWarps) * static_cast<size_t>(d) * sizeof(float) + kFusedWarps * 2 * kSliceBytes +
+           static_cast<size_t>(stamp_words) * 4 + 1024) <= 227 * 1024;
   if (((mode == 0 && staged_fits3) || mode == 3) && d % 128 == 0 &&
       static_cast<long long>(F) * d * 2 <= 0xffffffffLL) {
-    const size_t base = (1 + kFusedWarps) * static_cast<size_t>(d) * sizeof(float);
+    const size_t base = (1 + kFusedWarps) * static_cast<size_t>(d) * sizeof(float) + static_cast<size_t>(stamp_words) * 4;
     // ring depth 2 leaves room for three resident blocks (12 warps per SM) at d = 384: measured
     // faster than depth 3 with two blocks (tools/bench_k23.py); WSAE_K23_STAGES overrides
     static const int want_stages = [] {
@@ -667,25 +691,25 @@ static int decode_backward_impl(const float* target, const float* const* target_
       if (stages == 3)
         launch_pdl(decode_backward_staged_kernel<3>, nblk, kFusedWarps * 32, smem_s, stream, target, wd, b_dec,
                    b_pre, idx, val, grad_out, coef, B, d, F, k, resid, rbf, st, last_activated, step_count,
-                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, dbg);
+                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, dbg);
       else
         launch_pdl(decode_backward_staged_kernel<2>, nblk, kFusedWarps * 32, smem_s, stream, target, wd, b_dec,
                    b_pre, idx, val, grad_out, coef, B, d, F, k, resid, rbf, st, last_activated, step_count,
-                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, dbg);
+                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, dbg);
       return static_cast<int>(cudaGetLastError());
     }
   }
-  const bool fast = (d % 128 == 0) && (mode == 2 || mode == 0);
+  const bool fast = (d % 128 == 0) && (mode == 2 || (mode == 0 && d <= 1024));
   if (fast)
     launch_pdl(decode_backward_kernel<true>, blocks, kFusedWarps * 32, smem, stream, target,
                static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
                F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
-               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at);
+               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words);
   else
     launch_pdl(decode_backward_kernel<false>, blocks, kFusedWarps * 32, smem, stream, target,
                static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
                F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
-               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at);
+               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words);
   return static_cast<int>(cudaGetLastError());
 }
 

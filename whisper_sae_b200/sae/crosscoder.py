@@ -16,7 +16,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import ops
-from .model import _FusedTopKSAE, _LazyOutput, _SparseState, _fp32_terms
+from .model import _FusedTopKSAE, _LazyOutput, _SparseState, _fp32_terms, _warn_encode_detached
 
 
 class CrosscoderOutput(_LazyOutput):
@@ -162,6 +162,8 @@ class TopKCrossLayerCrosscoder(CrossLayerCrosscoder):
 
     def encode(self, layer_activations: dict[int, Tensor]) -> Tensor:
         x = self._concat(layer_activations).contiguous()
+        if torch.is_grad_enabled() and (x.requires_grad or self.W_enc.requires_grad):
+            _warn_encode_detached()       # no grad_fn on the result (see TopKSAE.encode)
         terms = 1 if self._use_bf16() else _fp32_terms()
         a = ops.pack_activations(x, None, terms)
         w = ops.pack_encoder(self._w_enc_cat().detach().contiguous(), self.b_enc.detach(), terms)

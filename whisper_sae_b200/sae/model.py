@@ -87,6 +87,19 @@ class SAEOutput(_LazyOutput):
     __slots__ = ()
 
 
+_ENCODE_WARNED = False
+
+
+def _warn_encode_detached() -> None:
+    global _ENCODE_WARNED
+    if not _ENCODE_WARNED:
+        _ENCODE_WARNED = True
+        import warnings
+        warnings.warn("whisper_sae_b200: encode() returns a tensor without grad_fn (the reference's encode() is "
+                      "differentiable); use forward() / output.loss for training, or wrap the call in "
+                      "torch.no_grad() to silence this", stacklevel=3)
+
+
 def _fp32_terms() -> int:
     t = int(os.environ.get("WSAE_FP32_TERMS", "6"))
     if t not in (3, 6):
@@ -296,8 +309,12 @@ class TopKSAE(nn.Module):
         return ops.encode_topk(a, w, x.shape[0], self.hidden_dim, self.input_dim, terms, self.k)
 
     def encode(self, x: Tensor) -> Tensor:
-        """Dense [batch, hidden_dim] TopK activations (model.py:98-118). Not differentiable."""
+        """Dense [batch, hidden_dim] TopK activations (model.py:98-118).  NOT differentiable (the
+        reference's is): the result carries no grad_fn, so a loss built on ``decode(encode(x))`` would
+        train the decoder only - a warning says so once; ``forward`` is the differentiable path."""
         x = self._check_input(x)
+        if torch.is_grad_enabled() and (x.requires_grad or self.encoder.weight.requires_grad):
+            _warn_encode_detached()
         idx, val = self._sparse_encode(x)
         return ops.densify_hidden(idx, val, self.hidden_dim)
 

@@ -81,6 +81,11 @@ class TorchDistCommunicator:
         after it.  Lets the gradient exchange of one weight matrix overlap the GEMM of the next."""
         return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
+    def broadcast(self, t: Tensor, src: int = 0) -> Tensor:
+        """In place: every rank ends up with rank ``src``'s ``t``."""
+        dist.broadcast(t, src=src, group=self.group)
+        return t
+
     def reduce_step(self, grads: Tensor | list[Tensor], stats: Tensor, last_activated: Tensor | None) -> None:
         parts = grads if isinstance(grads, (list, tuple)) else [grads]
         for g in parts[:-1]:
@@ -120,6 +125,12 @@ class ThreadCommunicator:
         if any(t.is_cuda for t in tensors):
             torch.cuda.synchronize()
         sh.barrier.wait()
+
+    def broadcast(self, t: Tensor, src: int = 0) -> Tensor:
+        def combine(all_parts):
+            t.copy_(all_parts[src][0])
+        self._exchange([t], combine)
+        return t
 
     def all_reduce_sum_async(self, t: Tensor):
         def combine(all_parts):

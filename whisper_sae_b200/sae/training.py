@@ -531,7 +531,16 @@ class SAETrainer:
             rows = [self._resample_dataset[int(i)] for i in picks]
             rows = [r[0] if isinstance(r, tuple) else r for r in rows]
             batch = torch.stack(rows)
-        n = self.model.resample_dead_features(batch.to(self.device))
+        batch = batch.to(self.device)
+        if self.data_parallel:
+            # replicas stay bit-identical only if every rank rewrites the same rows: rank 0's pick (its
+            # RNG, its dataset shard) is broadcast; the resample forward itself is deterministic
+            want = torch.tensor([batch.shape[0]], dtype=torch.int64, device=batch.device)
+            self.dp_comm.broadcast(want)
+            if batch.shape[0] != int(want):
+                batch = torch.empty((int(want), batch.shape[1]), dtype=batch.dtype, device=batch.device)
+            batch = self.dp_comm.broadcast(batch.contiguous())
+        n = self.model.resample_dead_features(batch)
         self.num_resampled_total += n
         if n > 0 and self.wandb_run is not None:
             self.wandb_run.log({"train/features_resampled": n}, step=self.global_step)

@@ -16,7 +16,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import ops
-from .model import _feature_major_, _FusedTopKSAE, _LazyOutput, _SparseState, _fp32_terms
+from .model import _feature_major_, _FusedTopKSAE, _LazyOutput, _SparseState, _fp32_terms, _warn_encode_detached
 
 
 class TranscoderOutput(_LazyOutput):
@@ -78,6 +78,8 @@ class _TranscoderBase(nn.Module):
     def encode(self, x: Tensor) -> Tensor:
         """Dense [batch, hidden_dim] TopK activations (transcoder.py:102-118). Not differentiable."""
         x = self._check(x, self.input_dim, "mlp_input")
+        if torch.is_grad_enabled() and (x.requires_grad or self.encoder.weight.requires_grad):
+            _warn_encode_detached()       # no grad_fn on the result (see TopKSAE.encode)
         terms = 1 if self._use_bf16() else _fp32_terms()
         x32 = x.detach().to(torch.float32).contiguous()
         a = ops.pack_activations(x32, None, terms)
