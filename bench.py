@@ -225,7 +225,7 @@ def bind_to_gpu_numa_node(local_rank: int) -> dict:
 
 
 def make_trainer(wl: dict, batch: int, device: str, layer_seed: int, use_amp: bool = True, cuda_graph=None,
-                 data_parallel: bool = False, global_rows: int | None = None):
+                 data_parallel: bool = False, global_rows: int | None = None, deterministic: bool = False):
     from whisper_sae_b200.config import ExperimentConfig
     from whisper_sae_b200.sae import SAETrainer, create_sae
 
@@ -238,7 +238,7 @@ def make_trainer(wl: dict, batch: int, device: str, layer_seed: int, use_amp: bo
     sae = create_sae(cfg.sae, wl["d"])
     run_dir = Path(tempfile.mkdtemp(prefix="wsae_bench_"))
     tr = SAETrainer(sae, cfg.training, device=device, run_dir=run_dir, cuda_graph=cuda_graph,
-                    data_parallel=data_parallel, global_batch_rows=global_rows)
+                    data_parallel=data_parallel, global_batch_rows=global_rows, deterministic=deterministic)
     tr.setup_scheduler(100_000)
     return tr, cfg
 
@@ -692,6 +692,15 @@ def main() -> None:
         small = [small_rows[i * cfg_batch:(i + 1) * cfg_batch].contiguous() for i in range(16)]
         blk_s, _ = time_blocks(step_runner(tr_small, small), 100, 10, 5, False)
         del tr_small
+        det_info = None
+        if bf16:      # the bit-reproducible accumulation mode, for the record (SAETrainer(deterministic=True))
+            tr_det, _ = make_trainer(wl, args.batch, dev, layer_seed=rank, deterministic=True)
+            blk_d, _ = time_blocks(step_runner(tr_det, dev_batches), args.steps, 3, 5, False)
+            det_info = {"ms_per_step": 1e3 * blk_d["median"] / args.steps,
+                        "value": args.batch * args.steps / blk_d["median"], "unit": UNIT,
+                        "note": "ordered split-K / fixed-point cross-row sums instead of float atomics; "
+                                "bit-identical from run to run (tests/test_gpu_fullsize.py)"}
+            del tr_det
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
@@ -715,6 +724,7 @@ def main() -> None:
             "kernel_avg_ms": {n: e["avg_ms"] for n, e in table.items()},
             "yaml_batch": {"batch_rows": cfg_batch, "value": cfg_batch * 100 / blk_s["median"], "unit": UNIT,
                            "ms_per_step": 1e3 * blk_s["median"] / 100},
+            "deterministic_mode": det_info,
         }
     del tr, dev_batches, host_batches, rows
     torch.cuda.empty_cache()

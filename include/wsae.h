@@ -251,6 +251,38 @@ int wsae_layernorm_rows(const void* x, int in_dtype, long long rows, int d, long
                         const float* gamma /*nullable*/, const float* beta /*nullable*/, float eps,
                         float* out, long long out_pitch_elems, wsae_stream_t stream);
 
+/* ---- deterministic accumulation mode (SAETrainer(..., deterministic=True)) ----------------------
+ * The default kernels add their cross-row / split-K partial sums with float atomics in arrival
+ * order, so two runs of the same step differ in the last bits.  These forms are bit-reproducible:
+ *   wsae_decode_backward_det : K23 with db_enc / db_dec / SSE accumulated as fixed-point int64 in
+ *       det_ws [F + d + 1] (caller-zeroed; addends are the unscaled dot products, |.| < 2^10);
+ *       wsae_det_finish converts: d_b_enc += s*sum, d_b_dec += s*sum, stats.sse += sum,
+ *       s = coef * (*grad_out).  target (direct) or target_at (slot) names the matrix; rows_at nullable.
+ *   wsae_wgrad_gemm_det      : K4 with one partial slab per k split in ws (wsae_wgrad_gemm_workspace
+ *       bytes; 0 = no split) and an ordered reduction instead of red.global.add.
+ *   wsae_sumsq_det           : per-block partials in ws (wsae_sumsq_det_blocks() doubles), ordered sum.
+ *   wsae_bpre_grad_det       : per-256-feature partial rows in ws (ceil(F/256)*d floats), ordered sum. */
+int wsae_decode_backward_det(const float* target /*nullable*/, const float* const* target_at /*nullable*/,
+                             const long long* const* rows_at /*nullable*/, const void* w_decT,
+                             int w_is_bf16, const float* b_dec, const float* b_pre /*nullable*/,
+                             const int32_t* idx, const float* val, const float* grad_out /*nullable*/,
+                             float coef, int B, int d, int F, int k, float* resid, void* resid_bf16,
+                             void* stats, long long* last_activated, const long long* step_count,
+                             float* d_b_enc, float* d_b_dec, float* dpre_val, long long* det_ws,
+                             wsae_stream_t stream);
+int wsae_det_finish(const long long* det_ws, int F, int d, const float* grad_out /*nullable*/, float coef,
+                    float* d_b_enc /*nullable*/, float* d_b_dec /*nullable*/, void* stats /*nullable*/,
+                    wsae_stream_t stream);
+int wsae_wgrad_gemm_workspace(int B, int F, int d, unsigned long long* bytes);
+int wsae_wgrad_gemm_det(const void* r_bf16, int r_pitch_elems, int B, int F, int d, const int* offsets,
+                        const uint32_t* ent_meta, const float* ent_val, const float* grad_out /*nullable*/,
+                        float alpha, float* out /*[F,d]*/, float* ws, unsigned long long ws_bytes,
+                        wsae_stream_t stream);
+int wsae_sumsq_det_blocks(void);
+int wsae_sumsq_det(const float* g, long long n, double* ws, double* out, wsae_stream_t stream);
+int wsae_bpre_grad_det(const float* d_b_dec, const float* d_b_enc, const float* w_enc, int F, int d,
+                       float* d_b_pre, float* ws, wsae_stream_t stream);
+
 /* ---- experiments only (tools/bench_k1.py); not part of the product path -----------------------
  * variant: 1 = one epilogue warp per TMEM lane quarter, 2 = scanner + selector warps (default);
  * mode (variant 1): 0 = product, 1 = release the accumulators unread (GEMM pipeline alone),

@@ -92,3 +92,45 @@ def test_fullsize_train_step_invariants(tmp_path):
     torch.testing.assert_close(norms, torch.ones(F, device="cuda"), atol=1e-5, rtol=0)
     for n, p in sae.named_parameters():
         assert torch.isfinite(p).all() and not torch.equal(p, w0[n]), n
+
+
+@pytest.mark.parametrize("shape", [(75776, 384, 3072), (8192, 768, 6144), (2048, 1280, 40960)])
+def test_deterministic_mode_is_bit_reproducible(shape, tmp_path):
+    """SAETrainer(deterministic=True): two runs of the bf16 graphed step from the same state on the
+    same batches are BIT-identical (losses, every parameter, AdamW moments, counters) - split-K
+    partials and cross-row sums are added in a fixed / order-independent way (wsae_*_det) instead of
+    float atomics in arrival order.  The default mode must agree with it to accumulation-order noise."""
+    from whisper_sae_b200.config import TrainingConfig
+    from whisper_sae_b200.sae import SAETrainer, TopKSAE
+
+    rows, d, f = shape
+    steps = 5
+    x = O.synthetic_activations(2 * rows, d, seed=21).cuda()
+
+    def run(deterministic: bool, tag: str):
+        torch.manual_seed(42)
+        sae = TopKSAE(d, f, k=K, dead_feature_threshold=10_000)
+        cfg = TrainingConfig(batch_size=rows, use_amp=True, num_workers=0, learning_rate=1e-3, warmup_steps=2)
+        tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path / tag, deterministic=deterministic)
+        tr.setup_scheduler(100)
+        losses = [tr.train_step(x[(s % 2) * rows:(s % 2 + 1) * rows]).loss for s in range(steps)]
+        torch.cuda.synchronize()
+        state = {n: t.detach().clone() for n, t in sae.state_dict().items()}
+        for i, p in enumerate(sae.parameters()):
+            st = tr.optimizer.state[p]
+            state[f"m{i}"], state[f"v{i}"] = st["exp_avg"].clone(), st["exp_avg_sq"].clone()
+        assert tr._graphs[rows].graph is not None and tr._graphs[rows].det == deterministic
+        return losses, state
+
+    la, sa = run(True, "a")
+    lb, sb = run(True, "b")
+    assert la == lb, "deterministic mode: losses differ between two runs"
+    for n in sa:
+        assert torch.equal(sa[n], sb[n]), f"deterministic mode: {n} differs between two runs"
+    lc, sc = run(False, "c")
+    for a, c in zip(la, lc):
+        assert a == pytest.approx(c, rel=1e-5)
+    assert torch.equal(sa["feature_last_activated"], sc["feature_last_activated"])
+    for n in ("encoder.weight", "decoder.weight"):
+        rel = ((sa[n] - sc[n]).norm() / sc[n].norm()).item()
+        assert rel < 1e-3, f"{n}: deterministic vs default rel-L2 {rel:.2e}"

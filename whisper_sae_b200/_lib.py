@@ -99,6 +99,22 @@ _SIGNATURES = {
          c_void_p, c_void_p, c_void_p],
         c_int,
     ),
+    "wsae_decode_backward_det": (
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+         c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_void_p],
+        c_int,
+    ),
+    "wsae_det_finish": ([c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "wsae_wgrad_gemm_workspace": ([c_int, c_int, c_int, POINTER(c_ulonglong)], c_int),
+    "wsae_wgrad_gemm_det": (
+        [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+         c_void_p, c_void_p, c_ulonglong, c_void_p],
+        c_int,
+    ),
+    "wsae_sumsq_det_blocks": ([], c_int),
+    "wsae_sumsq_det": ([c_void_p, c_longlong, c_void_p, c_void_p, c_void_p], c_int),
+    "wsae_bpre_grad_det": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "wsae_bucket_cells": ([c_int, c_int, POINTER(c_int), POINTER(c_int)], c_int),
     "wsae_bucket_by_tile": (
         [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -182,6 +182,35 @@ bpre_grad_kernel(const float* __restrict__ d_b_dec, const float* __restrict__ d_
   }
 }
 
+// Deterministic form of bpre_grad: chunk c of kBpreDetFeat features writes its partial GEMV row to
+// ws[c][:] (features in index order), bpre_det_reduce_kernel subtracts the chunks in order.
+constexpr int kBpreDetFeat = 256;
+__global__ void __launch_bounds__(256)
+bpre_det_partial_kernel(const float* __restrict__ d_b_enc, const float* __restrict__ w_enc, int F, int d,
+                        float* __restrict__ ws) {
+  __shared__ float s_coef[kBpreDetFeat];
+  const int f0 = blockIdx.x * kBpreDetFeat;
+  for (int i = threadIdx.x; i < kBpreDetFeat; i += blockDim.x) s_coef[i] = f0 + i < F ? d_b_enc[f0 + i] : 0.f;
+  __syncthreads();
+  for (int col = threadIdx.x; col < d; col += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < kBpreDetFeat; ++j) {
+      const float c = s_coef[j];
+      if (c != 0.f) acc = fmaf(c, __ldg(w_enc + static_cast<size_t>(f0 + j) * d + col), acc);
+    }
+    ws[static_cast<size_t>(blockIdx.x) * d + col] = acc;
+  }
+}
+__global__ void __launch_bounds__(256)
+bpre_det_reduce_kernel(const float* __restrict__ d_b_dec, const float* __restrict__ ws, int nchunk, int d,
+                       float* __restrict__ d_b_pre) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= d) return;
+  float acc = 0.f;
+  for (int c = 0; c < nchunk; ++c) acc += ws[static_cast<size_t>(c) * d + col];
+  d_b_pre[col] = d_b_dec[col] - acc;
+}
+
 // dx[b, :] = sum_j dv_j * W_enc[i_j, :] - g[b, :]    (only when the input itself requires grad)
 __global__ void __launch_bounds__(256)
 input_grad_kernel(const float* __restrict__ resid, const float* __restrict__ w_enc,
@@ -303,6 +332,16 @@ extern "C" int wsae_bpre_grad(const float* d_b_dec, const float* d_b_enc, const 
   const int threads = d >= 256 ? 256 : 128;
   bpre_grad_kernel<<<ceil_div(F, kBpreFeat), threads, 0, stream>>>(d_b_dec, d_b_enc, w_enc, F, d,
                                                                  d_b_pre);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// db_pre = db_dec - db_enc . W_enc in a fixed summation order; ws: ceil(F / 256) * d floats.
+extern "C" int wsae_bpre_grad_det(const float* d_b_dec, const float* d_b_enc, const float* w_enc,
+                                  int F, int d, float* d_b_pre, float* ws, cudaStream_t stream) {
+  if (!d_b_dec || !d_b_enc || !w_enc || !d_b_pre || !ws || F <= 0 || d <= 0) return kBadArg;
+  const int nchunk = ceil_div(F, kBpreDetFeat);
+  bpre_det_partial_kernel<<<nchunk, 256, 0, stream>>>(d_b_enc, w_enc, F, d, ws);
+  bpre_det_reduce_kernel<<<ceil_div(d, 256), 256, 0, stream>>>(d_b_dec, ws, nchunk, d, d_b_pre);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -79,6 +79,23 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 }
 
 constexpr int kFusedWarps = 4;
+
+// ---- deterministic accumulation (wsae_decode_backward_det) ------------------------------------------
+// The three cross-row sums of this kernel - db_enc[f], db_dec[c] and the SSE - are float atomics in
+// the default mode, i.e. summed in whatever order the warps arrive: two runs differ in the last bits,
+// and early AdamW steps amplify that (profiles/r1_v12_check_dp_2gpu.txt: 1e-2 rel-L2 in the weights
+// after 24 steps).  With a workspace `det_ws` (int64 [F + d + 1], caller-zeroed) every addend is
+// rounded ONCE to fixed point and added with integer atomics - integer addition is associative, so
+// the result does not depend on the order.  The addends are the UNSCALED dot products r . w (|.| <
+// 2^10, scale 2^30), residual column sums (scale 2^28) and squared errors (scale 2^20): the common
+// factor s = coef * grad_out is applied by wsae_det_finish, which converts the sums back.
+constexpr double kDetScaleEnc = 1073741824.0;      // 2^30
+constexpr double kDetScaleDec = 268435456.0;       // 2^28
+constexpr double kDetScaleSse = 1048576.0;         // 2^20
+__device__ __forceinline__ void det_add(long long* slot, double v, double scale) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(slot),
+            static_cast<unsigned long long>(__double2ll_rn(v * scale)));
+}
 constexpr int kDotScratch = 32 * 9;   // floats per warp: 32 dot products x 8 partial sums, stride 9 (bank-conflict free)
 
 // bf16 decoder shadow only.  k <= 32, d % 8 == 0.
@@ -105,7 +122,8 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
                        const long long* __restrict__ step_count, float* __restrict__ d_b_enc,
                        float* __restrict__ d_b_dec, float* __restrict__ dpre_val,
                        const float* const* __restrict__ target_at,
-                       const long long* const* __restrict__ rows_at, int stamp_words) {
+                       const long long* const* __restrict__ rows_at, int stamp_words,
+                       long long* __restrict__ det_ws) {
   extern __shared__ __align__(16) float fsm[];   // [dp] bias (b_dec + b_pre), then one [dp] db_dec accumulator per warp
   pdl_prologue();
   if (target_at != nullptr) target = *target_at;   // address from a device-resident slot (graph replay)
@@ -229,7 +247,10 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
       const float my_dv = fired ? s * dot : 0.f;
       if (lane < k) {
         if (dpre_val != nullptr) dpre_val[static_cast<size_t>(row) * k + lane] = my_dv;
-        if (fired && d_b_enc != nullptr) atomicAdd(d_b_enc + my_i, my_dv);
+        if (fired && d_b_enc != nullptr) {
+          if (det_ws != nullptr) det_add(det_ws + my_i, static_cast<double>(dot), kDetScaleEnc);
+          else atomicAdd(d_b_enc + my_i, my_dv);
+        }
       }
       continue;
     }
@@ -304,7 +325,10 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
     const float my_dv = fired ? s * part[0] : 0.f;
     if (lane < k) {
       if (dpre_val != nullptr) dpre_val[static_cast<size_t>(row) * k + lane] = my_dv;
-      if (fired && d_b_enc != nullptr) atomicAdd(d_b_enc + my_i, my_dv);
+      if (fired && d_b_enc != nullptr) {
+        if (det_ws != nullptr) det_add(det_ws + my_i, static_cast<double>(part[0]), kDetScaleEnc);
+        else atomicAdd(d_b_enc + my_i, my_dv);
+      }
     }
   }
 
@@ -325,7 +349,8 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < kFusedWarps; ++w) t += fsm[dp + w * dp + i];
-      atomicAdd(d_b_dec + i, s * t);
+      if (det_ws != nullptr) det_add(det_ws + F + i, static_cast<double>(t), kDetScaleDec);
+      else atomicAdd(d_b_dec + i, s * t);
     }
   if (threadIdx.x == 0 && stats != nullptr) {
     double tsum = 0.0;
@@ -334,7 +359,8 @@ decode_backward_kernel(const float* __restrict__ target, const __nv_bfloat16* __
       tsum += static_cast<double>(s_sse[w]);
       c += s_l0[w];
     }
-    atomicAdd(&stats->sse, tsum);
+    if (det_ws != nullptr) det_add(det_ws + F + d, tsum, kDetScaleSse);
+    else atomicAdd(&stats->sse, tsum);
     atomicAdd(&stats->l0_count, c);
   }
 }
@@ -377,7 +403,8 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
                               const long long* __restrict__ step_count, float* __restrict__ d_b_enc,
                               float* __restrict__ d_b_dec, float* __restrict__ dpre_val,
                               const float* const* __restrict__ target_at,
-                              const long long* const* __restrict__ rows_at, int stamp_words, int dbg) {
+                              const long long* const* __restrict__ rows_at, int stamp_words,
+                              long long* __restrict__ det_ws, int dbg) {
   extern __shared__ __align__(16) float fsm[];   // [d] bias, [warps][d] db_dec partials, the slice rings, the fired bitmap
   pdl_prologue();
   if (target_at != nullptr) target = *target_at;
@@ -557,7 +584,10 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
     const float my_dv = fired ? s * part[0] : 0.f;
     if (lane < k && !(dbg & 8)) {
       if (dpre_val != nullptr) dpre_val[static_cast<size_t>(row) * k + lane] = my_dv;
-      if (fired && d_b_enc != nullptr) atomicAdd(d_b_enc + my_i, my_dv);
+      if (fired && d_b_enc != nullptr) {
+        if (det_ws != nullptr) det_add(det_ws + my_i, static_cast<double>(part[0]), kDetScaleEnc);
+        else atomicAdd(d_b_enc + my_i, my_dv);
+      }
     }
     // rotate the metadata window
     cur_i = nxt_i; cur_v = nxt_v; cur_f = nxt_f; cur_off = nxt_off;
@@ -583,7 +613,8 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < kFusedWarps; ++w) t += fsm[d + w * d + i];
-      atomicAdd(d_b_dec + i, s * t);
+      if (det_ws != nullptr) det_add(det_ws + F + i, static_cast<double>(t), kDetScaleDec);
+      else atomicAdd(d_b_dec + i, s * t);
     }
   if (threadIdx.x == 0 && stats != nullptr) {
     double tsum = 0.0;
@@ -592,8 +623,26 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
       tsum += static_cast<double>(s_sse[w]);
       c += s_l0[w];
     }
-    atomicAdd(&stats->sse, tsum);
+    if (det_ws != nullptr) det_add(det_ws + F + d, tsum, kDetScaleSse);
+    else atomicAdd(&stats->sse, tsum);
     atomicAdd(&stats->l0_count, c);
+  }
+}
+
+// det_ws (see kDetScale*) -> d_b_enc += s * sum, d_b_dec += s * sum, stats->sse += sum
+__global__ void __launch_bounds__(256)
+det_finish_kernel(const long long* __restrict__ det_ws, int F, int d, const float* __restrict__ grad_out,
+                  float coef, float* __restrict__ d_b_enc, float* __restrict__ d_b_dec,
+                  FusedStats* __restrict__ stats) {
+  const double s = static_cast<double>(coef) * (grad_out != nullptr ? static_cast<double>(*grad_out) : 1.0);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < F) {
+    if (d_b_enc != nullptr) d_b_enc[i] += static_cast<float>(s * (static_cast<double>(det_ws[i]) / kDetScaleEnc));
+  } else if (i < F + d) {
+    if (d_b_dec != nullptr)
+      d_b_dec[i - F] += static_cast<float>(s * (static_cast<double>(det_ws[i]) / kDetScaleDec));
+  } else if (i == F + d) {
+    if (stats != nullptr) stats->sse += static_cast<double>(det_ws[i]) / kDetScaleSse;
   }
 }
 
@@ -609,7 +658,7 @@ extern "C" int wsae_debug_decode_backward_general(int on) { g_decode_backward_ge
 // See include/wsae.h.  Returns WSAE_E_UNSUPPORTED for shapes the fused kernel does not cover
 // (fp32 decoder, k > 32, d % 8 != 0): callers then use K2 + K3.
 static int decode_backward_impl(const float* target, const float* const* target_at,
-                                const long long* const* rows_at, const void* w_decT, int w_is_bf16, const float* b_dec,
+                                const long long* const* rows_at, long long* det_ws, const void* w_decT, int w_is_bf16, const float* b_dec,
                                 const float* b_pre, const int32_t* idx, const float* val,
                                 const float* grad_out, float coef, int B, int d, int F, int k,
                                 float* resid, void* resid_bf16, void* stats,
@@ -691,11 +740,11 @@ static int decode_backward_impl(const float* target, const float* const* target_
       if (stages == 3)
         launch_pdl(decode_backward_staged_kernel<3>, nblk, kFusedWarps * 32, smem_s, stream, target, wd, b_dec,
                    b_pre, idx, val, grad_out, coef, B, d, F, k, resid, rbf, st, last_activated, step_count,
-                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, dbg);
+                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, det_ws, dbg);
       else
         launch_pdl(decode_backward_staged_kernel<2>, nblk, kFusedWarps * 32, smem_s, stream, target, wd, b_dec,
                    b_pre, idx, val, grad_out, coef, B, d, F, k, resid, rbf, st, last_activated, step_count,
-                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, dbg);
+                   d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, det_ws, dbg);
       return static_cast<int>(cudaGetLastError());
     }
   }
@@ -704,12 +753,12 @@ static int decode_backward_impl(const float* target, const float* const* target_
     launch_pdl(decode_backward_kernel<true>, blocks, kFusedWarps * 32, smem, stream, target,
                static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
                F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
-               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words);
+               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, det_ws);
   else
     launch_pdl(decode_backward_kernel<false>, blocks, kFusedWarps * 32, smem, stream, target,
                static_cast<const __nv_bfloat16*>(w_decT), b_dec, b_pre, idx, val, grad_out, coef, B, d,
                F, k, resid, static_cast<__nv_bfloat16*>(resid_bf16), static_cast<FusedStats*>(stats),
-               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words);
+               last_activated, step_count, d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, det_ws);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -721,7 +770,7 @@ extern "C" int wsae_decode_backward(const float* target, const void* w_decT, int
                                     const long long* step_count, float* d_b_enc, float* d_b_dec,
                                     float* dpre_val, cudaStream_t stream) {
   if (!target) return kBadArg;
-  return decode_backward_impl(target, nullptr, nullptr, w_decT, w_is_bf16, b_dec, b_pre, idx, val, grad_out,
+  return decode_backward_impl(target, nullptr, nullptr, nullptr, w_decT, w_is_bf16, b_dec, b_pre, idx, val, grad_out,
                               coef, B, d, F, k, resid, resid_bf16, stats, last_activated, step_count,
                               d_b_enc, d_b_dec, dpre_val, stream);
 }
@@ -736,7 +785,7 @@ extern "C" int wsae_decode_backward_at(const float* const* target_at, const void
                                        const long long* step_count, float* d_b_enc, float* d_b_dec,
                                        float* dpre_val, cudaStream_t stream) {
   if (!target_at) return kBadArg;
-  return decode_backward_impl(nullptr, target_at, nullptr, w_decT, w_is_bf16, b_dec, b_pre, idx, val,
+  return decode_backward_impl(nullptr, target_at, nullptr, nullptr, w_decT, w_is_bf16, b_dec, b_pre, idx, val,
                               grad_out, coef, B, d, F, k, resid, resid_bf16, stats, last_activated,
                               step_count, d_b_enc, d_b_dec, dpre_val, stream);
 }
@@ -753,7 +802,34 @@ extern "C" int wsae_decode_backward_rows_at(const float* const* target_at,
                                             float* d_b_enc, float* d_b_dec, float* dpre_val,
                                             cudaStream_t stream) {
   if (!target_at || !rows_at) return kBadArg;
-  return decode_backward_impl(nullptr, target_at, rows_at, w_decT, w_is_bf16, b_dec, b_pre, idx, val,
+  return decode_backward_impl(nullptr, target_at, rows_at, nullptr, w_decT, w_is_bf16, b_dec, b_pre, idx, val,
                               grad_out, coef, B, d, F, k, resid, resid_bf16, stats, last_activated,
                               step_count, d_b_enc, d_b_dec, dpre_val, stream);
+}
+
+// Deterministic form (see kDetScale* above): the slot form of wsae_decode_backward_rows_at
+// (target_at / rows_at as there; target may be given directly instead of target_at) with the three
+// cross-row float sums accumulated order-independently in det_ws (int64 [F + d + 1], caller-zeroed);
+// d_b_enc / d_b_dec / stats->sse are NOT touched here - wsae_det_finish adds the converted sums.
+extern "C" int wsae_decode_backward_det(const float* target, const float* const* target_at,
+                                        const long long* const* rows_at, const void* w_decT,
+                                        int w_is_bf16, const float* b_dec, const float* b_pre,
+                                        const int32_t* idx, const float* val, const float* grad_out,
+                                        float coef, int B, int d, int F, int k, float* resid,
+                                        void* resid_bf16, void* stats, long long* last_activated,
+                                        const long long* step_count, float* d_b_enc, float* d_b_dec,
+                                        float* dpre_val, long long* det_ws, cudaStream_t stream) {
+  if ((!target && !target_at) || !det_ws) return kBadArg;
+  return decode_backward_impl(target, target_at, rows_at, det_ws, w_decT, w_is_bf16, b_dec, b_pre, idx,
+                              val, grad_out, coef, B, d, F, k, resid, resid_bf16, stats, last_activated,
+                              step_count, d_b_enc, d_b_dec, dpre_val, stream);
+}
+
+extern "C" int wsae_det_finish(const long long* det_ws, int F, int d, const float* grad_out, float coef,
+                               float* d_b_enc, float* d_b_dec, void* stats, cudaStream_t stream) {
+  if (!det_ws || F <= 0 || d <= 0) return kBadArg;
+  const int n = F + d + 1;
+  det_finish_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(det_ws, F, d, grad_out, coef, d_b_enc, d_b_dec,
+                                                          static_cast<FusedStats*>(stats));
+  return static_cast<int>(cudaGetLastError());
 }

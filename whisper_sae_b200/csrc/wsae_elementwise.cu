@@ -135,6 +135,40 @@ sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ out) {
   }
 }
 
+// Deterministic form of sumsq: every block writes its partial to ws[blockIdx.x] (float4 grid-stride
+// sums in a fixed order), sumsq_ordered_kernel adds them up in index order.
+__global__ void __launch_bounds__(256)
+sumsq_partial_kernel(const float* __restrict__ g, size_t n, double* __restrict__ ws) {
+  float acc = 0.f;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
+  size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  for (; i + 3 < n; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(g + i);
+    acc = fmaf(v.x, v.x, acc);
+    acc = fmaf(v.y, v.y, acc);
+    acc = fmaf(v.z, v.z, acc);
+    acc = fmaf(v.w, v.w, acc);
+  }
+  if (i < n && i + 3 >= n)
+    for (size_t j = i; j < n; ++j) acc = fmaf(g[j], g[j], acc);
+  __shared__ float s[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += static_cast<double>(s[w]);
+    ws[blockIdx.x] = t;
+  }
+}
+__global__ void sumsq_ordered_kernel(const double* __restrict__ ws, int nblocks, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += ws[b];
+    *out += t;
+  }
+}
+
 // AdamW with the clip_grad_norm_ scale folded in (torch.optim.AdamW semantics, amsgrad=False):
 //   g   = grad * min(1, max_norm / (sqrt(sumsq) + 1e-6))
 //   p  *= 1 - lr * wd ; m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g
@@ -444,5 +478,18 @@ extern "C" int wsae_fused_adamw(float* p, const float* grad, float* m, float* v,
   const unsigned blocks = static_cast<unsigned>(want < cap ? want : cap);
   fused_adamw_kernel<<<blocks, 256, 0, stream>>>(p, grad, m, v, static_cast<size_t>(n), hyper,
                                                  grad_sumsq);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// *out += sum(g^2), bit-reproducible: per-block partials in ws (>= wsae_sumsq_det_blocks() doubles),
+// summed in block order by a second kernel (wsae_sumsq adds them with atomics in arrival order).
+extern "C" int wsae_sumsq_det_blocks(void) { return 1024; }
+extern "C" int wsae_sumsq_det(const float* g, long long n, double* ws, double* out, cudaStream_t stream) {
+  if (!g || !ws || !out || n <= 0) return kBadArg;
+  size_t want = (static_cast<size_t>(n) / 4 + 255) / 256;
+  if (want < 1) want = 1;
+  const unsigned blocks = static_cast<unsigned>(want < 1024 ? want : 1024);   // fixed cap: same split on every device
+  sumsq_partial_kernel<<<blocks, 256, 0, stream>>>(g, static_cast<size_t>(n), ws);
+  sumsq_ordered_kernel<<<1, 32, 0, stream>>>(ws, static_cast<int>(blocks), out);
   return static_cast<int>(cudaGetLastError());
 }

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(256, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int n_chunks, int n_ft,
                   int n_nt, int nb_tile, int ksplit, const int* __restrict__ offsets,
                   const uint32_t* __restrict__ ent_meta, const float* __restrict__ ent_val,
-                  const float* __restrict__ grad_out, float alpha, float* __restrict__ out) {
+                  const float* __restrict__ grad_out, float alpha, float* __restrict__ out,
+                  float* __restrict__ det_ws) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = kWgATile + nb_tile * kWgRBlock;
@@ -335,7 +336,20 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
         tmem_ld16(taddr + cb, r);
         tmem_ld_wait16(r);
         const int col0 = nb0 * 64 + cb;
-        if (f < F) {
+        if (f < F && det_ws != nullptr) {
+          // deterministic mode: this (feature tile, k split) partial goes to its own slab with plain
+          // stores; wgrad_reduce_kernel adds the slabs to `out` in k-split order
+          float* wrow = det_ws + (static_cast<size_t>(ks) * F + f) * d + col0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            if (col0 + j + 3 < d)
+              *reinterpret_cast<float4*>(wrow + j) =
+                  make_float4(s * __uint_as_float(r[j]), s * __uint_as_float(r[j + 1]),
+                              s * __uint_as_float(r[j + 2]), s * __uint_as_float(r[j + 3]));
+            else
+              for (int jj = j; jj < j + 4; ++jj)
+                if (col0 + jj < d) wrow[jj] = s * __uint_as_float(r[jj]);
+        } else if (f < F) {
           float* orow = out + static_cast<size_t>(f) * d + col0;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
@@ -359,6 +373,26 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_r, int F, int d, int 
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// out[i] += ws[0][i] + ws[1][i] + ... + ws[nslab-1][i], slabs of n floats, in that order.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, int nslab, size_t n, float* __restrict__ out) {
+  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 acc = *reinterpret_cast<const float4*>(out + i);
+    for (int sl = 0; sl < nslab; ++sl) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + static_cast<size_t>(sl) * n + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = acc;
+  } else {
+    for (size_t j = i; j < n; ++j) {
+      float acc = out[j];
+      for (int sl = 0; sl < nslab; ++sl) acc += ws[static_cast<size_t>(sl) * n + j];
+      out[j] = acc;
+    }
   }
 }
 
@@ -412,22 +446,24 @@ extern "C" int wsae_bucket_by_tile(const int32_t* idx, const float* val, const f
 
 // out[F,d] += alpha * (*grad_out) * S^T . R, S from the bucketed entries with values ent_val,
 // R = bf16 [B rows, >= ceil(d/64)*64 columns] with row pitch r_pitch_elems.
-extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int F, int d,
-                               const int* offsets, const uint32_t* ent_meta, const float* ent_val,
-                               const float* grad_out, float alpha, float* out,
-                               cudaStream_t stream) {
-  if (!r_bf16 || !offsets || !ent_meta || !ent_val || !out) return kBadArg;
+// plan_only: just report the k-split count (workspace sizing), launch nothing.
+static int wgrad_gemm_impl(const void* r_bf16, int r_pitch_elems, int B, int F, int d,
+                           const int* offsets, const uint32_t* ent_meta, const float* ent_val,
+                           const float* grad_out, float alpha, float* out, float* det_ws,
+                           unsigned long long det_ws_bytes, int* plan_only, cudaStream_t stream) {
+  if (!plan_only && (!r_bf16 || !offsets || !ent_meta || !ent_val || !out)) return kBadArg;
   if (B <= 0 || F <= 0 || d <= 0) return kBadArg;
   const int nb_total = ceil_div(d, 64);
-  if (r_pitch_elems < d || (r_pitch_elems % 8) != 0) return kBadArg;
-  if ((reinterpret_cast<uintptr_t>(r_bf16) & 15u) != 0) return kBadArg;
+  if (!plan_only && (r_pitch_elems < d || (r_pitch_elems % 8) != 0)) return kBadArg;
+  if (!plan_only && (reinterpret_cast<uintptr_t>(r_bf16) & 15u) != 0) return kBadArg;
   const int n_chunks = ceil_div(B, kWgRows), n_ft = ceil_div(F, kWgFeat);
   const int n_nt = ceil_div(nb_total, kWgMaxNB);
   const int nb_tile = ceil_div(nb_total, n_nt);
 
+  CUtensorMap tm;
+  if (!plan_only) {
   auto fn = wg_encode_fn();
   if (!fn) return kNoDriver;
-  CUtensorMap tm;
   // [B rows, d columns] bf16, row pitch r_pitch_elems; box = 64 rows x 64 columns; columns >= d and
   // rows >= B of a box are zero-filled by TMA
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(B)};
@@ -438,6 +474,7 @@ extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return static_cast<int>(1000 + cr);
+  }
 
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -494,6 +531,17 @@ extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int
       ksplit = ks;
     }
   }
+  const int per_split = ceil_div(n_chunks, ksplit);
+  const int nslab = ceil_div(n_chunks, per_split);     // k splits that own at least one row chunk
+  if (plan_only) {
+    *plan_only = nslab;
+    return kOk;
+  }
+  // deterministic mode: one partial slab per k split, then an ordered reduction.  A single split
+  // already writes every output element from exactly one CTA (a RED onto the caller's value).
+  const bool det = det_ws != nullptr && nslab > 1;
+  if (det && det_ws_bytes < static_cast<unsigned long long>(nslab) * F * d * sizeof(float)) return kBadArg;
+  if (det && d % 4 != 0) return kUnsupported;
   const int grid = n_ft * n_nt * ksplit;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -510,7 +558,40 @@ extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   e = cudaLaunchKernelEx(&cfg, kern, tm, F, d, n_chunks, n_ft, n_nt, nb_tile, ksplit, offsets, ent_meta,
-                         ent_val, grad_out, alpha, out);
+                         ent_val, grad_out, alpha, out, det ? det_ws : static_cast<float*>(nullptr));
   if (e != cudaSuccess) return static_cast<int>(e);
+  if (det) {
+    const size_t n = static_cast<size_t>(F) * d;
+    const unsigned blocks = static_cast<unsigned>((n / 4 + 255) / 256 + 1);
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(det_ws, nslab, n, out);
+  }
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int wsae_wgrad_gemm(const void* r_bf16, int r_pitch_elems, int B, int F, int d,
+                               const int* offsets, const uint32_t* ent_meta, const float* ent_val,
+                               const float* grad_out, float alpha, float* out,
+                               cudaStream_t stream) {
+  return wgrad_gemm_impl(r_bf16, r_pitch_elems, B, F, d, offsets, ent_meta, ent_val, grad_out, alpha, out,
+                         nullptr, 0, nullptr, stream);
+}
+
+// Deterministic form: the split-K partial sums go to `ws` (wsae_wgrad_gemm_workspace bytes) with
+// plain stores and are added to `out` in k-split order by a second kernel, instead of red.global.add
+// in arrival order.  Same result up to the summation order; bit-reproducible from run to run.
+extern "C" int wsae_wgrad_gemm_workspace(int B, int F, int d, unsigned long long* bytes) {
+  if (!bytes || B <= 0 || F <= 0 || d <= 0) return kBadArg;
+  int nslab = 0;
+  const int rc = wgrad_gemm_impl(nullptr, 0, B, F, d, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr,
+                                 nullptr, 0, &nslab, nullptr);
+  if (rc) return rc;
+  *bytes = nslab > 1 ? static_cast<unsigned long long>(nslab) * F * d * sizeof(float) : 0ull;
+  return kOk;
+}
+extern "C" int wsae_wgrad_gemm_det(const void* r_bf16, int r_pitch_elems, int B, int F, int d,
+                                   const int* offsets, const uint32_t* ent_meta, const float* ent_val,
+                                   const float* grad_out, float alpha, float* out, float* ws,
+                                   unsigned long long ws_bytes, cudaStream_t stream) {
+  return wgrad_gemm_impl(r_bf16, r_pitch_elems, B, F, d, offsets, ent_meta, ent_val, grad_out, alpha, out,
+                         ws, ws_bytes, nullptr, stream);
 }

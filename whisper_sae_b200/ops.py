@@ -258,12 +258,26 @@ def decode_backward(target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: Tensor
                     resid: Tensor | None, resid_bf16: Tensor | None, stats: Tensor | None,
                     last_activated: Tensor | None, step_count: Tensor | None,
                     d_b_enc: Tensor | None, d_b_dec: Tensor | None, dpre_val: Tensor | None,
-                    target_is_slot: bool = False, rows_at: Tensor | None = None) -> None:
+                    target_is_slot: bool = False, rows_at: Tensor | None = None,
+                    det_ws: Tensor | None = None) -> None:
     """K23: sparse decode + MSE + L0 + fired stamps + dv / bias gradients in one pass.
     ``target_is_slot``: ``target`` is a one-element int64 tensor holding the device address of the
     ``[B, d]`` fp32 target, read when the kernel runs (see ``pack_activations_at``)."""
     _need_cuda(target, w_decT, b_dec, b_pre, idx, val, grad_out)
     F, d = w_decT.shape
+    if det_ws is not None:
+        # deterministic accumulation: fixed-point int64 sums in det_ws [F + d + 1] (zeroed by the caller),
+        # converted by det_finish; the float atomics on d_b_enc / d_b_dec / stats.sse are not issued
+        if det_ws.dtype != torch.int64 or det_ws.numel() < F + d + 1 or not det_ws.is_cuda:
+            raise RuntimeError("det_ws must be an int64 CUDA tensor of >= F + d + 1 elements")
+        if w_decT.dtype != torch.bfloat16 or not w_decT.is_contiguous():
+            raise RuntimeError("w_decT must be contiguous [F, d] bfloat16")
+        B, k = idx.shape
+        lib = _lib.load()
+        tgt, tgt_at = (None, target) if target_is_slot else (target, None)
+        _run("wsae_decode_backward", lib.wsae_decode_backward_det, _ptr(tgt), _ptr(tgt_at), _ptr(rows_at), _ptr(w_decT), 1, _ptr(b_dec), _ptr(b_pre), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(resid), _ptr(resid_bf16), _ptr(stats), _ptr(last_activated), _ptr(step_count), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _ptr(det_ws), _stream())
+        _run("wsae_det_finish", lib.wsae_det_finish, _ptr(det_ws), F, d, _ptr(grad_out), float(coef), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(stats), _stream())
+        return
     if target_is_slot:
         if target.dtype != torch.int64 or target.numel() != 1:
             raise RuntimeError("target slot must be a one-element int64 CUDA tensor")
@@ -326,8 +340,16 @@ def wgrad_gemm_supported(d: int) -> bool:
     return d % 8 == 0 and os.environ.get("WSAE_WGRAD", "gemm") != "scatter"
 
 
+def wgrad_gemm_workspace(B: int, F: int, d: int) -> int:
+    """Bytes of split-K workspace the deterministic wgrad GEMM needs at this shape (0 = no split)."""
+    lib = _lib.load()
+    n = ctypes.c_ulonglong(0)
+    _lib.check(lib.wsae_wgrad_gemm_workspace(B, F, d, ctypes.byref(n)), "wsae_wgrad_gemm_workspace")
+    return int(n.value)
+
+
 def wgrad_gemm_(out: Tensor, r_bf16: Tensor, B: int, d: int, buckets: TileBuckets, values: Tensor,
-                grad_out: Tensor | None, alpha: float) -> None:
+                grad_out: Tensor | None, alpha: float, det_ws: Tensor | None = None) -> None:
     """K4. out[F, d] += alpha * grad_out * S^T @ r_bf16[:B, :d] (S = bucketed sparse entries of the
     same B rows)."""
     _need_cuda(out, r_bf16, values, grad_out)
@@ -338,6 +360,9 @@ def wgrad_gemm_(out: Tensor, r_bf16: Tensor, B: int, d: int, buckets: TileBucket
     if r_bf16.shape[0] < B or r_bf16.shape[1] < d:
         raise RuntimeError("r_bf16 is smaller than [B, d]")
     lib = _lib.load()
+    if det_ws is not None:      # ordered split-K reduction through a workspace (bit-reproducible)
+        _run("wsae_wgrad_gemm", lib.wsae_wgrad_gemm_det, _ptr(r_bf16), r_bf16.stride(0), B, F, d, _ptr(buckets.offsets), _ptr(buckets.meta), _ptr(values), _ptr(grad_out), float(alpha), _ptr(out), _ptr(det_ws), det_ws.numel() * det_ws.element_size(), _stream(), launches=2)
+        return
     _run("wsae_wgrad_gemm", lib.wsae_wgrad_gemm, _ptr(r_bf16), r_bf16.stride(0), B, F, d, _ptr(buckets.offsets), _ptr(buckets.meta), _ptr(values), _ptr(grad_out), float(alpha), _ptr(out), _stream())
 
 
@@ -352,11 +377,17 @@ def scatter_rows_(out: Tensor, rows: Tensor, center: Tensor | None, idx: Tensor,
     _run("wsae_scatter_rows", lib.wsae_scatter_rows, _ptr(rows), _ptr(center), _ptr(idx), _ptr(vals), B, dr, F, idx.shape[1], _ptr(out), _stream())
 
 
-def bpre_grad(d_b_dec: Tensor, d_b_enc: Tensor, w_enc: Tensor, out: Tensor | None = None) -> Tensor:
+def bpre_grad(d_b_dec: Tensor, d_b_enc: Tensor, w_enc: Tensor, out: Tensor | None = None,
+              det_ws: Tensor | None = None) -> Tensor:
     F, d = w_enc.shape
     if out is None:
         out = torch.empty(d, dtype=torch.float32, device=w_enc.device)
     lib = _lib.load()
+    if det_ws is not None:      # fixed summation order: ceil(F / 256) * d floats of workspace
+        if det_ws.numel() < (F + 255) // 256 * d:
+            raise RuntimeError("bpre_grad det_ws too small")
+        _run("wsae_bpre_grad", lib.wsae_bpre_grad_det, _ptr(d_b_dec), _ptr(d_b_enc), _ptr(w_enc), F, d, _ptr(out), _ptr(det_ws), _stream(), launches=2)
+        return out
     _run("wsae_bpre_grad", lib.wsae_bpre_grad, _ptr(d_b_dec), _ptr(d_b_enc), _ptr(w_enc), F, d, _ptr(out), _stream())
     return out
 
@@ -418,9 +449,14 @@ def cast_bf16(src: Tensor, out: Tensor | None = None) -> Tensor:
     return out
 
 
-def sumsq_(g: Tensor, out: Tensor) -> None:
-    """out (float64[1]) += sum(g**2)."""
+def sumsq_(g: Tensor, out: Tensor, det_ws: Tensor | None = None) -> None:
+    """out (float64[1]) += sum(g**2).  ``det_ws`` (float64, >= 1024): ordered, bit-reproducible form."""
     lib = _lib.load()
+    if det_ws is not None:
+        if det_ws.dtype != torch.float64 or det_ws.numel() < lib.wsae_sumsq_det_blocks():
+            raise RuntimeError("sumsq det_ws must be float64 with >= 1024 elements")
+        _run("wsae_sumsq", lib.wsae_sumsq_det, _ptr(g), g.numel(), _ptr(det_ws), _ptr(out), _stream(), launches=2)
+        return
     _run("wsae_sumsq", lib.wsae_sumsq, _ptr(g), g.numel(), _ptr(out), _stream())
 
 

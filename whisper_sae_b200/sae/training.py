@@ -157,6 +157,18 @@ class _GraphedStep:
         # what autograd would leave in .grad (decoder.weight's grad is the [d, F] transposed view)
         self._grad_views = [g.t() if p is m.decoder.weight else g for p, g in zip(self.params, self.grads)]
         self.state = _SparseState()
+        # deterministic mode workspaces (bf16 step with K23 + K4 only)
+        self.det = bool(trainer.deterministic) and self.bf16 and ops.wgrad_gemm_supported(d_in) \
+            and ops.decode_backward_supported(d_in, k_sel, True)
+        if trainer.deterministic and not self.det:
+            raise RuntimeError("deterministic=True covers the bf16 (use_amp) graphed step with d % 8 == 0, k <= 32")
+        self.det_k23 = self.det_k4 = self.det_sumsq = self.det_bpre = None
+        if self.det:
+            self.det_k23 = torch.zeros(F + d + 1, dtype=torch.int64, device=dev)
+            ws_bytes = ops.wgrad_gemm_workspace(rows, F, d)
+            self.det_k4 = torch.empty(max(ws_bytes // 4, 1), dtype=torch.float32, device=dev) if ws_bytes else None
+            self.det_sumsq = torch.empty(1024, dtype=torch.float64, device=dev)
+            self.det_bpre = torch.empty((F + 255) // 256 * d, dtype=torch.float32, device=dev)
         self.graph: torch.cuda.CUDAGraph | list | None = None
         self._mid: dict = {}
         self.kernels_per_replay = 0
@@ -208,6 +220,8 @@ class _GraphedStep:
         terms = 1 if self.bf16 else _fp32_terms()
         w_decT = m.decoder.weight.data.t()
         self.zeroed.zero_()
+        if self.det:
+            self.det_k23.zero_()
         main = torch.cuda.current_stream()
         if self.fork:
             if self._w_used_buf is None:
@@ -242,7 +256,7 @@ class _GraphedStep:
                                 last_activated=m.feature_last_activated, step_count=m.step_count,
                                 d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec, dpre_val=dpre,
                                 target_is_slot=self.in_place,
-                                rows_at=self.rows_slot if self.in_place else None)
+                                rows_at=self.rows_slot if self.in_place else None, det_ws=self.det_k23)
         else:
             resid, _ = ops.decode_mse(x, w_used, m.decoder.bias.data, m.b_pre.data, idx, val,
                                       stats=self.stats, last_activated=m.feature_last_activated,
@@ -260,7 +274,8 @@ class _GraphedStep:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):      # joined in _update, before the gradient norm
                 self._counters()
-                ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
+                ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre,
+                              det_ws=self.det_bpre)
         elif not self.trainer.data_parallel:
             # the metrics are final once K23 has run: post them now, so the host has them (and the
             # next step queued) long before the weight-gradient GEMMs and the optimizer finish
@@ -269,7 +284,8 @@ class _GraphedStep:
         if use_gemm:
             # weight gradients on the tensor cores (K4)
             buckets = ops.bucket_by_tile(idx, val, dpre, F)
-            ops.wgrad_gemm_(self.g_w_enc, a_packed, B, d, buckets, buckets.dpre, None, 1.0)
+            ops.wgrad_gemm_(self.g_w_enc, a_packed, B, d, buckets, buckets.dpre, None, 1.0,
+                            det_ws=self.det_k4 if self.det else None)
         else:
             resid_bf = None
         self._mid = dict(use_gemm=use_gemm, buckets=buckets, resid_bf=resid_bf, B=B, d=d, coef=coef)
@@ -283,9 +299,11 @@ class _GraphedStep:
         mid = self._mid
         if mid["use_gemm"]:
             ops.wgrad_gemm_(self.g_w_decT, mid["resid_bf"], mid["B"], mid["d"], mid["buckets"],
-                            mid["buckets"].act, self.one, mid["coef"])
+                            mid["buckets"].act, self.one, mid["coef"],
+                            det_ws=self.det_k4 if self.det else None)
         if not self.fork:
-            ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre)
+            ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre,
+                          det_ws=self.det_bpre)
 
     def _update(self) -> None:
         """Counters, clip + AdamW + decoder renorm on the (possibly all-reduced) gradient bucket."""
@@ -295,7 +313,7 @@ class _GraphedStep:
             self._counters()
         if self.fork:
             torch.cuda.current_stream().wait_stream(self._side)
-        ops.sumsq_(self.g_flat, self.sumsq)
+        ops.sumsq_(self.g_flat, self.sumsq, det_ws=self.det_sumsq)
         opt_state = self.trainer.optimizer.state
         entries = []
         for p, g in zip(self.params, self.grads):
@@ -454,6 +472,7 @@ class SAETrainer:
         dp_comm=None,
         global_batch_rows: int | None = None,
         project_decoder_grad: bool = False,
+        deterministic: bool | None = None,
     ):
         self.model = model.to(device)
         self.config = config
@@ -495,6 +514,12 @@ class SAETrainer:
         # the row before the AdamW step (fused into adamw_multi).  The reference does not do this
         # (grep finds no projection in sae/training.py), so it is OFF by default and excluded from parity.
         self.project_decoder_grad = bool(project_decoder_grad)
+        # deterministic=True (or WSAE_DETERMINISTIC=1): the bf16 graphed step accumulates its cross-row
+        # and split-K sums in a fixed / order-independent way (wsae_*_det), so two runs from the same
+        # state are bit-identical; the default adds them with float atomics in arrival order
+        if deterministic is None:
+            deterministic = os.environ.get("WSAE_DETERMINISTIC", "0") == "1"
+        self.deterministic = bool(deterministic)
         self.data_parallel = bool(data_parallel)
         self.dp_comm = None
         self.global_batch_rows = global_batch_rows     # default: local rows x world (equal shards)
