@@ -284,7 +284,8 @@ int wsae_bpre_grad_det(const float* d_b_dec, const float* d_b_enc, const float* 
                        float* d_b_pre, float* ws, wsae_stream_t stream);
 
 /* ---- experiments only (tools/bench_k1.py); not part of the product path -----------------------
- * variant: 1 = one epilogue warp per TMEM lane quarter, 2 = scanner + selector warps (default);
+ * variant: 0 = per-batch choice (default: CTA pairs from 1024 rows), 1 = one epilogue warp per TMEM lane
+ * quarter, 2 = scanner + selector warps (single CTA), 3 = scanner + selector on CTA pairs (cta_group::2);
  * mode (variant 1): 0 = product, 1 = release the accumulators unread (GEMM pipeline alone),
  * 2 = scan without compaction; counters: device buffer u64 [grid][8][8] for the scanner/selector
  * wait breakdown (NULL = off). */

@@ -158,25 +158,37 @@ backward_sparse_kernel(const float* __restrict__ resid, const float* __restrict_
 // db_pre[c] = db_dec[c] - sum_f db_enc[f] * W_enc[f, c].  One block per chunk of 32 features;
 // thread t owns columns {t, t + blockDim, ...}; features with a zero bias gradient (never selected
 // in this batch) are skipped, so only fired rows of W_enc are read.
-constexpr int kBpreFeat = 8;
+constexpr int kBpreFeat = 64;
+// One block = 64 features x all columns: 8-feature blocks issued F/8 * d atomics onto the same d
+// addresses (6.5 M at 1280 -> 40960: 2.2 ms, 1.5 % of HBM speed; 0.26 ms at 768 -> 6144).
 __global__ void __launch_bounds__(256)
 bpre_grad_kernel(const float* __restrict__ d_b_dec, const float* __restrict__ d_b_enc,
                  const float* __restrict__ w_enc, int F, int d, float* __restrict__ d_b_pre) {
   __shared__ float s_coef[kBpreFeat];
+  __shared__ int s_any;
   const int f0 = blockIdx.x * kBpreFeat;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
   if (threadIdx.x < kBpreFeat) {
     const int f = f0 + threadIdx.x;
-    s_coef[threadIdx.x] = f < F ? d_b_enc[f] : 0.f;
+    const float c = f < F ? d_b_enc[f] : 0.f;
+    s_coef[threadIdx.x] = c;
+    if (c != 0.f) s_any = 1;
   }
   __syncthreads();
+  if (s_any == 0 && blockIdx.x != 0) return;            // no fired feature in this block
   for (int col = threadIdx.x; col < d; col += blockDim.x) {
-    float acc = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < kBpreFeat; ++j) {
-      const float c = s_coef[j];
-      if (c != 0.f) acc = fmaf(c, __ldg(w_enc + static_cast<size_t>(f0 + j) * d + col), acc);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains; loads stay coalesced per feature row
+    const float* wp = w_enc + static_cast<size_t>(f0) * d + col;
+#pragma unroll 4
+    for (int j = 0; j < kBpreFeat; j += 4) {
+      const float c0 = s_coef[j], c1 = s_coef[j + 1], c2 = s_coef[j + 2], c3 = s_coef[j + 3];
+      if (c0 != 0.f) a0 = fmaf(c0, __ldg(wp + static_cast<size_t>(j) * d), a0);
+      if (c1 != 0.f) a1 = fmaf(c1, __ldg(wp + static_cast<size_t>(j + 1) * d), a1);
+      if (c2 != 0.f) a2 = fmaf(c2, __ldg(wp + static_cast<size_t>(j + 2) * d), a2);
+      if (c3 != 0.f) a3 = fmaf(c3, __ldg(wp + static_cast<size_t>(j + 3) * d), a3);
     }
-    float out = -acc;
+    float out = -((a0 + a1) + (a2 + a3));
     if (blockIdx.x == 0) out += d_b_dec[col];
     if (out != 0.f) atomicAdd(d_b_pre + col, out);
   }

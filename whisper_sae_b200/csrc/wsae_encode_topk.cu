@@ -1127,6 +1127,557 @@ encode_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+// ================================================================================================
+// K1, CTA-PAIR form (cta_group::2): the same scanner / selector epilogue, but the two CTAs of a
+// 2-CTA cluster (two SMs of one TPC) run ONE 256 x 256 x 16 tcgen05.mma per K step over 256
+// activation rows.  Each CTA stages its own 128 A' rows and only HALF of the W' tile (128 of the 256
+// feature rows); the tensor cores read the other half out of the peer's shared memory.  The
+// single-CTA main loop moves 48 KB in and 48 KB out of shared memory per 64-wide K block against 512
+// cycles of MMA (96 KB at 128 B/cycle = 768 cycles: shared-memory bound, 86 % of it measured); here a
+// CTA moves 32 KB in and reads 32 KB - 512 cycles, level with the MMA.  A stage shrinks from 48 to
+// 32 KB.  Protocol (CUTLASS sm100 2-SM pipeline): both CTAs' TMA copies complete on the LEADER's
+// (rank 0) full barrier (.cta_group::2, peer bit of the barrier address cleared); the leader's MMA
+// warp issues tcgen05.mma.cta_group::2 and multicasts its commits to both CTAs' empty / tfull
+// barriers; the scanner threads of both CTAs arrive on the leader's tempty barrier (256 arrivals).
+// ================================================================================================
+constexpr int kBHalfStage = (kBN / 2) * kBK * 2;     // 16 KB: this CTA's half of a W' tile
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;       // shared::cluster address -> same offset in the even CTA
+
+constexpr int kPairFifoBufs = 2;                     // scanner -> selector FIFO ring depth of the pair kernel (3 buffers + 3 stages measured slower: 240 vs 221 us at 384->3072, 3374 vs 2610 us at 1280->40960)
+
+template <int STAGES>
+struct Encode3Smem {
+  static constexpr int kPipeBytes = STAGES * (kAStage + kBHalfStage);
+  static constexpr int kFifoTotal = 2 * kPairFifoBufs * kFifoBytes;     // NB buffers x (val + idx)
+  static constexpr int kTauBytes = kBM * 8;
+  static constexpr int kCntBytes = kPairFifoBufs * kBM * 2;
+  static constexpr int kBarBytes = 512;
+  static_assert((2 * STAGES + 20) * 8 + 8 + 32 <= kBarBytes, "barrier block too small");
+  static constexpr int kTotal = kPipeBytes + kFifoTotal + kTauBytes + kCntBytes + kBarBytes + 1024;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB shared-memory limit");
+};
+
+// scanner_handoff for a ring of NB FIFO buffers.  st: bits 0-1 = buffer in use, bit 2 + i = parity of
+// the number of fills of buffer i.
+template <bool DBG, int NB>
+__device__ __noinline__ uint32_t scanner_handoff_ring(uint32_t st, uint32_t nslots, uint32_t last,
+                                                      uint32_t cnt_addr, uint32_t* meta_q,
+                                                      uint64_t* ffull_q, uint64_t* fempty_q, int lane,
+                                                      unsigned long long* waited) {
+  const uint32_t b = st & 3u;
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(cnt_addr + b * (kBM * 2)),
+               "h"(static_cast<unsigned short>(nslots))
+               : "memory");
+  if (lane == 0) meta_q[b * 4] = last;
+  mbar_arrive(&ffull_q[b * 4]);
+  const uint32_t nb = (b + 1 == NB) ? 0u : b + 1;
+  st = ((st ^ (4u << b)) & ~3u) | nb;      // one more fill of buffer b; continue on the next buffer
+  if (!last) {
+    const long long t = DBG ? clock64() : 0;
+    mbar_wait_backoff(&fempty_q[nb * 4], ((st >> (2u + nb)) & 1u) ^ 1u);
+    if (DBG) *waited += clock64() - t;
+  }
+  return st;
+}
+
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* bar,
+                                                int32_t c_inner, int32_t c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int STAGES, bool DBG>
+__global__ void __launch_bounds__(384, 1)
+encode_topk3_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_w, int B, int F, int k, int ksteps,
+                    int num_m_blocks, int num_n_tiles, int nsplit, int tiles_per_split,
+                    float* __restrict__ out_val, int32_t* __restrict__ out_idx,
+                    unsigned long long* __restrict__ dbg, int mode, uint32_t slot) {
+  using SM = Encode3Smem<STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* pipe = smem;
+  uint8_t* fifo = smem + SM::kPipeBytes;
+  uint8_t* tau_s = fifo + SM::kFifoTotal;
+  uint8_t* cnt_s = tau_s + SM::kTauBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cnt_s + SM::kCntBytes);
+  uint64_t* full_bar = bars;                        // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;              // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;          // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;     // [2]
+  constexpr int NB = kPairFifoBufs;                 // FIFO ring depth (3: the W' half-stages free the room)
+  constexpr int kIdxOff = NB * kFifoBytes;          // the index arrays sit behind all value buffers
+  uint64_t* ffull_bar = bars + 2 * STAGES + 4;             // [NB buffers][4 quarters]
+  uint64_t* fempty_bar = bars + 2 * STAGES + 4 + 4 * NB;   // [NB][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 8 * NB);
+  uint32_t* meta = tmem_slot + 2;                   // [NB][4]: 1 = last hand-over of the work item
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = ceil_div(ksteps, kBK / 16);
+  // work items are PAIRS of 128-row blocks: CTA rank r of the cluster owns block 2 * pair + r; the
+  // persistent loop strides over pair-items by the number of clusters
+  const uint32_t crank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int total_items = ((num_m_blocks + 1) >> 1) * nsplit;
+  const float neg_inf = __uint_as_float(0xff800000u);
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * kBM);     // leader's: the scanner threads of BOTH CTAs arrive
+    }
+    for (int s = 0; s < 4 * NB; ++s) {
+      mbar_init(&ffull_bar[s], 32);
+      mbar_init(&fempty_bar[s], 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  for (int i = threadIdx.x; i < kBM * 2; i += blockDim.x) reinterpret_cast<uint32_t*>(tau_s)[i] = 0u;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // set-up done under the predecessor's tail; global memory (TMA, results) from here on
+
+  if (warp < 4) {
+    reg_alloc_dec<56>();
+    if (warp == 0) {
+      // ===================== TMA producer (both CTAs): own A rows + own half of the W' tile =====================
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = cluster_id; item < total_items; item += n_clusters) {
+          const int pair = item / nsplit;
+          const int sp = item - pair * nsplit;
+          const int m_blk = 2 * pair + static_cast<int>(crank);
+          const int t0 = sp * tiles_per_split;
+          const int t1 = min(t0 + tiles_per_split, num_n_tiles);
+          for (int nt = t0; nt < t1; ++nt) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+              mbar_wait_sleep<kRoleSleepNs>(&empty_bar[stage], phase ^ 1u);
+              // the leader's full barrier collects the bytes of both CTAs' copies
+              if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kAStage + kBHalfStage));
+              uint8_t* sa = pipe + stage * (kAStage + kBHalfStage);
+              tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+              tma_load_2d_2sm(sa + kAStage, &tmap_w, &full_bar[stage], kb * kBK,
+                              nt * kBN + static_cast<int>(crank) * (kBN / 2));
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    } else if (warp == 1 && crank == 0) {
+      // ===================== MMA issuer (leader CTA only): 256 x 256 x 16 across the CTA pair =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, kBN);
+      int stage = 0;
+      uint32_t phase = 0, tile = 0;
+      for (int item = cluster_id; item < total_items; item += n_clusters) {
+        const int sp = item - (item / nsplit) * nsplit;
+        const int t0 = sp * tiles_per_split;
+        const int t1 = min(t0 + tiles_per_split, num_n_tiles);
+        for (int nt = t0; nt < t1; ++nt, ++tile) {
+          const uint32_t as = tile & 1u;
+          const uint32_t aphase = (tile >> 1) & 1u;
+          mbar_wait_sleep<kRoleSleepNs>(&tempty_bar[as], aphase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + as * kBN;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait_sleep<kRoleSleepNs>(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sa = smem_u32(pipe + stage * (kAStage + kBHalfStage));
+              const uint64_t da = umma_desc_sw128_kmajor(sa);
+              const uint64_t db = umma_desc_sw128_kmajor(sa + kAStage);
+              const int nks = min(kBK / 16, ksteps - kb * (kBK / 16));
+              for (int ks = 0; ks < nks; ++ks)
+                umma_bf16_2sm(tmem_d, da + static_cast<uint64_t>(2 * ks), db + static_cast<uint64_t>(2 * ks),
+                              idesc, (kb | ks) != 0 ? 1u : 0u);
+              umma_commit_2sm(&empty_bar[stage]);                      // both CTAs' producers
+              if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[as]);   // both CTAs' scanners
+            }
+            __syncwarp();
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== scanner =====================
+    reg_alloc_dec<152>();
+    const int q = warp - 4;
+    const int row_in_blk = q * 32 + lane;
+    const uint32_t fv0 = smem_u32(fifo) + row_in_blk * 4;          // buffer 0, slot 0 of this row
+    const uint32_t tau_addr = smem_u32(tau_s) + row_in_blk * 8;
+    const uint32_t cnt_addr = smem_u32(cnt_s) + row_in_blk * 2;
+    uint32_t st = 0, seq = 0, tile = 0;      // st: bit 0 = FIFO buffer in use, bits 1/2 = fill parities
+    unsigned long long d_hand = 0, d_wait_e = 0, d_wait_t = 0;
+    const long long d_t0 = clock64();
+    for (int item = cluster_id; item < total_items; item += n_clusters) {
+      const int sp = item - (item / nsplit) * nsplit;
+      const int t0 = sp * tiles_per_split;
+      const int t1 = min(t0 + tiles_per_split, num_n_tiles);
+      ++seq;
+      // mode 3 (experiments): nothing passes the filter - times the GEMM pipeline + bare scan
+      float tau = (DBG && mode >= 3) ? __uint_as_float(0x7f800000u) : neg_inf;
+      mbar_wait_backoff(&fempty_bar[(st & 3u) * 4 + q], ((st >> (2u + (st & 3u))) & 1u) ^ 1u);
+      uint32_t wbase = fv0 + (st & 3u) * kFifoBytes;
+      uint32_t waddr = wbase;
+      uint32_t wlimit = wbase + (kFifo - kCheck) * (kBM * 4);
+
+      for (int nt = t0; nt < t1; ++nt, ++tile) {
+        const uint32_t as = tile & 1u;
+        const uint32_t aphase = (tile >> 1) & 1u;
+        {
+          const long long t = DBG ? clock64() : 0;
+          mbar_wait(&tfull_bar[as], aphase);
+          if (DBG) d_wait_t += clock64() - t;
+        }
+        tc_fence_after();
+        const int col0 = nt * kBN;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBN;
+
+        // ---- first tile of a work item: a floor for the row's threshold before anything is scanned ----
+        // The tile's 256 columns form 32 groups of 8; the smallest of the 32 group maxima has at
+        // least 32 >= k values at or above it, so the row's k-th largest value cannot be below it.
+        // Starting from (just under) that floor instead of -inf, the first tile passes ~40 % of
+        // its values instead of all of the first ~120 columns: about two hand-overs fewer per item,
+        // in the part of the item where the selector is the bottleneck.  Costs one extra read of
+        // the tile (16 tcgen05.ld) and ~0.6 instructions per value while the selector is idle.
+        // Padding columns (-3.39e38) only make the floor useless, never wrong.  (k <= 32 here.)
+        if (nt == t0 && !(DBG && mode >= 3)) {
+          float floor_v = __uint_as_float(0x7f800000u);
+          uint32_t rp[16];
+#pragma unroll 1
+          for (int c = 0; c < kBN; c += 16) {
+            tmem_ld16(taddr + c, rp);
+            tmem_ld_wait16(rp);
+            const float m0 = fmaxf(fmaxf(fmaxf(__uint_as_float(rp[0]), __uint_as_float(rp[1])),
+                                         fmaxf(__uint_as_float(rp[2]), __uint_as_float(rp[3]))),
+                                   fmaxf(fmaxf(__uint_as_float(rp[4]), __uint_as_float(rp[5])),
+                                         fmaxf(__uint_as_float(rp[6]), __uint_as_float(rp[7]))));
+            const float m1 = fmaxf(fmaxf(fmaxf(__uint_as_float(rp[8]), __uint_as_float(rp[9])),
+                                         fmaxf(__uint_as_float(rp[10]), __uint_as_float(rp[11]))),
+                                   fmaxf(fmaxf(__uint_as_float(rp[12]), __uint_as_float(rp[13])),
+                                         fmaxf(__uint_as_float(rp[14]), __uint_as_float(rp[15]))));
+            floor_v = fminf(floor_v, fminf(m0, m1));
+          }
+          // candidates must be strictly above the threshold: step to the next float below the floor
+          // so that values EQUAL to it still pass.  NaN maxima (NaN rows) leave tau at -inf.
+          if (floor_v == floor_v) tau = fmaxf(tau, key2f(f2key(floor_v) - 1u));
+        }
+
+        // ---- scan of one 128x256 accumulator tile, 32 columns (two tcgen05.ld.x16) per trip ----
+        // A taken branch costs a lone warp ~45-60 cycles (instruction-fetch bubble) and ptxas lays a
+        // rare `if (overflow) handoff();` block inline, i.e. the COMMON path takes a skip-branch at
+        // every overflow check - four per trip, a third of the scan time.  So the hot trip has no
+        // branch at all: an overflow check only folds its vote into `need`, and from then on the
+        // filter is closed (threshold +inf) for the rest of the trip.  The single branch per trip is
+        // the loop back-edge, which also tests `need`; when it falls through, the cold code below
+        // hands the FIFO over and re-scans the groups of that trip that ran with the filter closed.
+        auto scan8 = [&](const uint32_t (&r)[16], int j0, int cbase, float thr) {
+          const uint32_t c = static_cast<uint32_t>(cbase + j0);
+          waddr = append4<kIdxOff>(waddr, thr, __uint_as_float(r[j0]), __uint_as_float(r[j0 + 1]),
+                                       __uint_as_float(r[j0 + 2]), __uint_as_float(r[j0 + 3]), c, c + 1,
+                                       c + 2, c + 3, slot);
+          waddr = append4<kIdxOff>(waddr, thr, __uint_as_float(r[j0 + 4]), __uint_as_float(r[j0 + 5]),
+                                       __uint_as_float(r[j0 + 6]), __uint_as_float(r[j0 + 7]), c + 4,
+                                       c + 5, c + 6, c + 7, slot);
+        };
+        auto handoff = [&]() {
+          st = scanner_handoff_ring<DBG, NB>(st, (waddr - wbase) / (kBM * 4), 0u, cnt_addr, meta + q,
+                                             ffull_bar + q, fempty_bar + q, lane, &d_wait_e);
+          ++d_hand;
+          wbase = fv0 + (st & 3u) * kFifoBytes;
+          waddr = wbase;
+          wlimit = wbase + (kFifo - kCheck) * (kBM * 4);
+        };
+        const float pos_inf = __uint_as_float(0x7f800000u);
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr, ra);
+        int c2 = 0;
+        while (true) {
+          bool need = false;
+          int done = 0;            // groups of 8 columns of the current trip scanned with the filter open
+#pragma unroll 1
+          do {
+            const uint32_t ta = taddr + c2 * 32;
+            const int cb = col0 + c2 * 32;
+            uint32_t tb, tq;   // the selector's latest threshold for this row (valid for this item only)
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tb), "=r"(tq) : "r"(tau_addr) : "memory");
+            tmem_ld_wait16(ra);
+            tmem_ld16(ta + 16, rb);
+            if (tq == seq) tau = fmaxf(tau, __uint_as_float(tb));
+            float thr = tau;
+            done = 0;
+            if (DBG && mode == 4) {        // experiments: TMEM reads only (one compare keeps the loads live)
+              if (__uint_as_float(ra[0]) == tau) waddr += 4;
+              tmem_ld_wait16(rb);
+              if (c2 + 1 < kBN / 32) tmem_ld16(ta + 32, ra);
+              if (__uint_as_float(rb[0]) == tau) waddr += 4;
+            } else {
+              scan8(ra, 0, cb, thr);
+              done += need ? 0 : 1;
+              need = need | __any_sync(0xffffffffu, waddr > wlimit);
+              thr = need ? pos_inf : thr;
+              scan8(ra, 8, cb, thr);
+              done += need ? 0 : 1;
+              need = need | __any_sync(0xffffffffu, waddr > wlimit);
+              thr = need ? pos_inf : thr;
+              tmem_ld_wait16(rb);
+              if (c2 + 1 < kBN / 32) tmem_ld16(ta + 32, ra);
+              scan8(rb, 0, cb + 16, thr);
+              done += need ? 0 : 1;
+              need = need | __any_sync(0xffffffffu, waddr > wlimit);
+              thr = need ? pos_inf : thr;
+              scan8(rb, 8, cb + 16, thr);
+              done += need ? 0 : 1;
+              need = need | __any_sync(0xffffffffu, waddr > wlimit);
+            }
+            ++c2;
+          } while (!need && c2 < kBN / 32);
+          if (!need) break;                                  // tile scanned
+          // ---- cold path: hand the FIFO over, re-scan groups [done, 4) of trip c2 - 1 ----
+          // One hand-over call site, in a loop (a second call site after a re-scan made ptxas fail
+          // register allocation).  Every group re-reads its 16-column chunk into rb and ra (the
+          // prefetched first chunk of the next trip) is fetched again afterwards, so no tcgen05.ld
+          // result is live across the call.
+          {
+            const uint32_t ta = taddr + (c2 - 1) * 32;
+            const int cb = col0 + (c2 - 1) * 32;
+            int g = done;
+            bool over = true;
+            while (over) {
+              handoff();
+              over = false;
+#pragma unroll 1
+              while (g < 4 && !over) {
+                tmem_ld16(ta + (g >> 1) * 16, rb);
+                tmem_ld_wait16(rb);
+                if (g & 1) scan8(rb, 8, cb + (g >> 1) * 16, tau);
+                else scan8(rb, 0, cb + (g >> 1) * 16, tau);
+                over = __any_sync(0xffffffffu, waddr > wlimit);
+                ++g;
+              }
+            }
+          }
+          if (c2 >= kBN / 32) break;
+          tmem_ld16(taddr + c2 * 32, ra);      // (again) the first chunk of the next trip
+          continue;
+          if (c2 >= kBN / 32) break;
+        }
+        tc_fence_before();
+        mbar_arrive_leader(&tempty_bar[as]);     // the leader CTA's MMA warp owns the accumulators of both
+      }
+      st = scanner_handoff_ring<DBG, NB>(st, (waddr - wbase) / (kBM * 4), 1u, cnt_addr, meta + q, ffull_bar + q,
+                                         fempty_bar + q, lane, &d_wait_e);
+      ++d_hand;
+    }
+    if (DBG && dbg && lane == 0) {
+      unsigned long long* o = dbg + (static_cast<size_t>(blockIdx.x) * 8 + (warp - 4)) * 8;
+      o[0] = d_hand; o[1] = d_wait_e; o[2] = d_wait_t; o[3] = clock64() - d_t0;
+    }
+  } else {
+    // ===================== selector =====================
+    reg_alloc_inc<232>();
+    const int q = warp - 8;
+    const int row_in_blk = q * 32 + lane;
+    const uint32_t fv0 = smem_u32(fifo) + row_in_blk * 4;
+    const uint32_t tau_addr = smem_u32(tau_s) + row_in_blk * 8;
+    const uint32_t cnt_addr = smem_u32(cnt_s) + row_in_blk * 2;
+    constexpr int N = 2 * kFifo;
+    float v[N];          // [0, kFifo): survivors, [kFifo, N): the batch being merged
+    uint32_t ix[N];
+    uint32_t uses = 0, b = 0, seq = 0;      // uses: bit i = parity of the number of drains of buffer i
+    unsigned long long d_wait_f = 0, d_sel = 0, d_t_load = 0, d_t_select = 0, d_t_repack = 0, d_t_reload = 0, d_t_final = 0;
+    const long long d_t0 = clock64();
+    for (int item = cluster_id; item < total_items; item += n_clusters) {
+      const int m_blk = 2 * (item / nsplit) + static_cast<int>(crank);
+      const int sp = item - (item / nsplit) * nsplit;
+      ++seq;
+      float tau = neg_inf;
+      int scnt = 0;
+#pragma unroll
+      for (int s = 0; s < kFifo; ++s) {
+        v[s] = neg_inf;
+        ix[s] = 0u;
+      }
+      while (true) {
+        {
+          const long long t = DBG ? clock64() : 0;
+          mbar_wait_backoff(&ffull_bar[b * 4 + q], (uses >> b) & 1u);
+          if (DBG) d_wait_f += clock64() - t;
+        }
+        const uint32_t base = fv0 + b * kFifoBytes;
+        unsigned short n16;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(n16) : "r"(cnt_addr + b * (kBM * 2)) : "memory");
+        const int n = static_cast<int>(n16);
+        const uint32_t last = meta[b * 4 + q];
+        long long tt0 = DBG ? clock64() : 0;
+#pragma unroll
+        for (int s = 0; s < kFifo; ++s) {
+          const float x = lds_f32(base + s * (kBM * 4));
+          v[kFifo + s] = (s < n) ? x : neg_inf;
+          ix[kFifo + s] = lds_u32(base + s * (kBM * 4) + kIdxOff);
+        }
+        if (DBG) { const long long t = clock64(); d_t_load += t - tt0; tt0 = t; }
+        const int total = scnt + n;
+        float thr = neg_inf;
+        bool ties = false;
+        int tie_left = 0;
+        // the item's last batch is reduced to EXACTLY k (slack 0; ties keep the lowest feature
+        // index), so the survivors re-read below are the result - no separate finalisation pass
+        const int slack = last ? 0 : kSlack;
+        if (__any_sync(0xffffffffu, total > k + slack)) {
+          thr = select_threshold<N>(v, total, k, slack, tau, ties, tie_left);
+          ++d_sel;
+        }
+        if (DBG) { const long long t = clock64(); d_t_select += t - tt0; tt0 = t; }
+        // repack the survivors (old ones first: ascending feature index) through the drained FIFO
+        uint32_t w = base;
+        if (!__any_sync(0xffffffffu, ties)) {
+#pragma unroll
+          for (int s = 0; s < N; s += 4)
+            w = append4<kIdxOff>(w, thr, v[s], v[s + 1], v[s + 2], v[s + 3], ix[s], ix[s + 1],
+                                     ix[s + 2], ix[s + 3], slot);
+        } else {
+#pragma unroll
+          for (int s = 0; s < N; ++s) {
+            const bool tie = ties && (v[s] == thr) && tie_left > 0;
+            tie_left -= tie ? 1 : 0;
+            if (v[s] > thr || tie) {
+              asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.u32 [%0+%3], %2;" ::"r"(w), "f"(v[s]),
+                           "r"(ix[s]), "n"(kIdxOff)
+                           : "memory");
+              w += kBM * 4;
+            }
+          }
+        }
+        scnt = static_cast<int>((w - base) / (kBM * 4));
+        if (DBG) { const long long t = clock64(); d_t_repack += t - tt0; tt0 = t; }
+#pragma unroll
+        for (int s = 0; s < kFifo; ++s) {
+          const float x = lds_f32(base + s * (kBM * 4));
+          v[s] = (s < scnt) ? x : neg_inf;
+          ix[s] = lds_u32(base + s * (kBM * 4) + kIdxOff);
+        }
+        if (DBG) { const long long t = clock64(); d_t_reload += t - tt0; tt0 = t; }
+        if (thr > tau) {
+          tau = thr;
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(tau_addr), "r"(__float_as_uint(tau)),
+                       "r"(seq)
+                       : "memory");
+        }
+        mbar_arrive(&fempty_bar[b * 4 + q]);
+        uses ^= 1u << b;
+        b = (b + 1 == NB) ? 0u : b + 1;
+        if (last) break;
+      }
+      // ---- write the row's k (value, index) pairs: v[0 .. scnt) in ascending feature index ----
+      const long long tf0 = DBG ? clock64() : 0;
+      const int row = m_blk * kBM + row_in_blk;
+      if (row < B) {
+        float* ov = out_val + (static_cast<size_t>(row) * nsplit + sp) * k;
+        int32_t* oi = out_idx + (static_cast<size_t>(row) * nsplit + sp) * k;
+        if ((k & 3) == 0) {          // 16-byte stores (rows of k * 4 bytes stay 16-byte aligned)
+#pragma unroll
+          for (int s = 0; s < 32; s += 4) {
+            if (s < k) {
+              // fewer than k candidates (split narrower than k, NaN rows): pad with (-inf, -1)
+              const int4 iv = make_int4(s < scnt ? static_cast<int>(ix[s]) : -1,
+                                        s + 1 < scnt ? static_cast<int>(ix[s + 1]) : -1,
+                                        s + 2 < scnt ? static_cast<int>(ix[s + 2]) : -1,
+                                        s + 3 < scnt ? static_cast<int>(ix[s + 3]) : -1);
+              *reinterpret_cast<float4*>(ov + s) = make_float4(v[s], v[s + 1], v[s + 2], v[s + 3]);
+              *reinterpret_cast<int4*>(oi + s) = iv;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < 32; ++s) {
+            if (s < k) {
+              ov[s] = v[s];
+              oi[s] = s < scnt ? static_cast<int32_t>(ix[s]) : -1;
+            }
+          }
+        }
+      }
+      if (DBG) d_t_final += clock64() - tf0;
+    }
+    if (DBG && dbg && lane == 0) {
+      unsigned long long* o = dbg + (static_cast<size_t>(blockIdx.x) * 8 + (warp - 4)) * 8;
+      o[0] = d_sel; o[1] = d_wait_f; o[3] = clock64() - d_t0;
+      o[2] = d_t_load; o[4] = d_t_select; o[5] = d_t_repack; o[6] = d_t_reload; o[7] = d_t_final;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // no CTA leaves (or frees TMEM) while its peer may still signal / use it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Merge of per-split partial top-k lists: part_[B, nsplit*k] -> out_[B, k].  One warp per row.
 // Candidate order (split, slot) is ascending feature index, so "first tie wins" = lowest index.
@@ -1307,7 +1858,56 @@ static int launch_encode2(const CUtensorMap& ta, const CUtensorMap& tw, int B, i
   return static_cast<int>(cudaGetLastError());
 }
 
-static int g_encode_variant = 2;   // 1 = single epilogue warp per quarter, 2 = scanner + selector
+// CTA-pair launch: 2-CTA clusters, one cluster per pair of SMs.
+template <int STAGES>
+static int launch_encode3(const CUtensorMap& ta, const CUtensorMap& tw_half, int B, int F, int k,
+                          int ksteps, int num_m_blocks, int num_n_tiles, int nsplit,
+                          int tiles_per_split, float* out_val, int32_t* out_idx, int num_sms,
+                          cudaStream_t stream) {
+  constexpr int smem = Encode3Smem<STAGES>::kTotal;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(encode_topk3_kernel<STAGES, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(encode_topk3_kernel<STAGES, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set[dev] = true;
+  }
+  const int total = ((num_m_blocks + 1) / 2) * nsplit;
+  int clusters = num_sms / 2;
+  if (total < clusters) clusters = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  cudaError_t e;
+  if (g_encode_dbg_buf != nullptr)
+    e = cudaLaunchKernelEx(&cfg, encode_topk3_kernel<STAGES, true>, ta, tw_half, B, F, k, ksteps, num_m_blocks,
+                           num_n_tiles, nsplit, tiles_per_split, out_val, out_idx, g_encode_dbg_buf,
+                           g_encode_dbg, static_cast<uint32_t>(kBM * 4));
+  else
+    e = cudaLaunchKernelEx(&cfg, encode_topk3_kernel<STAGES, false>, ta, tw_half, B, F, k, ksteps, num_m_blocks,
+                           num_n_tiles, nsplit, tiles_per_split, out_val, out_idx,
+                           static_cast<unsigned long long*>(nullptr), 0, static_cast<uint32_t>(kBM * 4));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return static_cast<int>(cudaGetLastError());
+}
+
+static int g_encode_variant = 0;   // 0 = per-batch choice (default), 1 = single epilogue warp per quarter, 2 = scanner + selector, 3 = 2 + CTA pairs (cta_group::2)
 
 }  // namespace wsae
 
@@ -1353,7 +1953,21 @@ extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int 
 #ifndef WSAE_K1_STAGES
 #define WSAE_K1_STAGES 3
 #endif
-  if (k + kSlack <= kFifo && g_encode_variant == 2)
+#ifndef WSAE_K1_PAIR_STAGES
+#define WSAE_K1_PAIR_STAGES 4
+#endif
+  // CTA-pair kernel (cta_group::2) by default once the batch fills the pairs (>= 1024 rows): 221 vs 231 us
+  // at 384 -> 3072, 527 vs 564 us at 768 -> 6144, 2610 vs 3145 us at 1280 -> 40960 (B = 75776 / 37888;
+  // tools/check_k1_pair.py, results bit-identical); tiny batches keep the single-CTA kernel (no cluster
+  // set-up cost).  wsae_debug_encode_variant: 2 = always single-CTA, 3 = always pairs, 0 = this choice.
+  const bool use_pair = g_encode_variant == 3 || (g_encode_variant == 0 && B >= 1024);
+  if (k + kSlack <= kFifo && use_pair) {
+    CUtensorMap tw_half;    // this CTA's half of a W' tile: 128 feature rows per box
+    rc = make_tmap_bf16(&tw_half, w_packed, static_cast<uint64_t>(Fp), static_cast<uint64_t>(Kp), kBN / 2);
+    if (rc) return rc;
+    rc = launch_encode3<WSAE_K1_PAIR_STAGES>(ta, tw_half, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
+                                             tiles_per_split, kv, ki, num_sms, stream);
+  } else if (k + kSlack <= kFifo && (g_encode_variant == 2 || g_encode_variant == 0))
     rc = launch_encode2<WSAE_K1_STAGES>(ta, tw, B, F, k, ksteps, num_m_blocks, num_n_tiles, nsplit,
                            tiles_per_split, kv, ki, num_sms, stream);
   else if (k <= 32)
