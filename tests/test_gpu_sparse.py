@@ -108,7 +108,8 @@ def test_backward_sparse_fp32(B, d, F, k):
 
 
 FUSED_SHAPES = [(1, 32, 128, 4), (33, 64, 256, 8), (64, 384, 3072, 32), (257, 768, 1024, 32),
-                (40, 1280, 2048, 32), (300, 392, 512, 17)]
+                (40, 1280, 2048, 32), (300, 392, 512, 17), (70, 128, 512, 17), (130, 256, 300, 5),
+                (1000, 1536, 640, 32)]
 
 
 def test_decode_backward_fused_rejects_fp32_decoder():

@@ -18,7 +18,7 @@ ALL_FIRED = False
 
 
 def run(B, d, F, k, mode, reps=20):
-    """mode: 0 = the library's per-shape choice, 1 = general (register staged), 2 = mma.sync dots, 3 = staged (cp.async ring)"""
+    """mode: 0 = the library's per-shape choice, 1 = general (register staged), 2 = mma.sync dots, 3 = staged (cp.async ring), 4 = tensor form (both contractions on mma.sync)"""
     lib = _lib.load()
     lib.wsae_debug_decode_backward_general(mode)
     g = torch.Generator().manual_seed(1)
@@ -68,7 +68,8 @@ def main():
         k = 32
         t_gen, m_gen, o_gen = run(B, d, F, k, 1)
         t_mma, m_mma, _ = run(B, d, F, k, 2)
-        t_fast, m_fast, o_fast = run(B, d, F, k, 3)
+        t_fast, m_fast, o_staged = run(B, d, F, k, 3)
+        t_tc, m_tc, o_fast = run(B, d, F, k, 4)
         t_auto, _, _ = run(B, d, F, k, 0)
         gather = B * k * d * 2
         errs = []
@@ -79,8 +80,8 @@ def main():
             else:
                 errs.append(f"{name} rel-L2 {((a - b).norm() / b.norm().clamp_min(1e-30)).item():.1e}")
         print(f"B={B} d={d} F={F}: general {t_gen * 1e3:.1f} us (min {m_gen * 1e3:.1f}), mma {t_mma * 1e3:.1f} us, "
-              f"staged {t_fast * 1e3:.1f} us (min {m_fast * 1e3:.1f}) = {gather / t_fast / 1e6:.0f} GB/s gathered; "
-              f"library choice {t_auto * 1e3:.1f} us; staged vs general: " + "; ".join(errs))
+              f"staged {t_fast * 1e3:.1f} us (min {m_fast * 1e3:.1f}), tensor form {t_tc * 1e3:.1f} us (min {m_tc * 1e3:.1f}) = "
+              f"{gather / t_tc / 1e6:.0f} GB/s gathered; library choice {t_auto * 1e3:.1f} us; tensor form vs general: " + "; ".join(errs))
 
 
 if __name__ == "__main__":

@@ -1,6 +1,8 @@
 set -x
 O=gpurun_out
-timeout 300 python tools/bench_k23.py > $O/r2d_k23.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_sparse.py tests/test_gpu_module.py tests/test_gpu_fullsize.py -q -s > $O/r2d_pytest.log 2>&1; echo "rc=$?" >> $O/r2d_pytest.log
-timeout 300 python bench.py --no-side-workloads --no-cpu-baseline > $O/r2d_bench.json 2> $O/r2d_bench.err
-cat $O/r2d_k23.txt; tail -4 $O/r2d_pytest.log
+T=${1:-r2u}
+for PF in 0 1 2 3 5; do
+  WSAE_K23_PF=$PF WSAE_K23_TC_CFG=32 timeout 300 python tools/bench_k23.py --all-fired --shapes 75776x384x3072,75776x768x6144,37888x1280x40960 > $O/${T}_k23_pf$PF.txt 2>&1
+done
+WSAE_K23_PF=2 timeout 600 python -m pytest tests/test_gpu_sparse.py -q -x -k fused > $O/${T}_pytest.log 2>&1; echo "rc=$?" >> $O/${T}_pytest.log
+tail -n 4 $O/${T}_pytest.log; cut -c1-250 $O/${T}_k23_*.txt

@@ -629,6 +629,411 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
   }
 }
 
+// ================================================================================================
+// K23, tensor form (d % 128 == 0): fragment-order gather, dot products on the warp-level tensor pipe,
+// the next 64 columns in flight while the current ones are multiplied.
+//
+// ncu of the staged kernel above (profiles/r2_k23_staged_ncu.txt): 1784 warp instructions per
+// activation row at d = 384 and the issue slots 48 % busy with 8 warps per SM - the FHFMA form spends
+// one instruction per (gathered row, 4 columns) on the reconstruction, another on the dot products,
+// 64 shuffles per slice to broadcast (offset, h_j) and a 31-step shuffle transpose to reduce the 32
+// partial sums.  The L2 gather itself (tools/l2_gather_bench: 115 us for the same bytes) is not
+// what holds it at 223 us.  A first tensor form that ran BOTH contractions as mma.sync (fragments
+// parked in shared memory, ldmatrix.trans for the reconstruction) halved the instruction count but
+// moved every gathered byte through the LSU data pipe three times (LDG, STS, LDSM): 353 wavefronts per
+// 128 columns, pipe 88 % busy, 341 us (profiles/r2_k23_tc_ldsm_rejected.txt).  This form moves them
+// once:
+//   * lane (rho = lane / 8, chi = lane % 8) loads, for its 8 entries j = 4 i + rho, the 16-byte
+//     chunk chi of a 64-column half slice: one LDG.128 covers 4 rows x 128 contiguous bytes
+//     (4 wavefronts per 512 B; the 8-rows-x-64-B pattern a plain A-fragment load needs costs 8).
+//   * dot products: the four registers of a load are the A fragments of two mma.m16n8k16 whose 16
+//     "rows" are (entry, column half beta = chi / 4) pairs: fragment row lane / 4 = 2 rho + beta reads
+//     entry 4 i + rho over the columns 32 beta + 8 q + .., and column n = beta of B carries the bf16
+//     residual of that half (lanes 0-3 and 4-7 load different 16-byte pieces of it).  D[2 rho + beta][beta]
+//     is the partial dot product over one half; the two halves meet in one shuffle at the end of
+//     the activation row.  8 HMMA per 64 columns, accumulators (16 registers) live across the row.
+//   * reconstruction: the lane holds 8 entries x 8 columns, so the products h_j * W[j][c] are FHFMA
+//     in registers with the activations h_j fetched ONCE per activation row (8 shuffles, not 32 per
+//     slice), and the sum over the 4 entry groups rho is a 2-step shuffle transpose (6 exchanges)
+//     that leaves every lane with 2 adjacent columns: coalesced 8-byte target loads, 4-byte bf16
+//     residual stores.
+// ~140 instructions per 64 columns (FHFMA form: 235), 40 LSU wavefronts; registers hold TWO half
+// slices so the loads of the next one (of this activation row or the next) are in flight during the
+// arithmetic.  Operands are the same bf16 values as in the other forms (bf16 x bf16 products, fp32
+// accumulation), only the order of the fp32 sums differs.
+// ================================================================================================
+constexpr int kTcGBytes = 256;                       // bf16 residual of two half slices (ping-pong), per warp
+
+template <bool kAllocL1>
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 v;
+  if (kAllocL1)
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+  return v;
+}
+// acc[0..3] += bf16x2(w0).{lo,hi}, bf16x2(w1).{lo,hi} times bf16(h.lo)
+__device__ __forceinline__ void fhfma_row4(float* acc, uint32_t w0, uint32_t w1, uint32_t h) {
+  asm("{\n\t"
+      ".reg .b16 a0, a1, c0, c1, h0, h1;\n\t"
+      "mov.b32 {a0, a1}, %4;\n\t"
+      "mov.b32 {c0, c1}, %5;\n\t"
+      "mov.b32 {h0, h1}, %6;\n\t"
+      "fma.rn.f32.bf16 %0, a0, h0, %0;\n\t"
+      "fma.rn.f32.bf16 %1, a1, h0, %1;\n\t"
+      "fma.rn.f32.bf16 %2, c0, h0, %2;\n\t"
+      "fma.rn.f32.bf16 %3, c1, h0, %3;\n\t"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+      : "r"(w0), "r"(w1), "r"(h));
+}
+
+// acc[0..3] += bf16x2(w0).{lo,hi}, bf16x2(w1).{lo,hi} times the HIGH half of h
+__device__ __forceinline__ void fhfma_row4_hi(float* acc, uint32_t w0, uint32_t w1, uint32_t h) {
+  asm("{\n\t"
+      ".reg .b16 a0, a1, c0, c1, h0, h1;\n\t"
+      "mov.b32 {a0, a1}, %4;\n\t"
+      "mov.b32 {c0, c1}, %5;\n\t"
+      "mov.b32 {h0, h1}, %6;\n\t"
+      "fma.rn.f32.bf16 %0, a0, h1, %0;\n\t"
+      "fma.rn.f32.bf16 %1, a1, h1, %1;\n\t"
+      "fma.rn.f32.bf16 %2, c0, h1, %2;\n\t"
+      "fma.rn.f32.bf16 %3, c1, h1, %3;\n\t"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+      : "r"(w0), "r"(w1), "r"(h));
+}
+
+// STAGES half slices live in registers: one being multiplied, STAGES - 1 in flight (d / 64 must be a
+// multiple of STAGES).
+template <int kMinBlocks, int STAGES, bool PF>
+__global__ void __launch_bounds__(kFusedWarps * 32, kMinBlocks)
+decode_backward_tc_kernel(const float* __restrict__ target, const __nv_bfloat16* __restrict__ w_decT,
+                          const float* __restrict__ b_dec, const float* __restrict__ b_pre,
+                          const int32_t* __restrict__ idx, const float* __restrict__ val,
+                          const float* __restrict__ grad_out, float coef, int B, int d, int F, int k,
+                          float* __restrict__ resid, __nv_bfloat16* __restrict__ resid_bf16,
+                          FusedStats* __restrict__ stats, long long* __restrict__ last_activated,
+                          const long long* __restrict__ step_count, float* __restrict__ d_b_enc,
+                          float* __restrict__ d_b_dec, float* __restrict__ dpre_val,
+                          const float* const* __restrict__ target_at,
+                          const long long* const* __restrict__ rows_at, int stamp_words,
+                          long long* __restrict__ det_ws, int pf_dist) {
+  static_assert(STAGES == 2 || STAGES == 3, "two or three half slices in registers");
+  // [d] bias | [warps][d] db_dec partials | [warps] bf16 residual ping-pong + 16 zero bytes | fired bitmap
+  extern __shared__ __align__(16) float fsm[];
+  pdl_prologue();
+  if (target_at != nullptr) target = *target_at;
+  const long long* perm = rows_at != nullptr ? *rows_at : nullptr;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int rho = lane >> 3;                 // entry group: this lane gathers entries 4 i + rho
+  const int chi = lane & 7;                  // 16-byte chunk of the 64-column half slice
+  float* s_bias = fsm;
+  float* s_g = fsm + d + warp * d;
+  char* dyn = reinterpret_cast<char*>(fsm + (1 + kFusedWarps) * d);
+  const uint32_t gbuf = smem_u32(dyn) + warp * kTcGBytes;
+  const uint32_t zbuf = smem_u32(dyn) + kFusedWarps * kTcGBytes;     // 16 zero bytes
+  uint32_t* s_fired = reinterpret_cast<uint32_t*>(dyn + kFusedWarps * kTcGBytes + 16);
+  if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(dyn + kFusedWarps * kTcGBytes)[threadIdx.x] = 0u;
+  for (int i = threadIdx.x; i < stamp_words; i += blockDim.x) s_fired[i] = 0u;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    s_bias[i] = b_dec[i] + (b_pre != nullptr ? b_pre[i] : 0.f);
+#pragma unroll
+    for (int w = 0; w < kFusedWarps; ++w) fsm[d + w * d + i] = 0.f;
+  }
+  __syncthreads();
+
+  const float s = coef * (grad_out != nullptr ? *grad_out : 1.f);
+  const long long stamp = (last_activated != nullptr && step_count != nullptr) ? (*step_count + 1) : 0;
+  const int warp_global = blockIdx.x * kFusedWarps + warp;
+  const int warp_stride = gridDim.x * kFusedWarps;
+  const int nhs = d >> 6;                    // half slices (64 columns) per activation row
+  const char* wbytes = reinterpret_cast<const char*>(w_decT);
+  const size_t row_bytes = static_cast<size_t>(d) * 2;
+  // after the shuffle transpose this lane owns 2 adjacent columns of every half slice
+  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1;
+  const int c0 = 8 * chi + 4 * b4 + 2 * b3;
+  // The bf16 residual of a half slice is parked chunk by chunk (16 bytes = 8 columns) with the column
+  // pairs in the order (0,1) (4,5) (2,3) (6,7): the HMMA below takes an LDG.128 register quad as its A
+  // operand, i.e. fragment row r reads pairs (0,1) | (4,5) and row r + 8 pairs (2,3) | (6,7) of the
+  // lane's chunk, so the matching B pieces are 8 adjacent bytes.
+  const uint32_t g_st = static_cast<uint32_t>(chi * 16 + (b4 + 2 * b3) * 4);
+  // B column n = lane / 4 stands for (column half beta = n & 1, fragment-row half gam = (n >> 1) & 1);
+  // columns 0-3 serve the even entry of a pair, 4-7 the odd one: the other set reads zeros
+  const int nB = lane >> 2;
+  const uint32_t g_ld = static_cast<uint32_t>(((nB & 1) * 4 + (lane & 3)) * 16 + ((nB >> 1) & 1) * 8);
+  const bool lowB = nB < 4;
+
+  float sse_local = 0.f;
+  unsigned int l0_local = 0;
+
+  auto load_meta = [&](int row, int32_t& mi, float& mv) {
+    mi = -1;
+    mv = 0.f;
+    if (row < B && lane < k) {
+      mi = __ldg(idx + static_cast<size_t>(row) * k + lane);
+      mv = __ldg(val + static_cast<size_t>(row) * k + lane);
+    }
+  };
+  // entries that did not fire gather their own row with weight 0; invalid ones a row that differs
+  // per (activation row, lane) - no L2 hot spot (see the staged kernel)
+  auto gather_feature = [&](int32_t mi, int row) -> uint32_t {
+    return (mi >= 0 && mi < F) ? static_cast<uint32_t>(mi)
+                               : (static_cast<uint32_t>(row) * 37u + static_cast<uint32_t>(lane)) % static_cast<uint32_t>(F);
+  };
+  const char* wp[8];                         // this lane's 8 gathered rows (+ its chunk), at the current half slice
+  auto set_row = [&](uint32_t feat) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t f = __shfl_sync(0xffffffffu, feat, 4 * i + rho);
+      wp[i] = wbytes + static_cast<size_t>(f) * row_bytes + chi * 16;
+    }
+  };
+  const float* trow = target;                // this lane's 2 target columns, at the current half slice
+  auto set_target = [&](int row) {
+    const size_t srow = perm != nullptr ? static_cast<size_t>(__ldg(perm + row)) : static_cast<size_t>(row);
+    trow = target + srow * d + c0;
+  };
+  auto gather = [&](uint4 (&w)[8], float2& x, int ahead) {     // `ahead` half slices past the current one
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = ldg_nc_v4<PF>(wp[i] + ahead * 128);
+    x = __ldg(reinterpret_cast<const float2*>(trow + ahead * 64));
+  };
+  // PF: every lane asks for ONE 128-byte line of ITS entry's row, pf_dist half slices past the one
+  // being gathered - a single instruction per half slice brings all 32 lines (4 KB) into L1 without
+  // holding registers; the LDG.128 of the gather then hit L1
+  const char* pf_cur = wbytes;               // row of this lane's entry, this activation row / the next
+  const char* pf_nxt = wbytes;
+  auto prefetch = [&](int h, bool more_rows) {
+    if (!PF) return;
+    const char* p = pf_cur + h * 128;
+    if (h >= nhs) {
+      if (!more_rows || h - nhs >= nhs) return;
+      p = pf_nxt + (h - nhs) * 128;
+    }
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  };
+  auto advance = [&](int n) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wp[i] += n * 128;
+    trow += n * 64;
+  };
+
+  int row = warp_global;
+  int32_t cur_i, nxt_i;
+  float cur_v, nxt_v;
+  load_meta(row, cur_i, cur_v);
+  load_meta(row + warp_stride, nxt_i, nxt_v);
+  uint4 w0[8], w1[8], w2[8];   // w2: three-stage form only (dead otherwise)
+  float2 x0 = make_float2(0.f, 0.f), x1 = x0, x2 = x0;
+  if (row < B) {
+    set_row(gather_feature(cur_i, row));
+    set_target(row);
+    gather(w0, x0, 0);
+    if (STAGES == 3) gather(w1, x1, 1);
+  }
+  if (PF) pf_nxt = wbytes + static_cast<size_t>(gather_feature(cur_i, row)) * row_bytes;
+
+  for (; row < B; row += warp_stride) {
+    const int32_t my_i = cur_i;
+    const bool fired = (my_i >= 0) && (my_i < F) && (cur_v > 0.f);
+    if (fired && last_activated != nullptr) {
+      if (stamp_words > 0) atomicOr(&s_fired[my_i >> 5], 1u << (my_i & 31));
+      else last_activated[my_i] = stamp;
+    }
+    const float my_v = fired ? cur_v : 0.f;
+    const uint32_t my_hb = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(my_v)));
+    const uint32_t mask = __ballot_sync(0xffffffffu, fired);
+    l0_local += (lane == 0) ? __popc(mask) : 0;
+    uint32_t hp[4];                          // bf16 activations of entries 8 m + rho (low half) and 8 m + 4 + rho (high)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const uint32_t lo = __shfl_sync(0xffffffffu, my_hb, 8 * m + rho);
+      const uint32_t hi = __shfl_sync(0xffffffffu, my_hb, 8 * m + 4 + rho);
+      hp[m] = lo | (hi << 16);
+    }
+    const size_t orow = static_cast<size_t>(row) * d + c0;
+    int32_t nn_i = -1;                       // entries two rows ahead
+    float nn_v = 0.f;
+    const bool more = row + warp_stride < B;
+    if (PF) {
+      pf_cur = pf_nxt;
+      pf_nxt = wbytes + static_cast<size_t>(gather_feature(nxt_i, row + warp_stride)) * row_bytes;
+    }
+
+    float dacc[4][4];                        // pair p: entries 8 p + rho (B columns 0-3) and 8 p + 4 + rho (4-7)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) dacc[p][0] = dacc[p][1] = dacc[p][2] = dacc[p][3] = 0.f;
+
+    auto compute = [&](const uint4 (&w)[8], const float2 x, int hs) {
+      // ---- reconstruction partials: 8 entries x 8 columns in this lane ----
+      float part[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) part[c] = 0.f;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        fhfma_row4(part, w[2 * m].x, w[2 * m].y, hp[m]);
+        fhfma_row4(part + 4, w[2 * m].z, w[2 * m].w, hp[m]);
+        fhfma_row4_hi(part, w[2 * m + 1].x, w[2 * m + 1].y, hp[m]);
+        fhfma_row4_hi(part + 4, w[2 * m + 1].z, w[2 * m + 1].w, hp[m]);
+      }
+      // ---- sum over the 4 entry groups (lane bits 4, 3); this lane keeps columns c0, c0 + 1 ----
+      {
+        const bool up = b4 != 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float send = up ? part[c] : part[c + 4];
+          const float keep = up ? part[c + 4] : part[c];
+          part[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool up = b3 != 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float send = up ? part[c] : part[c + 2];
+          const float keep = up ? part[c + 2] : part[c];
+          part[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      // ---- residual, SSE, decoder-bias gradient, bf16 residual ----
+      const int col = hs * 64 + c0;
+      const float2 bias = *reinterpret_cast<const float2*>(s_bias + col);
+      const float r0 = part[0] + bias.x - x.x;
+      const float r1 = part[1] + bias.y - x.y;
+      sse_local = fmaf(r0, r0, sse_local);
+      sse_local = fmaf(r1, r1, sse_local);
+      float2 gs = *reinterpret_cast<float2*>(s_g + col);
+      gs.x += r0;
+      gs.y += r1;
+      *reinterpret_cast<float2*>(s_g + col) = gs;
+      if (resid != nullptr) *reinterpret_cast<float2*>(resid + orow + hs * 64) = make_float2(r0, r1);
+      __nv_bfloat162 rb2 = __floats2bfloat162_rn(r0, r1);
+      const uint32_t rb = *reinterpret_cast<uint32_t*>(&rb2);
+      if (resid_bf16 != nullptr) *reinterpret_cast<uint32_t*>(resid_bf16 + orow + hs * 64) = rb;
+      const uint32_t gb = gbuf + (hs & 1) * 128;
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(gb + g_st), "r"(rb) : "memory");
+      __syncwarp();
+      // ---- dot products: A = one gathered register quad, B = the residual (or zeros) ----
+      uint32_t ge0, ge1, go0, go1;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ge0), "=r"(ge1) : "r"(lowB ? gb + g_ld : zbuf));
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(go0), "=r"(go1) : "r"(lowB ? zbuf : gb + g_ld));
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        mma_bf16_16816(dacc[p], w[2 * p].x, w[2 * p].y, w[2 * p].z, w[2 * p].w, ge0, ge1);
+        mma_bf16_16816(dacc[p], w[2 * p + 1].x, w[2 * p + 1].y, w[2 * p + 1].z, w[2 * p + 1].w, go0, go1);
+      }
+    };
+    auto next_row = [&]() {                  // all of this row's gathers are out: retarget the pointers
+      set_row(gather_feature(nxt_i, row + warp_stride));
+      set_target(row + warp_stride);
+    };
+
+    if constexpr (STAGES == 2) {
+      for (int hs = 0; hs < nhs; hs += 2) {
+        gather(w1, x1, 1);
+        prefetch(hs + 1 + pf_dist, more);
+        if (hs == 0) load_meta(row + 2 * warp_stride, nn_i, nn_v);
+        compute(w0, x0, hs);
+        const bool last = hs + 2 >= nhs;
+        prefetch(hs + 2 + pf_dist, more);
+        if (!last) {
+          gather(w0, x0, 2);
+        } else if (more) {
+          next_row();
+          gather(w0, x0, 0);
+        }
+        compute(w1, x1, hs + 1);
+        if (!last) advance(2);
+      }
+    } else {
+      for (int hs = 0; hs < nhs; hs += 3) {
+        gather(w2, x2, 2);
+        if (hs == 0) load_meta(row + 2 * warp_stride, nn_i, nn_v);
+        compute(w0, x0, hs);
+        const bool last = hs + 3 >= nhs;
+        if (!last) {
+          gather(w0, x0, 3);
+        } else if (more) {
+          next_row();
+          gather(w0, x0, 0);
+        }
+        compute(w1, x1, hs + 1);
+        if (!last) {
+          gather(w1, x1, 4);
+        } else if (more) {
+          gather(w1, x1, 1);
+        }
+        compute(w2, x2, hs + 2);
+        if (!last) advance(3);
+      }
+    }
+
+    // Pair p, lane (r = lane / 4, q = lane % 4): the partial dot product of entry 8 p + 4 (q / 2) + rho
+    // over the column quarter (beta = r & 1, gam = q & 1) is D[r + 8 gam][2 q + beta]; the four
+    // quarters meet through lanes ^ 4 and ^ 1.  Lane j then takes dot[j] from lane 8 (j % 4) + 2 ((j / 4) % 2)
+    // of pair j / 8.
+    const bool beta = (lane & 4) != 0, gam = (lane & 1) != 0;
+    const int src = 8 * (lane & 3) + 2 * ((lane >> 2) & 1);
+    float dot = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float t = gam ? (beta ? dacc[p][3] : dacc[p][2]) : (beta ? dacc[p][1] : dacc[p][0]);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      const float v = __shfl_sync(0xffffffffu, t, src);
+      if ((lane >> 3) == p) dot = v;
+    }
+    const float my_dv = fired ? s * dot : 0.f;
+    if (lane < k) {
+      if (dpre_val != nullptr) dpre_val[static_cast<size_t>(row) * k + lane] = my_dv;
+      if (fired && d_b_enc != nullptr) {
+        if (det_ws != nullptr) det_add(det_ws + my_i, static_cast<double>(dot), kDetScaleEnc);
+        else atomicAdd(d_b_enc + my_i, my_dv);
+      }
+    }
+    cur_i = nxt_i; cur_v = nxt_v;
+    nxt_i = nn_i; nxt_v = nn_v;
+  }
+
+  __shared__ float s_sse[kFusedWarps];
+  __shared__ unsigned int s_l0[kFusedWarps];
+  const float wsum = warp_sum(sse_local);
+  if (lane == 0) {
+    s_sse[warp] = wsum;
+    s_l0[warp] = l0_local;
+  }
+  __syncthreads();
+  if (stamp_words > 0 && last_activated != nullptr)
+    for (int f = threadIdx.x; f < F; f += blockDim.x)
+      if ((s_fired[f >> 5] >> (f & 31)) & 1u) last_activated[f] = stamp;
+  if (d_b_dec != nullptr)
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kFusedWarps; ++w) t += fsm[d + w * d + i];
+      if (det_ws != nullptr) det_add(det_ws + F + i, static_cast<double>(t), kDetScaleDec);
+      else atomicAdd(d_b_dec + i, s * t);
+    }
+  if (threadIdx.x == 0 && stats != nullptr) {
+    double tsum = 0.0;
+    unsigned long long c = 0;
+    for (int w = 0; w < kFusedWarps; ++w) {
+      tsum += static_cast<double>(s_sse[w]);
+      c += s_l0[w];
+    }
+    if (det_ws != nullptr) det_add(det_ws + F + d, tsum, kDetScaleSse);
+    else atomicAdd(&stats->sse, tsum);
+    atomicAdd(&stats->l0_count, c);
+  }
+}
+
 // det_ws (see kDetScale*) -> d_b_enc += s * sum, d_b_dec += s * sum, stats->sse += sum
 __global__ void __launch_bounds__(256)
 det_finish_kernel(const long long* __restrict__ det_ws, int F, int d, const float* __restrict__ grad_out,
@@ -705,7 +1110,62 @@ static int decode_backward_impl(const float* target, const float* const* target_
   //   d = 768:  staged 541 us | mma 451 us | general 461 us   -> mma (the ring leaves room for 8 warps only)
   //   d = 1280: staged 434 us | mma 451 us | general 444 us   -> general (F = 40960: decoder > L2 share)
   //   d % 128 != 0: general
-  // mode (wsae_debug_decode_backward_general): 0 = this choice, 1 = general, 2 = mma, 3 = staged
+  // tensor form (profiles/r2_k23_tensor_form.txt, same boxes): 384: 219-227 us (step 0.769 vs 0.776 ms with
+  //   staged), 768: 393 us, 1280: 379 us with the L2 prefetch, 1536: 715 us  -> the choice for d % 128 == 0
+  // mode (wsae_debug_decode_backward_general): 0 = this choice, 1 = general, 2 = mma, 3 = staged, 4 = tensor form
+  // tensor form (mode 4): the choice for every d % 128 == 0 shape (WSAE_K23_TC=0: the older forms below)
+  static const int want_tc = [] {
+    const char* e = std::getenv("WSAE_K23_TC");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  if ((mode == 4 || (mode == 0 && want_tc)) && d % 128 == 0) {
+    const size_t smem_t = (1 + kFusedWarps) * static_cast<size_t>(d) * sizeof(float) +
+                          static_cast<size_t>(kFusedWarps) * kTcGBytes + 16 +
+                          static_cast<size_t>(stamp_words) * 4;
+    // WSAE_K23_TC = "<blocks per SM: 3|4><stages: 2|3>", e.g. 32 (default 3 blocks; 3 stages where d / 64 % 3 == 0)
+    static const int tc_cfg = [] {
+      const char* e = std::getenv("WSAE_K23_TC_CFG");
+      return (e && e[0] && e[1]) ? (e[0] - '0') * 10 + (e[1] - '0') : 0;
+    }();
+    int per_want = tc_cfg ? tc_cfg / 10 : 3;
+    int stages = tc_cfg ? tc_cfg % 10 : 2;
+    if ((d / 64) % 3 != 0) stages = 2;
+    if (stages == 3) per_want = 3;
+    // L2 prefetch distance (half slices): CCTL.PF1 does not fill L1 here, but it does pull decoder rows
+    // that miss L2 in from HBM early - 452 -> 379 us at 1280 -> 40960 (105 MB decoder), +4 % where the
+    // decoder is L2 resident (profiles/r2_k23_tensor_form.txt).  WSAE_K23_PF overrides.
+    static const int pf_env = [] {
+      const char* e = std::getenv("WSAE_K23_PF");
+      return e ? std::atoi(e) : -1;
+    }();
+    const int pf_dist = pf_env >= 0 ? pf_env : (static_cast<long long>(F) * d * 2 > (64LL << 20) ? 1 : 0);
+    using KernT = decltype(&decode_backward_tc_kernel<3, 2, false>);
+    KernT kern = stages == 3 ? decode_backward_tc_kernel<3, 3, false>
+                             : (per_want == 4 ? (pf_dist > 0 ? decode_backward_tc_kernel<4, 2, true> : decode_backward_tc_kernel<4, 2, false>)
+                                              : (pf_dist > 0 ? decode_backward_tc_kernel<3, 2, true> : decode_backward_tc_kernel<3, 2, false>));
+    static bool attr_tc[64] = {};
+    if (dev >= 64 || !attr_tc[dev]) {
+      cudaError_t e = cudaSuccess;
+      for (KernT kf : {decode_backward_tc_kernel<4, 2, false>, decode_backward_tc_kernel<4, 2, true>,
+                       decode_backward_tc_kernel<3, 2, false>, decode_backward_tc_kernel<3, 2, true>,
+                       decode_backward_tc_kernel<3, 3, false>})
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      if (dev < 64) attr_tc[dev] = true;
+    }
+    if (smem_t <= 220 * 1024) {
+      int per = static_cast<int>((227 * 1024) / (smem_t + 1024));
+      if (per > per_want) per = per_want;
+      if (per < 1) per = 1;
+      int nblk = ceil_div(B, kFusedWarps);
+      if (nblk > sms * per) nblk = sms * per;
+      launch_pdl(kern, nblk, kFusedWarps * 32, smem_t, stream, target, wd, b_dec,
+                 b_pre, idx, val, grad_out, coef, B, d, F, k, resid, rbf, st, last_activated, step_count,
+                 d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, det_ws, pf_dist);
+      return static_cast<int>(cudaGetLastError());
+    }
+  }
   const bool staged_fits3 =
       3 * ((1 + kFusedWarps) * static_cast<size_t>(d) * sizeof(float) + kFusedWarps * 2 * kSliceBytes +
            static_cast<size_t>(stamp_words) * 4 + 1024) <= 227 * 1024;

@@ -16,6 +16,14 @@ gloo in the CPU tests) for the plumbing.
       counters stay bit-exact against the single-device run).
   Clip, AdamW and the decoder renorm then run identically on every rank (deterministic), so the
   replicas stay bit-identical without a weight broadcast.
+* Sharded optimizer (default when ``hidden_dim % world == 0``): the two weight-gradient matrices are
+  REDUCE-SCATTERED by feature rows instead of all-reduced (rank r ends up with the summed rows
+  ``[r F/N, (r+1) F/N)`` of dW_enc and dW_decT), every rank runs clip + AdamW + renorm on its rows
+  only - the optimizer pass and its m/v traffic shrink by 1/N - and the updated rows are ALL-GATHERED
+  back into every replica's parameters (same bytes on the wire as the all-reduce they replace).  The
+  small tensors (biases) are all-reduced and updated on every rank; the clip norm is the all-reduced
+  sum of the per-shard sums of squares.  Feature rows are the natural shard: a decoder row is
+  re-normalised as a whole and the K4 GEMMs write their output feature-major.
 """
 
 from __future__ import annotations
@@ -92,6 +100,46 @@ class TorchDistCommunicator:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
         reduce_step(parts[-1], stats, last_activated, self.group)
 
+    # ---- sharded optimizer: feature rows [rank * R / world, (rank + 1) * R / world) of an [R, c] matrix ----
+    def row_block(self, rows: int) -> tuple[int, int]:
+        per = rows // self.world
+        return self.rank * per, (self.rank + 1) * per
+
+    def _native_scatter(self, t: Tensor) -> bool:
+        # ncclReduceScatter / ncclAllGather in place (recvbuff = sendbuff + rank * count); gloo has no
+        # reduce-scatter: the CPU tests take the all-reduce route, which leaves the same rows
+        return t.is_cuda and dist.get_backend(self.group) == "nccl"
+
+    def reduce_scatter_rows_async(self, t: Tensor):
+        """SUM over ranks of the contiguous ``[R, c]`` matrix ``t``; afterwards this rank's row block
+        holds the sum (the other rows are unspecified).  Returns a handle with ``.wait()``."""
+        a, b = self.row_block(t.shape[0])
+        if self._native_scatter(t):
+            return dist.reduce_scatter_tensor(t[a:b], t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def all_gather_rows(self, t: Tensor) -> None:
+        """Every rank's row block of the contiguous ``[R, c]`` matrix ``t`` -> all replicas, in place."""
+        a, b = self.row_block(t.shape[0])
+        if self._native_scatter(t):
+            dist.all_gather_into_tensor(t, t[a:b], group=self.group)
+            return
+        parts = [torch.empty_like(t[a:b]) for _ in range(self.world)]
+        dist.all_gather(parts, t[a:b].contiguous(), group=self.group)
+        per = t.shape[0] // self.world
+        for r, part in enumerate(parts):
+            t[r * per:(r + 1) * per].copy_(part)
+
+    def all_reduce_sum(self, t: Tensor) -> None:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def reduce_stats(self, stats: Tensor, last_activated: Tensor | None) -> None:
+        """``{sse, l0}`` (SUM) and the fired stamps (MAX): the non-gradient part of ``reduce_step``."""
+        dist.all_reduce(stats[:1].view(torch.float64), op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(stats[1:2], op=dist.ReduceOp.SUM, group=self.group)
+        if last_activated is not None:
+            dist.all_reduce(last_activated, op=dist.ReduceOp.MAX, group=self.group)
+
 
 class ThreadCommunicator:
     """In-process stand-in with the same interface: ``world`` threads of ONE process (one GPU, or
@@ -139,6 +187,36 @@ class ThreadCommunicator:
                 t.add_(p)
         self._exchange([t], combine)
         return _Done()
+
+    def row_block(self, rows: int) -> tuple[int, int]:
+        per = rows // self.world
+        return self.rank * per, (self.rank + 1) * per
+
+    def reduce_scatter_rows_async(self, t: Tensor):
+        a, b = self.row_block(t.shape[0])
+
+        def combine(all_parts):
+            own = torch.zeros_like(t[a:b])
+            for (p,) in all_parts:
+                own.add_(p[a:b])
+            t.fill_(float("nan"))          # the other rows are unspecified: make a wrong read visible
+            t[a:b].copy_(own)
+        self._exchange([t], combine)
+        return _Done()
+
+    def all_gather_rows(self, t: Tensor) -> None:
+        per = t.shape[0] // self.world
+
+        def combine(all_parts):
+            for r, (p,) in enumerate(all_parts):
+                t[r * per:(r + 1) * per].copy_(p[r * per:(r + 1) * per])
+        self._exchange([t], combine)
+
+    def all_reduce_sum(self, t: Tensor) -> None:
+        self.all_reduce_sum_async(t)
+
+    def reduce_stats(self, stats: Tensor, last_activated: Tensor | None) -> None:
+        self.reduce_step([], stats, last_activated)
 
     def reduce_step(self, grads: Tensor | list[Tensor], stats: Tensor, last_activated: Tensor | None) -> None:
         parts = list(grads) if isinstance(grads, (list, tuple)) else [grads]
