@@ -41,7 +41,19 @@ def _gloo_worker(rank: int, world: int, port: int, out_dir: str):
         last[rank::2] = 7                               # each rank stamps its own fired features
         last[0] = 3 if rank == 0 else 0
         comm.reduce_step(g, stats, last)
-        torch.save({"g": g, "stats": stats, "last": last, "world": comm.world, "rank": comm.rank},
+        # sharded-optimizer collectives: rows [rank * R / world, ...) hold the sum after the
+        # reduce-scatter; the all-gather spreads every rank's own rows
+        m = torch.arange(8 * 3, dtype=torch.float32).reshape(8, 3) * (rank + 1)
+        comm.reduce_scatter_rows_async(m).wait()
+        a, b = comm.row_block(8)
+        own = m[a:b].clone()
+        w = torch.full((8, 3), -1.0)
+        w[a:b] = float(rank + 10)
+        comm.all_gather_rows(w)
+        ss = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        comm.all_reduce_sum(ss)
+        torch.save({"g": g, "stats": stats, "last": last, "world": comm.world, "rank": comm.rank,
+                    "own": own, "block": (a, b), "w": w, "ss": ss},
                    os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -59,6 +71,12 @@ def test_reduce_step_gloo_world2(tmp_path):
         want = torch.full((16,), 7, dtype=torch.int64)
         want[0] = 3                                                            # max(3, 0)
         assert torch.equal(o["last"], want)                                    # MAX = union of stamps
+        a, b = o["block"]
+        assert (a, b) == (4 * r, 4 * r + 4)
+        full = torch.arange(8 * 3, dtype=torch.float32).reshape(8, 3) * 3.0    # (1 + 2) x the matrix
+        assert torch.equal(o["own"], full[a:b])
+        assert torch.equal(o["w"], torch.tensor([10.0] * 12 + [11.0] * 12).reshape(8, 3))
+        assert o["ss"].item() == 3.0
 
 
 def test_thread_communicator_cpu():
@@ -84,10 +102,12 @@ def test_thread_communicator_cpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shard", [True, False])
 @pytest.mark.parametrize("use_amp,tol", [(False, 2e-6), (True, 2e-3)])
-def test_batch_sharded_step_matches_single_device(tmp_path, use_amp, tol):
+def test_batch_sharded_step_matches_single_device(tmp_path, use_amp, tol, shard):
     """Two emulated ranks (threads, one GPU) x B/2 rows == one device x B rows: same losses, same
-    counters (bit-exact), same weights after 3 steps."""
+    counters (bit-exact), same weights after 3 steps - with the sharded optimizer (reduce-scatter,
+    AdamW on this rank's feature rows, all-gather) and with the replicated one (all-reduce)."""
     from oracle import topk_sae_oracle as O
     from whisper_sae_b200.config import TrainingConfig
     from whisper_sae_b200.sae import SAETrainer, TopKSAE
@@ -106,7 +126,7 @@ def test_batch_sharded_step_matches_single_device(tmp_path, use_amp, tol):
     single = make()
     ref = [single.train_step(x[s * B:(s + 1) * B]) for s in range(steps)]
     comms = parallel.ThreadCommunicator.make(2)
-    ranks = [make(data_parallel=True, dp_comm=c) for c in comms]
+    ranks = [make(data_parallel=True, dp_comm=c, shard_optimizer=shard) for c in comms]
     got = [[None] * steps for _ in range(2)]
     errors = []
 
@@ -138,6 +158,18 @@ def test_batch_sharded_step_matches_single_device(tmp_path, use_amp, tol):
             torch.testing.assert_close(p, q, rtol=tol * 10, atol=tol * scale, msg=lambda msg: f"{n}: {msg}")
     for p, q in zip(ranks[0].model.parameters(), ranks[1].model.parameters()):
         assert torch.equal(p, q)          # replicas stay bit-identical without a broadcast
+    gs = next(iter(ranks[0]._graphs.values()), None)
+    assert gs is None or gs.shard == shard
+    if shard:       # the moments of the rows a rank does not own are stale until consolidated (collective)
+        ts = [threading.Thread(target=ranks[r].consolidate_optimizer_state) for r in range(2)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        for name in ("exp_avg", "exp_avg_sq"):
+            for p0, p1, ps in zip(ranks[0].model.parameters(), ranks[1].model.parameters(), single.model.parameters()):
+                a, b = ranks[0].optimizer.state[p0][name], ranks[1].optimizer.state[p1][name]
+                assert torch.equal(a, b)
+                ref_t = single.optimizer.state[ps][name]
+                torch.testing.assert_close(a, ref_t, rtol=tol * 50, atol=tol * 10 * ref_t.abs().max().item())
 
 
 @pytest.mark.gpu

@@ -9,7 +9,7 @@ gloo in the CPU tests) for the plumbing.
 * Batch-sharded data parallel (configs 3-4): rows are i.i.d. and the loss is a mean over
   B_global * d, so every rank runs the kernels on B_global / world rows with the *global*
   denominator and ``reduce_step`` combines, per step,
-    - the flat fp32 gradient bucket ``[b_pre | W_enc | b_enc | W_decT | b_dec]``  (SUM),
+    - the flat fp32 gradient bucket ``[b_pre | b_enc | b_dec | W_enc | W_decT]``  (SUM),
     - ``{sse, l0 count}``                                                        (SUM, f64 / i64),
     - the fired stamps ``feature_last_activated``                                (MAX, i64: every
       rank stamps ``step_count + 1``, so MAX is the union of fired features and the dead-feature

@@ -132,7 +132,8 @@ class _GraphedStep:
         F, d = m.hidden_dim, m.input_dim
         # one flat gradient bucket (segments 64-byte aligned): a single memset and a single
         # sum-of-squares pass per step; also the unit a data-parallel all-reduce ships
-        sizes = [d, F * d, F, F * d, d]
+        # layout [b_pre | b_enc | b_dec | W_enc | W_decT]: the three small tensors are one contiguous piece
+        sizes = [d, F, d, F * d, F * d]
         starts, off = [], 0
         for n in sizes:
             starts.append(off)
@@ -145,13 +146,19 @@ class _GraphedStep:
         self.stats = tail[0:3]
         self.sumsq = tail[3:4].view(torch.float64)
         seg = [self.g_flat[s0:s0 + n] for s0, n in zip(starts, sizes)]
-        self.g_b_pre, self.g_b_enc, self.g_b_dec = seg[0], seg[2], seg[4]
-        self.g_w_enc, self.g_w_decT = seg[1].view(F, d), seg[3].view(F, d)
+        self.g_b_pre, self.g_b_enc, self.g_b_dec = seg[0], seg[1], seg[2]
+        self.g_w_enc, self.g_w_decT = seg[3].view(F, d), seg[4].view(F, d)
         # data-parallel exchange in three contiguous pieces: dW_enc starts as soon as its GEMM is
-        # done and overlaps the dW_dec GEMM; [b_pre] and [b_enc | W_decT | b_dec] follow
-        self.g_part_w_enc = self.g_flat[starts[1]:starts[2]]
-        self.g_part_head = self.g_flat[:starts[1]]
-        self.g_part_tail = self.g_flat[starts[2]:]
+        # done and overlaps the dW_dec GEMM; the small tensors and W_decT follow
+        self.g_part_w_enc = self.g_flat[starts[3]:starts[4]]
+        self.g_part_head = self.g_flat[:starts[3]]
+        self.g_part_tail = self.g_flat[starts[4]:]
+        # sharded optimizer (sae/parallel.py): reduce-scatter the two weight-gradient matrices by
+        # feature rows, clip + AdamW + renorm on this rank's rows only, all-gather the updated rows
+        comm = trainer.dp_comm
+        self.shard = bool(trainer.data_parallel and trainer.shard_optimizer and comm is not None
+                          and comm.world > 1 and F % comm.world == 0 and not trainer.deterministic)
+        self.f0, self.f1 = comm.row_block(F) if self.shard else (0, F)
         self._early = None
         self.grads = [self.g_b_pre, self.g_w_enc, self.g_b_enc, self.g_w_decT, self.g_b_dec]
         # what autograd would leave in .grad (decoder.weight's grad is the [d, F] transposed view)
@@ -196,18 +203,49 @@ class _GraphedStep:
     def _body(self) -> None:
         self._compute()
         if self.trainer.data_parallel:      # batch-sharded: exchange gradients / stats / fired stamps
+            self._exchange()
+        self._update_pre()
+        if self.shard:
+            self.trainer.dp_comm.all_reduce_sum(self.sumsq)
+        self._update_opt()
+        if self.shard:
+            self._gather_weights()
+
+    def _exchange(self) -> None:
+        """The per-step collectives behind the kernels (gradients, {sse, l0}, fired stamps)."""
+        comm = self.trainer.dp_comm
+        last = self.trainer.model.feature_last_activated
+        if self.shard:
+            h_enc = self._early if self._early is not None else comm.reduce_scatter_rows_async(self.g_w_enc)
+            h_dec = comm.reduce_scatter_rows_async(self.g_w_decT)
+            comm.all_reduce_sum(self.g_part_head)
+            comm.reduce_stats(self.stats, last)
+            h_enc.wait()
+            h_dec.wait()
+        else:
             parts = [self.g_part_head, self.g_part_tail] if self._early is not None else [self.g_flat]
-            self.trainer.dp_comm.reduce_step(parts, self.stats, self.trainer.model.feature_last_activated)
+            comm.reduce_step(parts, self.stats, last)
             if self._early is not None:
                 self._early.wait()
-                self._early = None
-        self._update()
+        self._early = None
+
+    def _start_early(self) -> None:
+        """dW_enc is final after its GEMM: start its exchange while the dW_dec GEMM runs."""
+        comm = self.trainer.dp_comm
+        self._early = (comm.reduce_scatter_rows_async(self.g_w_enc) if self.shard
+                       else comm.all_reduce_sum_async(self.g_part_w_enc))
+
+    def _gather_weights(self) -> None:
+        m = self.trainer.model
+        comm = self.trainer.dp_comm
+        comm.all_gather_rows(m.encoder.weight.data)
+        comm.all_gather_rows(m.decoder.weight.data.t())     # feature-major storage: [F, d] contiguous
 
     def _compute(self) -> None:
         """Forward + backward kernels of this rank's rows: fills g_flat, stats[0:2], fired stamps."""
         self._compute_a()
         if self._mid["use_gemm"] and self.trainer.data_parallel:   # exchange dW_enc while the dW_dec GEMM runs
-            self._early = self.trainer.dp_comm.all_reduce_sum_async(self.g_part_w_enc)
+            self._start_early()
         self._compute_b()
 
     def _compute_a(self) -> None:
@@ -305,22 +343,37 @@ class _GraphedStep:
             ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre,
                           det_ws=self.det_bpre)
 
-    def _update(self) -> None:
-        """Counters, clip + AdamW + decoder renorm on the (possibly all-reduced) gradient bucket."""
-        m = self.trainer.model
-        d = m.input_dim
+    def _update_pre(self) -> None:
+        """Counters and the gradient sum of squares on the (possibly reduced) gradient bucket."""
         if self.trainer.data_parallel:      # needs the all-reduced stats / fired stamps
             self._counters()
         if self.fork:
             torch.cuda.current_stream().wait_stream(self._side)
-        ops.sumsq_(self.g_flat, self.sumsq, det_ws=self.det_sumsq)
+        if self.shard:
+            # this rank's rows of the two matrices; the (all-reduced) small tensors count once
+            ops.sumsq_(self.g_w_enc[self.f0:self.f1], self.sumsq)
+            ops.sumsq_(self.g_w_decT[self.f0:self.f1], self.sumsq)
+            if self.trainer.dp_comm.rank == 0:
+                ops.sumsq_(self.g_part_head, self.sumsq)
+        else:
+            ops.sumsq_(self.g_flat, self.sumsq, det_ws=self.det_sumsq)
+
+    def _update_opt(self) -> None:
+        """Clip + AdamW + decoder renorm (sharded: on this rank's feature rows and the small tensors)."""
+        m = self.trainer.model
+        d = m.input_dim
         opt_state = self.trainer.optimizer.state
         entries = []
         for p, g in zip(self.params, self.grads):
             st = opt_state[p]
             is_dec = p is m.decoder.weight          # feature-major storage: rows = decoder vectors
             flags = ops.ADAMW_PROJECT_GRAD if (is_dec and self.trainer.project_decoder_grad) else 0
-            entries.append((p.data, g, st["exp_avg"], st["exp_avg_sq"], d if is_dec else 0, flags))
+            pd, ea, es = p.data, st["exp_avg"], st["exp_avg_sq"]
+            if self.shard and p.dim() == 2:
+                if is_dec:
+                    pd, ea, es = pd.t(), ea.t(), es.t()
+                pd, g, ea, es = (t[self.f0:self.f1] for t in (pd, g, ea, es))
+            entries.append((pd, g, ea, es, d if is_dec else 0, flags))
         ops.adamw_multi_(entries, self.hyper, self.sumsq, 1e-12)   # clip + AdamW + decoder renorm
 
     def _counters(self) -> None:
@@ -388,15 +441,15 @@ class _GraphedStep:
             self._ptrs = key
             self.calls = 1
         if self.calls > 1 and tr.cuda_graph == "segments":
-            # data parallel: the kernels between the collectives are three CUDA graphs (compute up to
-            # dW_enc | dW_dec + b_pre gradient | counters + optimizer), the NCCL calls stay eager
-            # between them (capturing them into one graph hung on the 2-GPU box in round 1)
+            # data parallel: the kernels between the collectives are four CUDA graphs (compute up to
+            # dW_enc | dW_dec + b_pre gradient | counters + gradient norm | optimizer), the NCCL calls
+            # stay eager between them (capturing them into one graph hung on the 2-GPU box in round 1)
             if self.graph is None:
                 torch.cuda.synchronize()
                 pool = torch.cuda.graph_pool_handle()
                 before = ops.GPU_LAUNCHES
                 segs = []
-                for part in (self._compute_a, self._compute_b, self._update):
+                for part in (self._compute_a, self._compute_b, self._update_pre, self._update_opt):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, pool=pool):
                         part()
@@ -404,16 +457,18 @@ class _GraphedStep:
                 self.kernels_per_replay = ops.GPU_LAUNCHES - before
                 ops.GPU_LAUNCHES = before
                 self.graph = segs
-            ga, gb, gc = self.graph
-            comm = tr.dp_comm
+            ga, gb, gc, gd = self.graph
             ga.replay()
-            early = comm.all_reduce_sum_async(self.g_part_w_enc) if self._mid["use_gemm"] else None
+            if self._mid["use_gemm"]:
+                self._start_early()
             gb.replay()
-            parts = [self.g_part_head, self.g_part_tail] if early is not None else [self.g_flat]
-            comm.reduce_step(parts, self.stats, tr.model.feature_last_activated)
-            if early is not None:
-                early.wait()
+            self._exchange()
             gc.replay()
+            if self.shard:
+                tr.dp_comm.all_reduce_sum(self.sumsq)
+            gd.replay()
+            if self.shard:
+                self._gather_weights()
             ops.GPU_LAUNCHES += self.kernels_per_replay
         elif self.calls == 1 or tr.cuda_graph in ("eager", "segments"):
             self._body()
@@ -473,6 +528,7 @@ class SAETrainer:
         global_batch_rows: int | None = None,
         project_decoder_grad: bool = False,
         deterministic: bool | None = None,
+        shard_optimizer: bool | None = None,
     ):
         self.model = model.to(device)
         self.config = config
@@ -521,6 +577,11 @@ class SAETrainer:
             deterministic = os.environ.get("WSAE_DETERMINISTIC", "0") == "1"
         self.deterministic = bool(deterministic)
         self.data_parallel = bool(data_parallel)
+        # data parallel: reduce-scatter / sharded AdamW / all-gather instead of all-reduce + replicated
+        # AdamW (sae/parallel.py); WSAE_DP_SHARD=0 or shard_optimizer=False keeps the replicated form
+        if shard_optimizer is None:
+            shard_optimizer = os.environ.get("WSAE_DP_SHARD", "1") != "0"
+        self.shard_optimizer = bool(shard_optimizer)
         self.dp_comm = None
         self.global_batch_rows = global_batch_rows     # default: local rows x world (equal shards)
         if self.data_parallel:
@@ -797,6 +858,7 @@ class SAETrainer:
     def save_checkpoint(self, filename: str) -> Path:
         """Same dict layout as training.py:328-338."""
         path = self.run_dir / filename
+        self.consolidate_optimizer_state()
         payload = {
             "model_state_dict": self.model.state_dict(),
             "optimizer_state_dict": self.optimizer.state_dict(),
@@ -807,6 +869,22 @@ class SAETrainer:
         }
         torch.save(payload, path)
         return path
+
+    def consolidate_optimizer_state(self) -> None:
+        """Sharded optimizer: every rank updates the AdamW moments of ITS feature rows only; gather the
+        rows so that ``optimizer.state_dict()`` is complete on every rank (collective: all ranks call it).
+        A no-op otherwise."""
+        gs = next((g for g in self._graphs.values() if getattr(g, "shard", False)), None)
+        if gs is None:
+            return
+        m = self.model
+        for p in (m.encoder.weight, m.decoder.weight):
+            st = self.optimizer.state.get(p)
+            if not st:
+                continue
+            for name in ("exp_avg", "exp_avg_sq"):
+                t = st[name].t() if p is m.decoder.weight else st[name]
+                self.dp_comm.all_gather_rows(t)
 
     def load_checkpoint(self, path: str | Path) -> None:
         ckpt = torch.load(path, map_location=self.device)
