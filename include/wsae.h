@@ -33,7 +33,7 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 108: + wsae_pack_activations_rows_at, wsae_decode_backward_rows_at, adamw flags). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 109: + wsae_encode_topk_dense). */
 int wsae_abi_version(void);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
@@ -74,6 +74,14 @@ int wsae_encode_topk(const void* a_packed, const void* w_packed, int B, int Bp, 
                      int Kp, int k_used_cols, int k, int nsplit, float* part_val,
                      int32_t* part_idx, float* out_val /*[B,k]*/, int32_t* out_idx /*[B,k]*/,
                      wsae_stream_t stream);
+
+/* Small-batch form (the shipped configs/tiny_default.yaml trains on 128-row batches): the same GEMM
+ * stores its [B,F] pre-activations to `pre_ws` (B*F floats of scratch, L2 resident at these sizes) and
+ * one thread block per row selects the k largest with a radix select - no F-split, no merge.  Same
+ * values and tie rule as wsae_encode_topk; output in ascending feature index.  F <= 49152, F % 4 == 0. */
+int wsae_encode_topk_dense(const void* a_packed, const void* w_packed, int B, int Bp, int F, int Fp,
+                           int Kp, int k_used_cols, int k, float* pre_ws, float* out_val /*[B,k]*/,
+                           int32_t* out_idx /*[B,k]*/, wsae_stream_t stream);
 
 /* ---- K2: k-sparse decode + MSE + L0 + fired stamps (sae/model.py:116,129,145,148,174-181) -----
  * recon = sum_j relu(val_j) * W_decT[idx_j,:] + b_dec (+ b_pre);  resid = recon - target.

@@ -178,3 +178,46 @@ def test_rejects_cpu_and_bad_k():
     w = ops.pack_encoder(torch.randn(16, 32, device="cuda"), None, 1)
     with pytest.raises(RuntimeError):
         ops.encode_topk(a, w, 4, 16, 32, 1, k=17)
+
+
+@pytest.mark.parametrize("B,d,F,k", [(128, 384, 3072, 32), (64, 384, 3072, 32), (130, 96, 400, 16),
+                                     (1000, 128, 1024, 32), (16, 64, 128, 64), (256, 768, 6144, 32)])
+def test_small_batch_dense_form_equals_fused(B, d, F, k):
+    """wsae_encode_topk_dense (GEMM -> [B,F] scratch -> radix select per row, the route of batches up
+    to 1024 rows) returns the same index sets and bit-identical values as the fused epilogue."""
+    ops = _ops()
+    torch.manual_seed(B + F)
+    state = O.init_state(d, F)
+    state["b_pre"] = torch.randn(d) * 0.05
+    x = O.synthetic_activations(B, d, seed=B + 3)
+    for terms in (1, 6):
+        a = ops.pack_activations(x.cuda(), state["b_pre"].cuda(), terms)
+        w = ops.pack_encoder(state["encoder.weight"].cuda(), state["encoder.bias"].cuda(), terms)
+        i_d, v_d = ops.encode_topk(a, w, B, F, d, terms, k)            # dense route (B <= 1024)
+        i_f, v_f = ops.encode_topk(a, w, B, F, d, terms, k, nsplit=1)  # fused epilogue
+        torch.cuda.synchronize()
+        o_d, o_f = torch.sort(i_d, -1), torch.sort(i_f, -1)
+        assert torch.equal(o_d.values, o_f.values)
+        assert torch.equal(v_d.gather(-1, o_d.indices), v_f.gather(-1, o_f.indices))
+        assert torch.equal(o_d.indices, torch.arange(k, device="cuda").expand(B, k)), "ascending feature order"
+
+
+def test_small_batch_dense_form_nan_rows_and_ties():
+    """Rows with NaN inputs: NaN pre-activations are never selected, the list is padded with
+    (-inf, -1) like the fused epilogue; equal values keep the lowest indices."""
+    ops = _ops()
+    d, F, k, B = 64, 512, 8, 6
+    state = O.init_state(d, F)
+    state["encoder.bias"] = torch.full((F,), 0.25)
+    x = torch.zeros(B, d)
+    x[2] = float("nan")
+    a = ops.pack_activations(x.cuda(), None, 1)
+    w = ops.pack_encoder(state["encoder.weight"].cuda(), state["encoder.bias"].cuda(), 1)
+    idx, val = ops.encode_topk(a, w, B, F, d, 1, k)
+    idx_f, val_f = ops.encode_topk(a, w, B, F, d, 1, k, nsplit=1)
+    torch.cuda.synchronize()
+    good = [0, 1, 3, 4, 5]
+    assert torch.equal(idx[good].cpu(), torch.arange(k, dtype=torch.int32).expand(len(good), k))
+    assert (val[good] == 0.25).all()
+    assert (idx[2] == -1).all() and torch.isinf(val[2]).all() and (val[2] < 0).all()
+    assert torch.equal(torch.sort(idx_f, -1).values, torch.sort(idx, -1).values)

@@ -70,6 +70,11 @@ _SIGNATURES = {
          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
         c_int,
     ),
+    "wsae_encode_topk_dense": (
+        [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+         c_void_p, c_void_p, c_void_p, c_void_p],
+        c_int,
+    ),
     "wsae_decode_mse": (
         [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

@@ -1769,6 +1769,278 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
   }
 }
 
+// ================================================================================================
+// K1 for SMALL batches (the shipped configs/tiny_default.yaml trains on 128 rows): dense
+// pre-activations + one block per row.
+//
+// With fewer 128-row blocks than SMs the fused epilogue is pure latency: one work item at B = 128 is
+// TMA -> 7 k-blocks of MMA -> scan of 256 columns with ~3 hand-overs/selections (the row starts at
+// threshold -inf) -> write, and the 12 partial lists per row then go through topk_merge_kernel:
+// 38-41 us for K1 + merge from 128 to 4096 rows (tools/bench_k1_small.py), 40 % of the 105 us step.
+// At these sizes the [B, F] pre-activations are tiny (1.5 MB at 128 x 3072: they stay in L2), so
+// here the GEMM simply stores its accumulators (encode_dense_kernel: same TMA / tcgen05 pipeline,
+// one 128 x 256 tile per work item, epilogue = tcgen05.ld -> st.global) and rowwise_topk_kernel
+// selects each row's k largest with a 4-pass most-significant-digit radix select over the
+// order-preserving integer keys in shared memory: exact, ties at the k-th value keep the lowest
+// feature index (as the fused epilogue does), output in ascending feature index.
+// ================================================================================================
+template <int STAGES>
+__global__ void __launch_bounds__(256, 1)
+encode_dense_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_w, int B, int F, int ksteps,
+                    int num_m_blocks, int num_n_tiles, float* __restrict__ pre) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* pipe = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (kAStage + kBStage));
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = ceil_div(ksteps, kBK / 16);
+  const int total_items = num_m_blocks * num_n_tiles;      // one 128 x 256 tile per item
+  const EncodeItems items{total_items, num_n_tiles, 1, num_n_tiles, num_kb, ksteps};
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kBM);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) encode_producer_loop<STAGES>(&tmap_a, &tmap_w, pipe, full_bar, empty_bar, items);
+  } else if (warp == 1) {
+    encode_mma_loop<STAGES>(pipe, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, items);
+  } else if (warp >= 4) {
+    const int q = warp - 4;               // TMEM lane quarter this warp may read
+    const int row_in_blk = q * 32 + lane;
+    uint32_t tile = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++tile) {
+      const int m_blk = item / num_n_tiles;
+      const int nt = item - m_blk * num_n_tiles;
+      const uint32_t as = tile & 1u;
+      const uint32_t aphase = (tile >> 1) & 1u;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * kBM + row_in_blk;
+      const int col0 = nt * kBN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBN;
+      float* out = pre + static_cast<size_t>(row < B ? row : 0) * F + col0;
+      uint32_t ra[16], rb[16];
+      tmem_ld16(taddr, ra);
+#pragma unroll 1
+      for (int c = 0; c < kBN; c += 32) {
+        tmem_ld_wait16(ra);
+        tmem_ld16(taddr + c + 16, rb);
+        if (row < B) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            if (col0 + c + j + 3 < F) {
+              *reinterpret_cast<uint4*>(out + c + j) = make_uint4(ra[j], ra[j + 1], ra[j + 2], ra[j + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col0 + c + j + e < F) out[c + j + e] = __uint_as_float(ra[j + e]);
+            }
+        }
+        tmem_ld_wait16(rb);
+        if (c + 32 < kBN) tmem_ld16(taddr + c + 32, ra);
+        if (row < B) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            if (col0 + c + 16 + j + 3 < F) {
+              *reinterpret_cast<uint4*>(out + c + 16 + j) = make_uint4(rb[j], rb[j + 1], rb[j + 2], rb[j + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col0 + c + 16 + j + e < F) out[c + 16 + j + e] = __uint_as_float(rb[j + e]);
+            }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// One block (256 threads) per row: the k largest of pre[row, 0:F].  Keys (order-preserving integer
+// image of the floats; NaN -> 0 = never selected) live in shared memory.  Four passes of an 8-bit
+// most-significant-digit radix select find the key T of the k-th largest value and how many keys
+// lie above it; then every thread walks a CONTIGUOUS chunk of features, a block scan turns the
+// per-thread counts into output slots, and ties at T are admitted in ascending feature index.
+constexpr int kRowTopkThreads = 256;
+__global__ void __launch_bounds__(kRowTopkThreads)
+rowwise_topk_kernel(const float* __restrict__ pre, int B, int F, int k, float* __restrict__ out_val,
+                    int32_t* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint32_t s_key[];          // [F]
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_pick[2];                             // chosen digit, count above it
+  __shared__ uint32_t s_scan[kRowTopkThreads / 32];
+  pdl_prologue();
+  const int row = blockIdx.x;
+  if (row >= B) return;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const float* src = pre + static_cast<size_t>(row) * F;
+  for (int f = tid; f < F; f += kRowTopkThreads) {
+    const float v = src[f];
+    s_key[f] = (v == v) ? f2key(v) : 0u;
+  }
+  uint32_t prefix = 0, prefix_mask = 0;       // bits decided so far
+  uint32_t need = static_cast<uint32_t>(k);   // rank still wanted inside the prefix bucket
+  uint32_t above = 0;                         // keys strictly above the prefix bucket
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    s_hist[tid] = 0u;
+    __syncthreads();
+    for (int f = tid; f < F; f += kRowTopkThreads) {
+      const uint32_t kk = s_key[f];
+      if ((kk & prefix_mask) == prefix && kk != 0u) atomicAdd(&s_hist[(kk >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // lane l owns digits 8 l .. 8 l + 7; suffix sums from the top digit down
+      uint32_t loc[8], tot = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        loc[i] = s_hist[8 * lane + i];
+        tot += loc[i];
+      }
+      uint32_t suf = tot;                      // inclusive suffix sum over lanes >= l
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += t;
+      }
+      const uint32_t higher = suf - tot;       // keys in digits above this lane's 8
+      const bool here = higher < need && suf >= need;
+      if (here) {
+        uint32_t acc = higher;                 // keys above digit i inside the prefix bucket
+        int dsel = 0;
+        bool found = false;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+          if (!found) {
+            if (acc + loc[i] >= need) {
+              dsel = i;
+              found = true;
+            } else {
+              acc += loc[i];
+            }
+          }
+        }
+        s_pick[0] = static_cast<uint32_t>(8 * lane + dsel);
+        s_pick[1] = acc;
+      }
+      if (lane == 0 && suf < need) {           // fewer than `need` valid keys: keep them all
+        s_pick[0] = 0xFFFFFFFFu;
+        s_pick[1] = 0u;
+      }
+    }
+    __syncthreads();
+    const uint32_t dsel = s_pick[0];
+    if (dsel == 0xFFFFFFFFu) {                 // (only possible in the first pass: NaN rows, k > valid keys)
+      prefix = 0u;
+      prefix_mask = 0u;
+      need = 0u;
+      break;
+    }
+    above += s_pick[1];
+    need -= s_pick[1];
+    prefix |= dsel << shift;
+    prefix_mask |= 255u << shift;
+    __syncthreads();
+  }
+  // prefix = key T of the k-th largest value (or 0: keep every valid key); `above` keys exceed it
+  const uint32_t T = prefix_mask ? prefix : 0u;
+  const uint32_t ties_wanted = prefix_mask ? static_cast<uint32_t>(k) - above : 0u;
+  // contiguous chunks: thread t owns features [t * per, (t + 1) * per)
+  const int per = ceil_div(F, kRowTopkThreads);
+  const int f_lo = tid * per, f_hi = min(F, f_lo + per);
+  uint32_t n_gt = 0, n_tie = 0;
+  for (int f = f_lo; f < f_hi; ++f) {
+    const uint32_t kk = s_key[f];
+    n_gt += (kk > T) ? 1u : 0u;
+    n_tie += (prefix_mask && kk == T) ? 1u : 0u;
+  }
+  // block exclusive scan of (n_gt | n_tie << 16)
+  uint32_t packed = n_gt | (n_tie << 16);
+  uint32_t incl = packed;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_scan[w];
+  const uint32_t excl = incl - packed + woff;
+  uint32_t gt_before = excl & 0xFFFFu, tie_before = excl >> 16;
+  float* ov = out_val + static_cast<size_t>(row) * k;
+  int32_t* oi = out_idx + static_cast<size_t>(row) * k;
+  for (int f = f_lo; f < f_hi; ++f) {
+    const uint32_t kk = s_key[f];
+    const bool gt = kk > T;
+    const bool tie = prefix_mask && kk == T;
+    bool keep = gt;
+    if (tie) {
+      keep = tie_before < ties_wanted;
+      ++tie_before;
+    }
+    if (keep && kk != 0u) {
+      // slot = kept entries before f: all greater ones + the admitted ties
+      const uint32_t ties_kept_before = min(tie_before - (tie ? 1u : 0u), ties_wanted);
+      const uint32_t slot = gt_before + ties_kept_before;
+      if (slot < static_cast<uint32_t>(k)) {
+        ov[slot] = src[f];
+        oi[slot] = f;
+      }
+    }
+    gt_before += gt ? 1u : 0u;
+  }
+  // fewer than k valid candidates (NaN rows): pad with (-inf, -1) like the fused epilogue
+  if (!prefix_mask) {
+    __syncthreads();
+    uint32_t total_valid = 0;
+    for (int w = 0; w < kRowTopkThreads / 32; ++w) total_valid += s_scan[w] & 0xFFFFu;
+    for (int sidx = static_cast<int>(total_valid) + tid; sidx < k; sidx += kRowTopkThreads) {
+      ov[sidx] = __uint_as_float(0xff800000u);
+      oi[sidx] = -1;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
@@ -1995,6 +2267,51 @@ extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int 
     rc = static_cast<int>(cudaGetLastError());
   }
   return rc;
+}
+
+
+// Small-batch form of wsae_encode_topk (see encode_dense_kernel): `pre_ws` is B * F floats of scratch.
+// Same results as wsae_encode_topk (values bit-identical: the same MMA sequence; ties to the lowest
+// feature index), output in ascending feature index.  F * 4 bytes of shared memory per row block:
+// F <= 49152.
+extern "C" int wsae_encode_topk_dense(const void* a_packed, const void* w_packed, int B, int Bp, int F,
+                                      int Fp, int Kp, int k_used_cols, int k, float* pre_ws,
+                                      float* out_val, int32_t* out_idx, cudaStream_t stream) {
+  if (!a_packed || !w_packed || !pre_ws || !out_val || !out_idx) return kBadArg;
+  if (B <= 0 || F <= 0 || k <= 0 || k > F) return kBadArg;
+  if (Bp % kBM != 0 || Fp % kBN != 0 || Kp % kBK != 0 || Bp < B || Fp < F) return kBadArg;
+  if (k_used_cols <= 0 || k_used_cols % 16 != 0 || k_used_cols > Kp) return kBadArg;
+  if (F > 49152 || k > 0xFFFF || F % 4 != 0) return kUnsupported;
+  CUtensorMap ta, tw;
+  int rc = make_tmap_bf16(&ta, a_packed, static_cast<uint64_t>(Bp), static_cast<uint64_t>(Kp), kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tw, w_packed, static_cast<uint64_t>(Fp), static_cast<uint64_t>(Kp), kBN);
+  if (rc) return rc;
+  int dev = 0, num_sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  constexpr int kStages = 3;
+  constexpr int smem_g = kStages * (kAStage + kBStage) + 256 + 1024;
+  const size_t smem_t = static_cast<size_t>(F) * 4;
+  static bool attr_set[64] = {};
+  if (dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(encode_dense_kernel<kStages>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(rowwise_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (dev < 64) attr_set[dev] = true;
+  }
+  const int num_m_blocks = Bp / kBM;
+  const int num_n_tiles = ceil_div(F, kBN);
+  const int total = num_m_blocks * num_n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  cudaError_t e = launch_pdl(encode_dense_kernel<kStages>, grid, 256, smem_g, stream, ta, tw, B, F,
+                             k_used_cols / 16, num_m_blocks, num_n_tiles, pre_ws);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = launch_pdl(rowwise_topk_kernel, B, kRowTopkThreads, smem_t, stream, static_cast<const float*>(pre_ws), B, F,
+                 k, out_val, out_idx);
+  return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 extern "C" int wsae_debug_encode_mode(int mode) { g_encode_dbg = mode; return 0; }

@@ -189,6 +189,10 @@ def choose_nsplit(B: int, F: int, k: int, num_sms: int) -> int:
     return best
 
 
+# rows up to which K1 runs as dense GEMM + row-wise select (wsae_encode_topk_dense); 0 switches it off
+_DENSE_ROWS = int(os.environ.get("WSAE_K1_DENSE_ROWS", "1024"))
+
+
 def encode_topk(a_packed: Tensor, w_packed: Tensor, B: int, F: int, d: int, terms: int, k: int,
                 nsplit: int | None = None) -> tuple[Tensor, Tensor]:
     """K1. Returns (idx int32 [B,k], val float32 [B,k]) — signed pre-activations, unordered."""
@@ -199,11 +203,17 @@ def encode_topk(a_packed: Tensor, w_packed: Tensor, B: int, F: int, d: int, term
     Bp, Fp = a_packed.shape[0], w_packed.shape[0]
     lib = _lib.load()
     dev = a_packed.device
+    nsplit_arg = nsplit
     if nsplit is None:
         nsplit = choose_nsplit(B, F, k, sm_count(dev))
     nsplit = lib.wsae_encode_effective_splits(F, nsplit)
     idx = torch.empty((B, k), dtype=torch.int32, device=dev)
     val = torch.empty((B, k), dtype=torch.float32, device=dev)
+    if nsplit_arg is None and B <= _DENSE_ROWS and F <= 49152 and F % 4 == 0:
+        # small batches (the shipped YAML batch is 128 rows): dense pre-activations + one block per row
+        pre = torch.empty((B, F), dtype=torch.float32, device=dev)
+        _run("wsae_encode_topk", lib.wsae_encode_topk_dense, _ptr(a_packed), _ptr(w_packed), B, Bp, F, Fp, ps.kp, ps.used_cols, k, _ptr(pre), _ptr(val), _ptr(idx), _stream(), launches=2)
+        return idx, val
     pv = pi = None
     if nsplit > 1:
         pv = torch.empty((B, nsplit * k), dtype=torch.float32, device=dev)
