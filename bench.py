@@ -306,6 +306,96 @@ def epoch_runner(tr, host_batches):
     return run
 
 
+def resident_loader_rate(tr, rows: torch.Tensor, batch: int, dev: str, epochs: int = 3) -> dict:
+    """the activation matrix lives in HBM behind the `FeatureCache.get_dataloader(
+    device=...)` iterable (`ResidentBatches`, shuffled: every batch is an IndexedBatch = matrix + a
+    slice of the epoch's device permutation, gathered inside K0 / K23) and is trained on through the
+    public `SAETrainer.train_epoch`.  Rows/s over whole epochs, randperm included."""
+    from whisper_sae_b200.data.feature_cache import ResidentBatches
+
+    loader = ResidentBatches(rows, batch, True, dev, drop_last=True, seed=99)
+    tr.train_epoch(loader)                      # warm-up epoch (captures the indexed graph)
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(epochs):
+        tr.train_epoch(loader)
+    end.record()
+    torch.cuda.synchronize()
+    sec = start.elapsed_time(end) / 1e3
+    n = epochs * len(loader) * batch
+    return {"value": n / sec, "unit": UNIT, "ms_per_step": 1e3 * sec / (epochs * len(loader)),
+            "resident_rows": int(rows.shape[0]), "batches_per_epoch": len(loader), "epochs": epochs,
+            "path": "FeatureCache.get_dataloader(device=...) -> ResidentBatches(shuffle=True) -> "
+                    "SAETrainer.train_epoch; rows gathered by index inside K0/K23 (no index_select pass)"}
+
+
+def variants_block(dev: str, rows: int = 16384, steps: int = 20) -> dict:
+    """BASELINE.json configs[4]: TopK crosscoder over the 4 whisper-tiny encoder layers and the TopK /
+    skip transcoders at 384 -> 3072, k = 32, B = 16384.  The reference has no
+    trainer for them (its tests step them by hand: forward, backward, optimizer step, renorm), so a
+    step here is exactly that through the public modules under bf16 autocast with torch AdamW."""
+    from whisper_sae_b200.sae import (GraphedVariantStep, SkipTranscoder, TopKCrossLayerCrosscoder,
+                                      TopKTranscoder, make_optimizer)
+
+    d, F, k, L = 384, 3072, 32, 4
+    out = {}
+
+    def timed(model, call, args, flops_per_row):
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.0, fused=True)
+
+        def step():
+            with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+                o = call()
+            opt.zero_grad(set_to_none=False)
+            o.loss.backward()
+            opt.step()
+            model.normalize_decoder_weights()
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        # the same step captured into one CUDA graph (whisper_sae_b200.sae.GraphedVariantStep)
+        stepper = GraphedVariantStep(model, make_optimizer(model))
+        for _ in range(5):
+            stepper(*args)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(steps):
+            stepper(*args)
+        b.record()
+        torch.cuda.synchronize()
+        gms = a.elapsed_time(b) / steps
+        return {"value": rows / gms * 1e3, "unit": UNIT, "ms_per_step": gms, "batch_rows": rows,
+                "gemm_tflops": flops_per_row * rows / gms / 1e9,
+                "hand_stepped": {"value": rows / ms * 1e3, "ms_per_step": ms}}
+
+    torch.manual_seed(7)
+    acts = {li: synth(rows, d, seed=50 + li).to(dev) for li in range(L)}
+    cc = TopKCrossLayerCrosscoder(d, L, F, k=k).to(dev)
+    out["topk_crosscoder_4x384_3072"] = timed(cc, lambda: cc(acts), (acts,), 6 * L * d * F)
+    del cc
+    x, y = acts[0], acts[1]
+    tc = TopKTranscoder(d, d, F, k=k).to(dev)
+    out["topk_transcoder_384_384_3072"] = timed(tc, lambda: tc(x, y), (x, y), 6 * d * F)
+    del tc
+    sk = SkipTranscoder(d, d, F, k=k).to(dev)
+    out["skip_transcoder_384_384_3072"] = timed(sk, lambda: sk(x, y), (x, y), 6 * d * F + 6 * d * d)
+    del sk, acts
+    torch.cuda.empty_cache()
+    out["note"] = ("forward + backward + torch fused AdamW + decoder renorm through the public modules "
+                   "(autograd node on the same K0/K1/K23/K4 kernels), bf16 autocast, device-resident inputs; "
+                   "value = the step replayed as one CUDA graph (GraphedVariantStep), hand_stepped = the "
+                   "same calls launched eagerly the way the reference's tests step these modules")
+    return out
+
+
 def kernel_profile(tr, batches, steps: int) -> dict:
     """Per-kernel CUDA-event spans of the eagerly launched step.  Each step is queued behind a ~3 ms
     device-side spin, so the host has enqueued the whole step (kernels and events) before the first
@@ -673,6 +763,7 @@ def main() -> None:
     blk_e, _ = time_blocks(epoch_runner(tr, host_batches), args.steps, args.warmup, repeats, dist_on)
     e2e = args.batch * args.steps * world / blk_e["median"]
     h2d_bytes = args.batch * d * 4 + 64          # batch + control block
+    resident = resident_loader_rate(tr, rows, args.batch, dev) if (rank == 0 and not dp) else None
 
     line = None
     side: dict = {}
@@ -725,6 +816,7 @@ def main() -> None:
             "yaml_batch": {"batch_rows": cfg_batch, "value": cfg_batch * 100 / blk_s["median"], "unit": UNIT,
                            "ms_per_step": 1e3 * blk_s["median"] / 100},
             "deterministic_mode": det_info,
+            "resident_loader": resident,
         }
     del tr, dev_batches, host_batches, rows
     torch.cuda.empty_cache()
@@ -749,6 +841,8 @@ def main() -> None:
     if line is not None:
         if side:
             line["workloads"] = side
+        if args.workload == "tiny" and not args.no_side_workloads and bf16:
+            line["variants"] = variants_block(dev)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             ref = cpu_reference_rate(wl, 8192, args.cpu_seconds, threads)

@@ -152,3 +152,54 @@ def test_crosscoder_whisper_tiny_shape(precision, tol):
         if precision == "fp32":
             torch.testing.assert_close(g.reshape(-1)[::997], dg["sample"], rtol=1e-3,
                                        atol=1e-5 * dg["sample"].abs().max().item() + 1e-12)
+
+
+@pytest.mark.parametrize("kind", ["transcoder", "skip", "crosscoder"])
+def test_graphed_variant_step_follows_the_hand_stepped_trajectory(kind):
+    """GraphedVariantStep (whole step in one CUDA graph) == the reference's hand-written step
+    (forward, backward, AdamW, renorm; tests/test_transcoder.py / test_crosscoder.py of the reference)
+    launched eagerly: same kernels, so losses agree to accumulation-order noise, dead-feature
+    counters exactly, over more steps than the eager + capture calls."""
+    from whisper_sae_b200.sae import (GraphedVariantStep, SkipTranscoder, TopKCrossLayerCrosscoder,
+                                      TopKTranscoder, make_optimizer)
+
+    d, F, k, B, L, steps = 128, 1024, 16, 512, 3, 6
+
+    def build():
+        torch.manual_seed(5)
+        if kind == "crosscoder":
+            return TopKCrossLayerCrosscoder(d, L, F, k=k).cuda().train()
+        cls = SkipTranscoder if kind == "skip" else TopKTranscoder
+        return cls(d, d, F, k=k).cuda().train()
+
+    def batch(s):
+        if kind == "crosscoder":
+            return ({li: _inputs(100 * s + li, B, d).cuda() for li in range(L)},)
+        return (_inputs(2 * s, B, d).cuda(), _inputs(2 * s + 1, B, d).cuda())
+
+    ref, ref_opt = build(), None
+    ref_opt = make_optimizer(ref, lr=1e-3)
+    ref_losses = []
+    for s in range(steps):
+        with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+            out = ref(*batch(s))
+        ref_opt.zero_grad()
+        out.loss.backward()
+        ref_opt.step()
+        ref.normalize_decoder_weights()
+        ref_losses.append(out.loss.item())
+
+    m = build()
+    stepper = GraphedVariantStep(m, make_optimizer(m, lr=1e-3))
+    got = [stepper(*batch(s)) for s in range(steps)]
+    assert stepper._graph is not None and stepper.calls == steps
+    for s, (r, g) in enumerate(zip(ref_losses, got)):
+        assert g.loss.item() == pytest.approx(r, rel=2e-3), f"step {s}"
+        assert 0 < g.l0.item() <= k
+    assert torch.equal(m.feature_last_activated, ref.feature_last_activated)
+    assert int(m.step_count) == steps
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        rel = ((p - q).norm() / (q.norm() + 1e-12)).item()
+        assert rel < 2e-2, f"{n}: rel-L2 {rel:.2e}"
+    with pytest.raises(RuntimeError):
+        GraphedVariantStep(m, torch.optim.AdamW(m.parameters(), lr=1e-3))

@@ -107,6 +107,17 @@ def _fp32_terms() -> int:
     return t
 
 
+_ONES: dict = {}
+
+
+def _one(device: torch.device) -> Tensor:
+    """A resident fp32 scalar 1.0 per device (grad_output of the fused forward pass)."""
+    t = _ONES.get(device)
+    if t is None:
+        t = _ONES[device] = torch.ones((), dtype=torch.float32, device=device)
+    return t
+
+
 class _SparseState:
     """Per-forward sparse results shared between the autograd node and the lazy SAEOutput."""
 
@@ -145,16 +156,36 @@ class _FusedTopKSAE(torch.autograd.Function):
         w_used = ops.cast_bf16(w_decT) if bf16 else w_decT
         stats = torch.zeros(3, dtype=torch.int64, device=x.device)
         training = bool(mod.training) and getattr(mod, "feature_last_activated", None) is not None
-        resid, _ = ops.decode_mse(
-            tgt, w_used, b_dec, b_pre, idx, val, stats=stats,
-            last_activated=mod.feature_last_activated if training else None,
-            step_count=mod.step_count if training else None,
-        )
+        rows_total = getattr(mod, "_global_rows", None) or B
+        d_out = tgt.shape[1]
+        # K23 (one pass over the gathered decoder rows for decode + MSE + dv + bias gradients) when a
+        # backward will follow: its dv / bias gradients are linear in grad_output, so they are computed
+        # here for grad_output = 1 and scaled in backward()
+        ctx.fused23 = None
+        if (bf16 and any(ctx.needs_input_grad[3:]) and ops.decode_backward_supported(d_out, mod.k, True)
+                and ops.wgrad_gemm_supported(d) and ops.wgrad_gemm_supported(d_out)):
+            resid = torch.empty((B, d_out), dtype=torch.float32, device=x.device)
+            resid_bf = torch.empty((B, d_out), dtype=torch.bfloat16, device=x.device)
+            d_b_enc = torch.zeros(F, dtype=torch.float32, device=x.device)
+            d_b_dec = torch.zeros(d_out, dtype=torch.float32, device=x.device)
+            dpre = torch.empty((B, mod.k), dtype=torch.float32, device=x.device)
+            ops.decode_backward(tgt, w_used, b_dec, b_pre, idx, val, _one(x.device),
+                                2.0 / (float(rows_total) * float(d_out)),
+                                resid=resid, resid_bf16=resid_bf, stats=stats,
+                                last_activated=mod.feature_last_activated if training else None,
+                                step_count=mod.step_count if training else None,
+                                d_b_enc=d_b_enc, d_b_dec=d_b_dec, dpre_val=dpre)
+            ctx.fused23 = (resid_bf, d_b_enc, d_b_dec, dpre)
+        else:
+            resid, _ = ops.decode_mse(
+                tgt, w_used, b_dec, b_pre, idx, val, stats=stats,
+                last_activated=mod.feature_last_activated if training else None,
+                step_count=mod.step_count if training else None,
+            )
         if training:
             ops.counters_update(mod.feature_last_activated, mod.step_count,
                                 mod.dead_feature_threshold, True, stats[2:])
-        rows_total = getattr(mod, "_global_rows", None) or B
-        numel = float(rows_total) * float(tgt.shape[1])
+        numel = float(rows_total) * float(d_out)
         loss = (stats[:1].view(torch.float64)[0] / numel).to(torch.float32)
         st.idx, st.val, st.resid, st.stats, st.w_dec_used, st.rows_total = idx, val, resid, stats, w_used, rows_total
         st.d_out = tgt.shape[1]
@@ -179,10 +210,24 @@ class _FusedTopKSAE(torch.autograd.Function):
         coef = 2.0 / (float(st.rows_total) * float(d_out))
         d_w_enc = torch.zeros((F, d_in), dtype=torch.float32, device=dev) if needs[6] else None
         d_w_decT = torch.zeros((F, d_out), dtype=torch.float32, device=dev) if needs[8] else None
-        d_b_enc = torch.zeros(F, dtype=torch.float32, device=dev)
-        d_b_dec = torch.zeros(d_out, dtype=torch.float32, device=dev)
-        dpre = torch.empty(st.idx.shape, dtype=torch.float32, device=dev)
-        if ctx.bf16 and ops.wgrad_gemm_supported(d_in) and ops.wgrad_gemm_supported(d_out):
+        if ctx.fused23 is None:
+            d_b_enc = torch.zeros(F, dtype=torch.float32, device=dev)
+            d_b_dec = torch.zeros(d_out, dtype=torch.float32, device=dev)
+            dpre = torch.empty(st.idx.shape, dtype=torch.float32, device=dev)
+        if ctx.fused23 is not None:
+            # dv, db_enc, db_dec came out of K23 in forward() for grad_output = 1
+            resid_bf, d_b_enc, d_b_dec, dpre = ctx.fused23
+            if d_w_enc is not None or d_w_decT is not None:
+                buckets = ops.bucket_by_tile(st.idx, st.val, dpre, F)
+                if d_w_enc is not None:
+                    ops.wgrad_gemm_(d_w_enc, ctx.a_packed, B, d_in, buckets, buckets.dpre, go, 1.0)
+                if d_w_decT is not None:
+                    ops.wgrad_gemm_(d_w_decT, resid_bf, B, d_out, buckets, buckets.act, go, coef)
+            d_b_enc = d_b_enc * go
+            d_b_dec = d_b_dec * go
+            if needs[3]:
+                dpre = dpre * go
+        elif ctx.bf16 and ops.wgrad_gemm_supported(d_in) and ops.wgrad_gemm_supported(d_out):
             resid_bf = torch.empty(st.resid.shape, dtype=torch.bfloat16, device=dev)
             ops.backward_sparse(st.resid, None, None, st.w_dec_used, st.idx, st.val, go, coef,
                                 d_w_enc=None, d_w_decT=None, d_b_enc=d_b_enc, d_b_dec=d_b_dec,

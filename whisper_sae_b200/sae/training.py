@@ -18,6 +18,8 @@ Same constructor, public attributes, ``train_step`` / ``train_epoch`` / ``train`
 
 from __future__ import annotations
 
+import contextlib
+import gc
 import json
 import math
 import os
@@ -64,6 +66,22 @@ def _ensure_adamw_state(optimizer: AdamW, p: Tensor) -> dict:
         if t.stride() != p.stride() or t.device != p.device:
             st[name] = torch.empty_strided(p.shape, p.stride(), dtype=p.dtype, device=p.device).copy_(t)
     return st
+
+
+@contextlib.contextmanager
+def _quiet_gc():
+    """Stream capture is invalidated by ANY forbidden CUDA call in the process, and destroying another
+    CUDA graph is one: a dead trainer (trainer <-> graphed-step reference cycle) that Python's cyclic
+    collector happens to free in the middle of a capture kills it (cudaErrorStreamCaptureInvalidated;
+    torch.cuda.graph stopped collecting up front in 2.9).  Collect before, keep the collector off inside."""
+    gc.collect()
+    was_on = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_on:
+            gc.enable()
 
 
 class _GraphedStep:
@@ -451,7 +469,7 @@ class _GraphedStep:
                 segs = []
                 for part in (self._compute_a, self._compute_b, self._update_pre, self._update_opt):
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, pool=pool):
+                    with _quiet_gc(), torch.cuda.graph(g, pool=pool):
                         part()
                     segs.append(g)
                 self.kernels_per_replay = ops.GPU_LAUNCHES - before
@@ -477,7 +495,7 @@ class _GraphedStep:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 before = ops.GPU_LAUNCHES
-                with torch.cuda.graph(g):
+                with _quiet_gc(), torch.cuda.graph(g):
                     self._body()
                 self.kernels_per_replay = ops.GPU_LAUNCHES - before   # captured, not yet executed
                 ops.GPU_LAUNCHES = before
