@@ -28,6 +28,7 @@ fixed batch per rank (weak) and at a fixed global batch (strong).
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -396,6 +397,22 @@ def variants_block(dev: str, rows: int = 16384, steps: int = 20) -> dict:
     return out
 
 
+@contextlib.contextmanager
+def serial_kernels():
+    """The per-kernel profile runs the step WITHOUT the forked graph branches (WSAE_FORK=0): a kernel
+    timed while it shares the SMs with a weight-gradient GEMM reads many times its own duration
+    (b_pre gradient at 1280 -> 40960: 2.3 ms beside K4, ~0.1 ms alone)."""
+    old = os.environ.get("WSAE_FORK")
+    os.environ["WSAE_FORK"] = "0"
+    try:
+        yield
+    finally:
+        if old is None:
+            os.environ.pop("WSAE_FORK", None)
+        else:
+            os.environ["WSAE_FORK"] = old
+
+
 def kernel_profile(tr, batches, steps: int) -> dict:
     """Per-kernel CUDA-event spans of the eagerly launched step.  Each step is queued behind a ~3 ms
     device-side spin, so the host has enqueued the whole step (kernels and events) before the first
@@ -676,9 +693,10 @@ def side_workload(name: str, batch: int, dev: str, rank: int, world: int, steps:
     if profile:
         del tr
         tr_e, _ = make_trainer(wl, batch, dev, layer_seed=0, cuda_graph="eager")
-        for i in range(3):
-            tr_e.train_step(batches[i % nb])
-        prof = kernel_profile(tr_e, batches, 6)
+        with serial_kernels():
+            for i in range(3):
+                tr_e.train_step(batches[i % nb])
+            prof = kernel_profile(tr_e, batches, 6)
         _, table = rooflines(prof, name, wl, batch, peaks, peak_src)
         out["kernels"] = {n: {kk: vv for kk, vv in e.items() if kk not in ("per_step",)} for n, e in table.items()}
         del tr_e
@@ -771,9 +789,10 @@ def main() -> None:
         # per-kernel CUDA-event timing needs eager launches: same kernels, graph replay switched off
         tr_eager, _ = make_trainer(wl, args.batch, dev, layer_seed=rank, use_amp=bf16,
                                    cuda_graph="eager")       # single-rank kernels (no collective)
-        for i in range(3):
-            tr_eager.train_step(dev_batches[i % nb])
-        prof = kernel_profile(tr_eager, dev_batches, min(args.steps, 10))
+        with serial_kernels():
+            for i in range(3):
+                tr_eager.train_step(dev_batches[i % nb])
+            prof = kernel_profile(tr_eager, dev_batches, min(args.steps, 10))
         del tr_eager
         roof, table = rooflines(prof, args.workload, wl, args.batch, peaks, peak_src)
         # the launch-bound YAML batch, for the record

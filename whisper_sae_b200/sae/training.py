@@ -140,6 +140,12 @@ class _GraphedStep:
         # changes streams.  0.7945 -> 0.7799 ms per step (same-box A/B); WSAE_FORK=0 switches it off.
         self.fork = os.environ.get("WSAE_FORK", "1") != "0" and not trainer.data_parallel and self.bf16
         self._side = torch.cuda.Stream(device=dev) if self.fork else None
+        # small batches: the two weight-gradient GEMMs (24 feature tiles x a few row chunks each at the
+        # YAML batch) leave most SMs idle, so dW_dec runs beside dW_enc on a second branch of the graph
+        # (96.9 -> 92.7 us per step at 128 rows; no gain from 1024 rows on: profiles/r2c_k4_fork_ab.txt)
+        self.fork_k4 = self.fork and rows <= int(os.environ.get("WSAE_FORK_K4_ROWS", "512"))
+        self._side2 = torch.cuda.Stream(device=dev) if self.fork_k4 else None
+        self._k4_forked = False
         self._w_packed_buf: Tensor | None = None
         self._w_used_buf: Tensor | None = None
         self._x: Tensor | None = None     # staging buffer, allocated on first use
@@ -340,6 +346,11 @@ class _GraphedStep:
         if use_gemm:
             # weight gradients on the tensor cores (K4)
             buckets = ops.bucket_by_tile(idx, val, dpre, F)
+            self._k4_forked = self.fork_k4 and not self.det     # (the ordered split-K workspace is shared)
+            if self._k4_forked:
+                self._side2.wait_stream(main)
+                with torch.cuda.stream(self._side2):     # joined in _update_pre, before the gradient norm
+                    ops.wgrad_gemm_(self.g_w_decT, resid_bf, B, d, buckets, buckets.act, self.one, coef)
             ops.wgrad_gemm_(self.g_w_enc, a_packed, B, d, buckets, buckets.dpre, None, 1.0,
                             det_ws=self.det_k4 if self.det else None)
         else:
@@ -353,7 +364,7 @@ class _GraphedStep:
         """The dW_dec GEMM and the b_pre gradient."""
         m = self.trainer.model
         mid = self._mid
-        if mid["use_gemm"]:
+        if mid["use_gemm"] and not self._k4_forked:
             ops.wgrad_gemm_(self.g_w_decT, mid["resid_bf"], mid["B"], mid["d"], mid["buckets"],
                             mid["buckets"].act, self.one, mid["coef"],
                             det_ws=self.det_k4 if self.det else None)
@@ -367,6 +378,8 @@ class _GraphedStep:
             self._counters()
         if self.fork:
             torch.cuda.current_stream().wait_stream(self._side)
+        if self._k4_forked:
+            torch.cuda.current_stream().wait_stream(self._side2)
         if self.shard:
             # this rank's rows of the two matrices; the (all-reduced) small tensors count once
             ops.sumsq_(self.g_w_enc[self.f0:self.f1], self.sumsq)
