@@ -46,6 +46,7 @@ def golden_fp32(name: str, rank: int, world: int, dev: str) -> dict:
         assert m.l0 == ref["l0"] or not strict, (m.l0, ref["l0"])
         assert abs(m.dead_feature_ratio - ref["dead_feature_ratio"]) < 1e-7 or not strict
         assert abs(m.learning_rate - ref["lr_reported"]) <= 1e-9 * ref["lr_reported"]
+    tr.consolidate_weights()
     sae = tr.model
     counters_equal = bool(torch.equal(sae.feature_last_activated.cpu(),
                                       fx["final_counters"]["feature_last_activated"]))
@@ -76,6 +77,7 @@ def single_vs_sharded_bf16(rank: int, world: int, dev: str) -> dict:
     for s in range(r["steps"]):
         a, b = parallel.shard_rows(r["B"], world, rank)
         got.append(dp.train_step(x[s * r["B"] + a:s * r["B"] + b]))
+    dp.consolidate_weights()      # bf16 operand gather: fp32 rows of the other ranks are gathered on demand
     loss_rel = max(abs(g.loss - q.loss) / abs(q.loss) for g, q in zip(got, ref))
     l0_equal = all(g.l0 == q.l0 for g, q in zip(got, ref))
     dead_equal = all(g.dead_feature_ratio == q.dead_feature_ratio for g, q in zip(got, ref))

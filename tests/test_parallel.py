@@ -149,6 +149,13 @@ def test_batch_sharded_step_matches_single_device(tmp_path, use_amp, tol, shard)
             assert got[r][s].loss == pytest.approx(ref[s].loss, rel=max(tol, 1e-6))
             assert got[r][s].l0 == ref[s].l0
             assert got[r][s].dead_feature_ratio == ref[s].dead_feature_ratio
+    gs = next(iter(ranks[0]._graphs.values()), None)
+    assert gs is None or gs.zero == (shard and use_amp)
+    # bf16 operand gather: the fp32 rows of the other rank are stale until consolidated (collective)
+    assert ranks[0]._dp_weights_stale == (shard and use_amp)
+    ts = [threading.Thread(target=ranks[r].consolidate_weights) for r in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
     for r in range(2):
         m = ranks[r].model
         assert torch.equal(m.feature_last_activated, single.model.feature_last_activated)

@@ -40,6 +40,7 @@ def run(mode: str, steps: int, d: int, F: int, k: int, rows: int, rank: int, wor
         losses.append(tr.train_step(x[lo:lo + rows]).loss)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / (steps - warm)
+    tr.consolidate_weights()      # bf16 operand gather: fp32 rows of the other ranks are gathered on demand
     return tr, losses, dt
 
 

@@ -158,6 +158,21 @@ def pack_encoder(w_enc: Tensor, b_enc: Tensor | None, terms: int, out: Tensor | 
     return out
 
 
+def pack_encoder_rows_(w_rows: Tensor, b_rows: Tensor | None, terms: int, out_rows: Tensor) -> None:
+    """K0 on a block of feature rows: packs ``w_rows`` [R, d] (+ bias) into the matching rows of a packed
+    encoder matrix (``out_rows`` = a row slice of it, [R, Kp] bf16) without touching any padding rows -
+    what a rank of the sharded optimizer does with the rows it has just updated."""
+    _need_cuda(w_rows, b_rows, out_rows)
+    _f32c(w_rows, "encoder.weight rows")
+    _f32c(b_rows, "encoder.bias rows")
+    R, d = w_rows.shape
+    ps = packed_shape(d, terms)
+    if out_rows.dtype != torch.bfloat16 or tuple(out_rows.shape) != (R, ps.kp) or not out_rows.is_contiguous():
+        raise RuntimeError(f"out_rows must be a contiguous [{R}, {ps.kp}] bfloat16 row block")
+    lib = _lib.load()
+    _run("wsae_pack_encoder", lib.wsae_pack_encoder, _ptr(w_rows), _ptr(b_rows), R, R, d, terms, _ptr(out_rows), _stream())
+
+
 _SM_COUNT: dict[int, int] = {}
 
 

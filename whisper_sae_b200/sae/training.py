@@ -183,6 +183,13 @@ class _GraphedStep:
         self.shard = bool(trainer.data_parallel and trainer.shard_optimizer and comm is not None
                           and comm.world > 1 and F % comm.world == 0 and not trainer.deterministic)
         self.f0, self.f1 = comm.row_block(F) if self.shard else (0, F)
+        # bf16 operand gather (sharded optimizer, bf16 step): after its AdamW pass a rank packs / casts
+        # only ITS updated rows into the bf16 operands K1 and K23 read (W' and the decoder shadow) and
+        # those rows are all-gathered - half the bytes of gathering the fp32 weights, and the encoder
+        # pack / decoder cast passes shrink by 1/N.  The fp32 rows other ranks own go stale in this
+        # replica until SAETrainer.consolidate_weights() gathers them (checkpoints, resampling, epoch end).
+        self.zero = bool(self.shard and self.bf16 and os.environ.get("WSAE_DP_OPERANDS", "1") != "0")
+        self._zeros_d: Tensor | None = None
         self._early = None
         self.grads = [self.g_b_pre, self.g_w_enc, self.g_b_enc, self.g_w_decT, self.g_b_dec]
         # what autograd would leave in .grad (decoder.weight's grad is the [d, F] transposed view)
@@ -235,6 +242,27 @@ class _GraphedStep:
         if self.shard:
             self._gather_weights()
 
+    def _operands(self) -> tuple[Tensor, Tensor]:
+        """The trainer-wide bf16 operand buffers of the operand-gather mode (shared by every batch shape)."""
+        tr = self.trainer
+        if tr._dp_operands is None:
+            m = tr.model
+            F, d = m.hidden_dim, m.input_dim
+            ps = ops.packed_shape(d, 1)
+            dev = m.b_pre.device
+            tr._dp_operands = (torch.empty(((F + 255) // 256 * 256, ps.kp), dtype=torch.bfloat16, device=dev),
+                               torch.empty((F, d), dtype=torch.bfloat16, device=dev))
+            tr._dp_operands_fresh = False
+        return tr._dp_operands
+
+    def _refresh_operands(self) -> None:
+        """Full local pack / cast from the fp32 weights (first step, after consolidate_weights / a load)."""
+        m = self.trainer.model
+        w_packed, w_used = self._operands()
+        ops.pack_encoder(m.encoder.weight.data, m.encoder.bias.data, 1, out=w_packed)
+        ops.cast_bf16(m.decoder.weight.data.t(), out=w_used)
+        self.trainer._dp_operands_fresh = True
+
     def _exchange(self) -> None:
         """The per-step collectives behind the kernels (gradients, {sse, l0}, fired stamps)."""
         comm = self.trainer.dp_comm
@@ -243,6 +271,15 @@ class _GraphedStep:
             h_enc = self._early if self._early is not None else comm.reduce_scatter_rows_async(self.g_w_enc)
             h_dec = comm.reduce_scatter_rows_async(self.g_w_decT)
             comm.all_reduce_sum(self.g_part_head)
+            if self.zero:
+                # db_pre = db_dec - db_enc . W_enc needs every fp32 encoder row, and this replica only keeps
+                # its own rows current: GEMV over those rows with the SUMMED db_enc, then a d-float all-reduce
+                m = self.trainer.model
+                if self._zeros_d is None:
+                    self._zeros_d = torch.zeros_like(self.g_b_dec)
+                ops.bpre_grad(self.g_b_dec if comm.rank == 0 else self._zeros_d, self.g_b_enc[self.f0:self.f1],
+                              m.encoder.weight.data[self.f0:self.f1], out=self.g_b_pre)
+                comm.all_reduce_sum(self.g_b_pre)
             comm.reduce_stats(self.stats, last)
             h_enc.wait()
             h_dec.wait()
@@ -262,6 +299,15 @@ class _GraphedStep:
     def _gather_weights(self) -> None:
         m = self.trainer.model
         comm = self.trainer.dp_comm
+        if self.zero:
+            F = m.hidden_dim
+            f0, f1 = self.f0, self.f1
+            w_packed, w_used = self._operands()
+            ops.pack_encoder_rows_(m.encoder.weight.data[f0:f1], m.encoder.bias.data[f0:f1], 1, w_packed[f0:f1])
+            ops.cast_bf16(m.decoder.weight.data.t()[f0:f1], out=w_used[f0:f1])
+            comm.all_gather_rows(w_packed[:F])
+            comm.all_gather_rows(w_used)
+            return
         comm.all_gather_rows(m.encoder.weight.data)
         comm.all_gather_rows(m.decoder.weight.data.t())     # feature-major storage: [F, d] contiguous
 
@@ -299,10 +345,12 @@ class _GraphedStep:
             a_packed = ops.pack_activations(x, m.b_pre.data, terms)
         if self.fork:
             main.wait_stream(self._side)
+        elif self.zero:
+            w_packed, w_used = self._operands()      # gathered at the end of the previous step
         else:
             w_packed = ops.pack_encoder(m.encoder.weight.data, m.encoder.bias.data, terms)
         idx, val = ops.encode_topk(a_packed, w_packed, B, F, d, terms, k)
-        if not self.fork:
+        if not self.fork and not self.zero:
             w_used = ops.cast_bf16(w_decT) if self.bf16 else w_decT
         rows_total = m._global_rows or B
         coef = 2.0 / (float(rows_total) * d)
@@ -368,7 +416,7 @@ class _GraphedStep:
             ops.wgrad_gemm_(self.g_w_decT, mid["resid_bf"], mid["B"], mid["d"], mid["buckets"],
                             mid["buckets"].act, self.one, mid["coef"],
                             det_ws=self.det_k4 if self.det else None)
-        if not self.fork:
+        if not self.fork and not self.zero:      # operand-gather mode: after the exchange (_exchange)
             ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre,
                           det_ws=self.det_bpre)
 
@@ -466,9 +514,16 @@ class _GraphedStep:
         self.ctl.copy_(self.ctl_host, non_blocking=True)
         self.calls += 1
         tr.model._w_decT()
+        if self.zero:
+            self._operands()
+            if not tr._dp_operands_fresh:
+                self._refresh_operands()
+            tr._dp_weights_stale = True      # after this step the fp32 rows of other ranks are one step behind
         key = self._pointer_key()
         if key != self._ptrs:      # storage was swapped behind our back (.data = ..., load): re-capture
             self.graph = None
+            if self.zero and self._ptrs and not tr._dp_weights_stale:
+                self._refresh_operands()
             self._ptrs = key
             self.calls = 1
         if self.calls > 1 and tr.cuda_graph == "segments":
@@ -614,6 +669,9 @@ class SAETrainer:
             shard_optimizer = os.environ.get("WSAE_DP_SHARD", "1") != "0"
         self.shard_optimizer = bool(shard_optimizer)
         self.dp_comm = None
+        self._dp_operands: tuple[Tensor, Tensor] | None = None   # bf16 operand gather (see _GraphedStep.zero)
+        self._dp_operands_fresh = False
+        self._dp_weights_stale = False
         self.global_batch_rows = global_batch_rows     # default: local rows x world (equal shards)
         if self.data_parallel:
             from .parallel import TorchDistCommunicator
@@ -640,6 +698,7 @@ class SAETrainer:
             return 0
         if self.global_step == 0 or self.global_step % self.resample_dead_every != 0:
             return 0
+        self.consolidate_weights()
         picks = torch.randperm(len(self._resample_dataset))[: self.resample_batch_size]
         tensors = getattr(self._resample_dataset, "tensors", None)
         if tensors is not None:  # TensorDataset: one indexed gather instead of a Python loop
@@ -858,6 +917,7 @@ class SAETrainer:
                      "train/lr": m.learning_rate},
                     step=self.global_step,
                 )
+        self.consolidate_weights()
         self.epoch += 1
         return epoch_metrics
 
@@ -889,6 +949,7 @@ class SAETrainer:
     def save_checkpoint(self, filename: str) -> Path:
         """Same dict layout as training.py:328-338."""
         path = self.run_dir / filename
+        self.consolidate_weights()
         self.consolidate_optimizer_state()
         payload = {
             "model_state_dict": self.model.state_dict(),
@@ -900,6 +961,20 @@ class SAETrainer:
         }
         torch.save(payload, path)
         return path
+
+    def consolidate_weights(self) -> None:
+        """Data parallel with the bf16 operand gather: a replica keeps only ITS feature rows of the fp32
+        encoder / decoder weights current between steps (the step itself reads the gathered bf16
+        operands).  This gathers the fp32 rows into every replica - call it before reading or editing
+        ``model``'s weights (collective: every rank calls it; ``train_epoch``, ``save_checkpoint`` and
+        the resampling hook do).  A no-op otherwise."""
+        if self.dp_comm is None or not self._dp_weights_stale:
+            return
+        m = self.model
+        self.dp_comm.all_gather_rows(m.encoder.weight.data)
+        self.dp_comm.all_gather_rows(m.decoder.weight.data.t())
+        self._dp_weights_stale = False
+        self._dp_operands_fresh = False      # the caller may edit the weights now: re-pack before the next step
 
     def consolidate_optimizer_state(self) -> None:
         """Sharded optimizer: every rank updates the AdamW moments of ITS feature rows only; gather the
@@ -920,6 +995,8 @@ class SAETrainer:
     def load_checkpoint(self, path: str | Path) -> None:
         ckpt = torch.load(path, map_location=self.device)
         self.model.load_state_dict(ckpt["model_state_dict"])
+        self._dp_weights_stale = False
+        self._dp_operands_fresh = False
         self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
         if ckpt["scheduler_state_dict"] and self.scheduler:
             self.scheduler.load_state_dict(ckpt["scheduler_state_dict"])
