@@ -14,7 +14,7 @@ for WL in tiny small-dp large-dp; do
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${TAG}_${WL}_launches.csv \
       python bench.py --workload $WL --steps 5 --warmup 3 --value-only > $O/${TAG}_${WL}_ncu.log 2>&1
   timeout 900 ncu --set full --import-source on --clock-control none \
-      -k regex:'encode_topk2|decode_backward_kernel|wgrad_gemm' -s 12 -c 4 -f -o $O/${TAG}_${WL}_top \
+      -k regex:'encode_topk2|encode_topk3|decode_backward|wgrad_gemm_kernel' -s 12 -c 4 -f -o $O/${TAG}_${WL}_top \
       python bench.py --workload $WL --steps 5 --warmup 3 --value-only > $O/${TAG}_${WL}_ncu_full.log 2>&1
 done
 ls -la $O | tail -30

@@ -664,17 +664,39 @@ decode_backward_staged_kernel(const float* __restrict__ target, const __nv_bfloa
 // ================================================================================================
 constexpr int kTcGBytes = 256;                       // bf16 residual of two half slices (ping-pong), per warp
 
+// L2 eviction policies: the activation stream (B * d * 4 bytes per launch, read once) is marked
+// evict_first and the gathered decoder rows (re-read ~B * k / F times each) evict_last, so the stream
+// does not push decoder rows out of L2 (ncu at 768 -> 6144: 896 MB of DRAM traffic per launch against
+// 350 MB of compulsory bytes without the hints).
+__device__ __forceinline__ uint64_t l2_policy(int kind) {   // 0 = normal, 1 = evict_first, 2 = evict_last
+  uint64_t pol;
+  if (kind == 1)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 2)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
 template <bool kAllocL1>
-__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p, uint64_t pol) {
   uint4 v;
   if (kAllocL1)
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
   else
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_stream_v2(const float* p, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
+               : "=f"(v.x), "=f"(v.y)
+               : "l"(p), "l"(pol));
   return v;
 }
 // acc[0..3] += bf16x2(w0).{lo,hi}, bf16x2(w1).{lo,hi} times bf16(h.lo)
@@ -723,8 +745,10 @@ decode_backward_tc_kernel(const float* __restrict__ target, const __nv_bfloat16*
                           float* __restrict__ d_b_dec, float* __restrict__ dpre_val,
                           const float* const* __restrict__ target_at,
                           const long long* const* __restrict__ rows_at, int stamp_words,
-                          long long* __restrict__ det_ws, int pf_dist) {
+                          long long* __restrict__ det_ws, int pf_dist, int l2hint) {
   static_assert(STAGES == 2 || STAGES == 3, "two or three half slices in registers");
+  const uint64_t pol_x = l2_policy((l2hint & 1) ? 1 : 0);      // activation stream
+  const uint64_t pol_w = l2_policy((l2hint & 2) ? 2 : 0);      // gathered decoder rows
   // [d] bias | [warps][d] db_dec partials | [warps] bf16 residual ping-pong + 16 zero bytes | fired bitmap
   extern __shared__ __align__(16) float fsm[];
   pdl_prologue();
@@ -802,8 +826,8 @@ decode_backward_tc_kernel(const float* __restrict__ target, const __nv_bfloat16*
   };
   auto gather = [&](uint4 (&w)[8], float2& x, int ahead) {     // `ahead` half slices past the current one
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = ldg_nc_v4<PF>(wp[i] + ahead * 128);
-    x = __ldg(reinterpret_cast<const float2*>(trow + ahead * 64));
+    for (int i = 0; i < 8; ++i) w[i] = ldg_nc_v4<PF>(wp[i] + ahead * 128, pol_w);
+    x = ldg_stream_v2(trow + ahead * 64, pol_x);
   };
   // PF: every lane asks for ONE 128-byte line of ITS entry's row, pf_dist half slices past the one
   // being gathered - a single instruction per half slice brings all 32 lines (4 KB) into L1 without
@@ -1139,6 +1163,13 @@ static int decode_backward_impl(const float* target, const float* const* target_
       return e ? std::atoi(e) : -1;
     }();
     const int pf_dist = pf_env >= 0 ? pf_env : (static_cast<long long>(F) * d * 2 > (64LL << 20) ? 1 : 0);
+    // L2 eviction hints (WSAE_K23_L2HINT: bit 0 = activation stream evict_first, bit 1 = decoder rows
+    // evict_last; default 3 where the bf16 decoder fits comfortably in L2, 1 above 48 MB)
+    static const int l2_env = [] {
+      const char* e = std::getenv("WSAE_K23_L2HINT");
+      return e ? std::atoi(e) : -1;
+    }();
+    const int l2hint = l2_env >= 0 ? l2_env : (static_cast<long long>(F) * d * 2 <= (48LL << 20) ? 3 : 1);
     using KernT = decltype(&decode_backward_tc_kernel<3, 2, false>);
     KernT kern = stages == 3 ? decode_backward_tc_kernel<3, 3, false>
                              : (per_want == 4 ? (pf_dist > 0 ? decode_backward_tc_kernel<4, 2, true> : decode_backward_tc_kernel<4, 2, false>)
@@ -1162,7 +1193,7 @@ static int decode_backward_impl(const float* target, const float* const* target_
       if (nblk > sms * per) nblk = sms * per;
       launch_pdl(kern, nblk, kFusedWarps * 32, smem_t, stream, target, wd, b_dec,
                  b_pre, idx, val, grad_out, coef, B, d, F, k, resid, rbf, st, last_activated, step_count,
-                 d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, det_ws, pf_dist);
+                 d_b_enc, d_b_dec, dpre_val, target_at, rows_at, stamp_words, det_ws, pf_dist, l2hint);
       return static_cast<int>(cudaGetLastError());
     }
   }
