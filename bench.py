@@ -437,16 +437,17 @@ def kernel_profile(tr, batches, steps: int) -> dict:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum and lts__t_sectors.sum x 32 B per launch from `ncu --set
-# full` of each workload's default batch (bf16): profiles/r2a_{tiny,small-dp,large-dp}_top3_ncu_full.txt
+# full` of each workload's default batch (bf16): profiles/r2c_{tiny,small-dp,large-dp}_top3_ncu_full.txt
+# (K1 = CTA-pair kernel, K23 = tensor form, K4 averaged over its two launches)
 NCU_TRAFFIC = {
-    "tiny": {"wsae_encode_topk": (74.46e6, 2390.7e6), "wsae_decode_backward": (184.95e6, 2370.4e6),
-             "wsae_wgrad_gemm": (90.0e6, 924.9e6)},
-    "small-dp": {"wsae_encode_topk": (148.9e6, 7387.1e6), "wsae_decode_backward": (373.97e6, 4598.1e6),
-                 "wsae_wgrad_gemm": (290.8e6, 3428.7e6)},
-    "large-dp": {"wsae_encode_topk": (332.3e6, 26269.8e6), "wsae_decode_backward": (1677.9e6, 4700.3e6),
-                 "wsae_wgrad_gemm": (1091.2e6, 17409.4e6)},
+    "tiny": {"wsae_encode_topk": (74.56e6, 1704.9e6), "wsae_decode_backward": (246.43e6, 2285.5e6),
+             "wsae_wgrad_gemm": (88.89e6, 925.6e6)},
+    "small-dp": {"wsae_encode_topk": (155.82e6, 6022.0e6), "wsae_decode_backward": (896.37e6, 4655.6e6),
+                 "wsae_wgrad_gemm": (289.79e6, 3436.5e6)},
+    "large-dp": {"wsae_encode_topk": (334.74e6, 23662.3e6), "wsae_decode_backward": (1541.80e6, 8688.1e6),
+                 "wsae_wgrad_gemm": (1094.70e6, 17442.1e6)},
 }
-NCU_SOURCE = "profiles/r2a_{wl}_top3_ncu_full.txt"
+NCU_SOURCE = "profiles/r2c_{wl}_top3_ncu_full.txt"
 
 
 def rooflines(prof: dict, wl_name: str, wl: dict, batch: int, peaks: dict, peak_src: str) -> tuple[dict, dict]:

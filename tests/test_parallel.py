@@ -214,3 +214,71 @@ def test_nccl_two_rank_step_matches_golden_and_single_device(tmp_path):
         b = by["bf16_768x6144_vs_single"]
         assert b["loss_rel"] <= 1e-4 and b["l0_equal"] and b["dead_equal"] and b["counters_equal"], b
         assert b["weight_rel"] <= 2e-2 and b["replicas_identical"], b
+
+
+@pytest.mark.gpu
+def test_operand_gather_across_batch_shapes_epochs_and_checkpoints(tmp_path):
+    """bf16 operand gather of the sharded optimizer: the gathered bf16 operands are trainer-wide, so a
+    ragged last batch (another graphed-step object), `train_epoch`'s consolidation of the fp32 rows,
+    the full re-pack after it and `save_checkpoint` (collective) must all keep two emulated ranks on
+    the single-device trajectory."""
+    from oracle import topk_sae_oracle as O
+    from whisper_sae_b200.config import TrainingConfig
+    from whisper_sae_b200.sae import SAETrainer, TopKSAE
+
+    d, F, k, B, tol = 128, 1024, 16, 256, 2e-3
+    sizes = [B, B, B, B // 2]                       # ragged last batch
+    cfg = TrainingConfig(batch_size=B, use_amp=True, num_workers=0, learning_rate=1e-3, warmup_steps=2)
+    x = O.synthetic_activations(sum(sizes), d, seed=13).cuda()
+    cuts = [sum(sizes[:i]) for i in range(len(sizes) + 1)]
+
+    def make(tag, **kw):
+        torch.manual_seed(3)
+        sae = TopKSAE(d, F, k=k, dead_feature_threshold=1)
+        tr = SAETrainer(sae, cfg, device="cuda", run_dir=tmp_path / tag, **kw)
+        tr.setup_scheduler(50)
+        return tr
+
+    single = make("single")
+    ref = [single.train_epoch([[x[cuts[i]:cuts[i + 1]]] for i in range(len(sizes))]) for _ in range(2)]
+    comms = parallel.ThreadCommunicator.make(2)
+    ranks = [make(f"rank{r}", data_parallel=True, dp_comm=comms[r]) for r in range(2)]
+    got, errors, paths = [None, None], [], [None, None]
+
+    def work(r):
+        try:
+            torch.cuda.set_device(0)
+            out = []
+            for _ in range(2):
+                batches = []
+                for i, n in enumerate(sizes):
+                    a, b = parallel.shard_rows(n, 2, r)
+                    batches.append([x[cuts[i] + a:cuts[i] + b]])
+                out.append(ranks[r].train_epoch(batches))
+            got[r] = out
+            paths[r] = ranks[r].save_checkpoint("ckpt.pt")
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            comms[r].shared.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+    gs = list(ranks[0]._graphs.values())
+    assert len(gs) == 2 and all(g.zero for g in gs)            # two batch shapes, one operand set
+    assert not ranks[0]._dp_weights_stale                      # train_epoch consolidated
+    for e in range(2):
+        for s in range(len(sizes)):
+            for r in range(2):
+                assert got[r][e][s].loss == pytest.approx(ref[e][s].loss, rel=tol)
+                assert got[r][e][s].l0 == ref[e][s].l0
+    want = single.model.state_dict()
+    for r in range(2):
+        sd = torch.load(paths[r], map_location="cuda")["model_state_dict"]
+        assert torch.equal(sd["feature_last_activated"], want["feature_last_activated"])
+        for n in ("encoder.weight", "decoder.weight", "encoder.bias", "decoder.bias", "b_pre"):
+            scale = want[n].abs().max().item()
+            torch.testing.assert_close(sd[n], want[n], rtol=tol * 10, atol=tol * scale, msg=lambda m: f"{n}: {m}")
+    for p, q in zip(ranks[0].model.parameters(), ranks[1].model.parameters()):
+        assert torch.equal(p, q)

@@ -514,18 +514,21 @@ class _GraphedStep:
         self.ctl.copy_(self.ctl_host, non_blocking=True)
         self.calls += 1
         tr.model._w_decT()
-        if self.zero:
-            self._operands()
-            if not tr._dp_operands_fresh:
-                self._refresh_operands()
-            tr._dp_weights_stale = True      # after this step the fp32 rows of other ranks are one step behind
         key = self._pointer_key()
         if key != self._ptrs:      # storage was swapped behind our back (.data = ..., load): re-capture
             self.graph = None
-            if self.zero and self._ptrs and not tr._dp_weights_stale:
-                self._refresh_operands()
+            if self._ptrs:
+                tr._dp_operands_fresh = False      # new weights: the gathered bf16 operands are void
             self._ptrs = key
             self.calls = 1
+        if self.zero:
+            self._operands()
+            if not tr._dp_operands_fresh:
+                if tr._dp_weights_stale:
+                    raise RuntimeError("data parallel: the model's weights were replaced while this replica's "
+                                       "fp32 rows were stale - call trainer.consolidate_weights() first")
+                self._refresh_operands()
+            tr._dp_weights_stale = True      # after this step the fp32 rows of other ranks are one step behind
         if self.calls > 1 and tr.cuda_graph == "segments":
             # data parallel: the kernels between the collectives are four CUDA graphs (compute up to
             # dW_enc | dW_dec + b_pre gradient | counters + gradient norm | optimizer), the NCCL calls
