@@ -289,3 +289,67 @@ def test_adamw_multi_matches_torch_with_renorm():
         torch.cuda.synchronize()
         for p, r in zip(gp, ref_p):
             torch.testing.assert_close(p.cpu(), r.detach(), rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("B,d,F,k", [(128, 384, 3072, 32), (64, 384, 3072, 32), (37, 96, 400, 16),
+                                     (256, 768, 6144, 32), (5, 64, 128, 8)])
+def test_row_step_small_batch_form(B, d, F, k):
+    """wsae_row_step (one block per row: TopK selection + decode + MSE + stamps + dv + bias gradients +
+    both weight-gradient rows) against the dense K1 form's selection and a plain fp32 statement of the
+    rest (model.py:114-148 and its autograd), same bf16 operand roundings as K23."""
+    ops = _ops()
+    torch.manual_seed(B + d)
+    state = O.init_state(d, F)
+    state["b_pre"] = torch.randn(d) * 0.05
+    state["decoder.weight"] = state["decoder.weight"].to(torch.bfloat16).float()
+    x = O.synthetic_activations(B, d, seed=B + 7)
+    dev = "cuda"
+    a = ops.pack_activations(x.cuda(), state["b_pre"].cuda(), 1)
+    w = ops.pack_encoder(state["encoder.weight"].cuda(), state["encoder.bias"].cuda(), 1)
+    idx_ref, val_ref = ops.encode_topk(a, w, B, F, d, 1, k)               # dense small-batch form of K1
+    pre = ops.encode_dense(a, w, B, F, d, 1)
+    w_decT = state["decoder.weight"].t().contiguous()
+    stats = torch.zeros(3, dtype=torch.int64, device=dev)
+    last = torch.zeros(F, dtype=torch.int64, device=dev)
+    step = torch.tensor(6, dtype=torch.int64, device=dev)
+    dbe, dbd, dbp = torch.zeros(F, device=dev), torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    dwe, dwd = torch.zeros(F, d, device=dev), torch.zeros(F, d, device=dev)
+    resid = torch.empty(B, d, device=dev)
+    dpre = torch.empty(B, k, device=dev)
+    grad_out, coef = 0.5, 2.0 / (B * d)
+    assert ops.row_step_supported(B, d, F, k, True)
+    idx, val = ops.row_step(pre, x.cuda(), w_decT.cuda().to(torch.bfloat16), state["decoder.bias"].cuda(),
+                            state["b_pre"].cuda(), torch.tensor(grad_out, device=dev), coef, k, stats=stats,
+                            last_activated=last, step_count=step, d_b_enc=dbe, d_b_dec=dbd, d_w_enc=dwe,
+                            d_w_decT=dwd, resid=resid, dpre_val=dpre, w_enc=state["encoder.weight"].cuda(),
+                            d_b_pre=dbp)
+    torch.cuda.synchronize()
+    assert torch.equal(idx, idx_ref) and torch.equal(val, val_ref)
+    idx_c, val_c = idx.cpu().long(), val.cpu()
+    h = torch.relu(val_c)
+    rows = w_decT[idx_c]                                                   # [B, k, d]
+    recon = (h.to(torch.bfloat16).float().unsqueeze(-1) * rows).sum(1) + state["decoder.bias"] + state["b_pre"]
+    resid_ref = recon - x
+    s = coef * grad_out
+    dv_ref = s * (resid_ref.to(torch.bfloat16).float().unsqueeze(1) * rows).sum(-1) * (val_c > 0)
+
+    def close(got, want, name, rtol=2e-5, arel=2e-6):
+        scale = want.abs().max().item() + 1e-30
+        torch.testing.assert_close(got.cpu(), want, rtol=rtol, atol=arel * scale, msg=lambda m: f"{name}: {m}")
+
+    close(resid, resid_ref, "resid")
+    raw = stats.cpu()
+    assert raw[:1].view(torch.float64).item() == pytest.approx((resid_ref.double() ** 2).sum().item(), rel=1e-6)
+    assert raw[1].item() == int((val_c > 0).sum())
+    want_last = torch.zeros(F, dtype=torch.int64)
+    want_last[idx_c[val_c > 0]] = 7
+    assert torch.equal(last.cpu(), want_last)
+    close(dpre, dv_ref, "dpre", rtol=1e-4, arel=1e-5)
+    close(dbe, torch.zeros(F).index_add_(0, idx_c.reshape(-1), dv_ref.reshape(-1)), "db_enc", rtol=1e-4, arel=1e-5)
+    close(dbd, s * resid_ref.sum(0), "db_dec", rtol=1e-4, arel=1e-5)
+    dense_dv = torch.zeros(B, F).scatter_(1, idx_c, dv_ref)
+    dense_h = torch.zeros(B, F).scatter_(1, idx_c, h)
+    close(dwe, dense_dv.t() @ (x - state["b_pre"]), "dW_enc", rtol=1e-4, arel=1e-5)
+    close(dwd, s * dense_h.t() @ resid_ref, "dW_decT", rtol=1e-4, arel=1e-5)
+    # db_pre = db_dec - db_enc . W_enc (what wsae_bpre_grad computes from the finished sums)
+    close(dbp, s * resid_ref.sum(0) - dense_dv.sum(0) @ state["encoder.weight"], "db_pre", rtol=1e-4, arel=2e-5)

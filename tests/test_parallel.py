@@ -104,10 +104,14 @@ def test_thread_communicator_cpu():
 @pytest.mark.gpu
 @pytest.mark.parametrize("shard", [True, False])
 @pytest.mark.parametrize("use_amp,tol", [(False, 2e-6), (True, 2e-3)])
-def test_batch_sharded_step_matches_single_device(tmp_path, use_amp, tol, shard):
+def test_batch_sharded_step_matches_single_device(tmp_path, use_amp, tol, shard, monkeypatch):
     """Two emulated ranks (threads, one GPU) x B/2 rows == one device x B rows: same losses, same
     counters (bit-exact), same weights after 3 steps - with the sharded optimizer (reduce-scatter,
     AdamW on this rank's feature rows, all-gather) and with the replicated one (all-reduce)."""
+    # same kernels on both sides (what is under test is the exchange): the single-device arm would
+    # otherwise take the one-block-per-row small-batch form at 256 rows, whose fp32 x fp32 weight-gradient
+    # rows differ from K4's bf16 operands in the last bits - enough for early-Adam sign flips
+    monkeypatch.setenv("WSAE_ROW_STEP_ROWS", "0")
     from oracle import topk_sae_oracle as O
     from whisper_sae_b200.config import TrainingConfig
     from whisper_sae_b200.sae import SAETrainer, TopKSAE
@@ -217,7 +221,7 @@ def test_nccl_two_rank_step_matches_golden_and_single_device(tmp_path):
 
 
 @pytest.mark.gpu
-def test_operand_gather_across_batch_shapes_epochs_and_checkpoints(tmp_path):
+def test_operand_gather_across_batch_shapes_epochs_and_checkpoints(tmp_path, monkeypatch):
     """bf16 operand gather of the sharded optimizer: the gathered bf16 operands are trainer-wide, so a
     ragged last batch (another graphed-step object), `train_epoch`'s consolidation of the fp32 rows,
     the full re-pack after it and `save_checkpoint` (collective) must all keep two emulated ranks on
@@ -226,6 +230,7 @@ def test_operand_gather_across_batch_shapes_epochs_and_checkpoints(tmp_path):
     from whisper_sae_b200.config import TrainingConfig
     from whisper_sae_b200.sae import SAETrainer, TopKSAE
 
+    monkeypatch.setenv("WSAE_ROW_STEP_ROWS", "0")  # same kernels in the single-device arm (see the test above)
     d, F, k, B, tol = 128, 1024, 16, 256, 2e-3
     sizes = [B, B, B, B // 2]                       # ragged last batch
     cfg = TrainingConfig(batch_size=B, use_amp=True, num_workers=0, learning_rate=1e-3, warmup_steps=2)

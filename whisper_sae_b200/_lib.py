@@ -75,6 +75,17 @@ _SIGNATURES = {
          c_void_p, c_void_p, c_void_p, c_void_p],
         c_int,
     ),
+    "wsae_graph_launch": ([c_void_p, c_void_p], c_int),
+    "wsae_encode_dense": (
+        [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+        c_int,
+    ),
+    "wsae_row_step": (
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+         c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+        c_int,
+    ),
     "wsae_decode_mse": (
         [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

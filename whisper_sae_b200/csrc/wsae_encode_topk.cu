@@ -29,6 +29,7 @@
 #include <unordered_map>
 
 #include "wsae_common.cuh"
+#include "wsae_rowselect.cuh"
 
 namespace wsae {
 
@@ -1894,151 +1895,17 @@ encode_dense_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-// One block (256 threads) per row: the k largest of pre[row, 0:F].  Keys (order-preserving integer
-// image of the floats; NaN -> 0 = never selected) live in shared memory.  Four passes of an 8-bit
-// most-significant-digit radix select find the key T of the k-th largest value and how many keys
-// lie above it; then every thread walks a CONTIGUOUS chunk of features, a block scan turns the
-// per-thread counts into output slots, and ties at T are admitted in ascending feature index.
-constexpr int kRowTopkThreads = 256;
+// One block (256 threads) per row: the k largest of pre[row, 0:F] (block_row_topk, wsae_rowselect.cuh).
 __global__ void __launch_bounds__(kRowTopkThreads)
 rowwise_topk_kernel(const float* __restrict__ pre, int B, int F, int k, float* __restrict__ out_val,
                     int32_t* __restrict__ out_idx) {
   extern __shared__ __align__(16) uint32_t s_key[];          // [F]
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_pick[2];                             // chosen digit, count above it
-  __shared__ uint32_t s_scan[kRowTopkThreads / 32];
+  __shared__ RowSelectSmem sm;
   pdl_prologue();
   const int row = blockIdx.x;
   if (row >= B) return;
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const float* src = pre + static_cast<size_t>(row) * F;
-  for (int f = tid; f < F; f += kRowTopkThreads) {
-    const float v = src[f];
-    s_key[f] = (v == v) ? f2key(v) : 0u;
-  }
-  uint32_t prefix = 0, prefix_mask = 0;       // bits decided so far
-  uint32_t need = static_cast<uint32_t>(k);   // rank still wanted inside the prefix bucket
-  uint32_t above = 0;                         // keys strictly above the prefix bucket
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    s_hist[tid] = 0u;
-    __syncthreads();
-    for (int f = tid; f < F; f += kRowTopkThreads) {
-      const uint32_t kk = s_key[f];
-      if ((kk & prefix_mask) == prefix && kk != 0u) atomicAdd(&s_hist[(kk >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      // lane l owns digits 8 l .. 8 l + 7; suffix sums from the top digit down
-      uint32_t loc[8], tot = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        loc[i] = s_hist[8 * lane + i];
-        tot += loc[i];
-      }
-      uint32_t suf = tot;                      // inclusive suffix sum over lanes >= l
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
-        if (lane + o < 32) suf += t;
-      }
-      const uint32_t higher = suf - tot;       // keys in digits above this lane's 8
-      const bool here = higher < need && suf >= need;
-      if (here) {
-        uint32_t acc = higher;                 // keys above digit i inside the prefix bucket
-        int dsel = 0;
-        bool found = false;
-#pragma unroll
-        for (int i = 7; i >= 0; --i) {
-          if (!found) {
-            if (acc + loc[i] >= need) {
-              dsel = i;
-              found = true;
-            } else {
-              acc += loc[i];
-            }
-          }
-        }
-        s_pick[0] = static_cast<uint32_t>(8 * lane + dsel);
-        s_pick[1] = acc;
-      }
-      if (lane == 0 && suf < need) {           // fewer than `need` valid keys: keep them all
-        s_pick[0] = 0xFFFFFFFFu;
-        s_pick[1] = 0u;
-      }
-    }
-    __syncthreads();
-    const uint32_t dsel = s_pick[0];
-    if (dsel == 0xFFFFFFFFu) {                 // (only possible in the first pass: NaN rows, k > valid keys)
-      prefix = 0u;
-      prefix_mask = 0u;
-      need = 0u;
-      break;
-    }
-    above += s_pick[1];
-    need -= s_pick[1];
-    prefix |= dsel << shift;
-    prefix_mask |= 255u << shift;
-    __syncthreads();
-  }
-  // prefix = key T of the k-th largest value (or 0: keep every valid key); `above` keys exceed it
-  const uint32_t T = prefix_mask ? prefix : 0u;
-  const uint32_t ties_wanted = prefix_mask ? static_cast<uint32_t>(k) - above : 0u;
-  // contiguous chunks: thread t owns features [t * per, (t + 1) * per)
-  const int per = ceil_div(F, kRowTopkThreads);
-  const int f_lo = tid * per, f_hi = min(F, f_lo + per);
-  uint32_t n_gt = 0, n_tie = 0;
-  for (int f = f_lo; f < f_hi; ++f) {
-    const uint32_t kk = s_key[f];
-    n_gt += (kk > T) ? 1u : 0u;
-    n_tie += (prefix_mask && kk == T) ? 1u : 0u;
-  }
-  // block exclusive scan of (n_gt | n_tie << 16)
-  uint32_t packed = n_gt | (n_tie << 16);
-  uint32_t incl = packed;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_scan[warp] = incl;
-  __syncthreads();
-  uint32_t woff = 0;
-  for (int w = 0; w < warp; ++w) woff += s_scan[w];
-  const uint32_t excl = incl - packed + woff;
-  uint32_t gt_before = excl & 0xFFFFu, tie_before = excl >> 16;
-  float* ov = out_val + static_cast<size_t>(row) * k;
-  int32_t* oi = out_idx + static_cast<size_t>(row) * k;
-  for (int f = f_lo; f < f_hi; ++f) {
-    const uint32_t kk = s_key[f];
-    const bool gt = kk > T;
-    const bool tie = prefix_mask && kk == T;
-    bool keep = gt;
-    if (tie) {
-      keep = tie_before < ties_wanted;
-      ++tie_before;
-    }
-    if (keep && kk != 0u) {
-      // slot = kept entries before f: all greater ones + the admitted ties
-      const uint32_t ties_kept_before = min(tie_before - (tie ? 1u : 0u), ties_wanted);
-      const uint32_t slot = gt_before + ties_kept_before;
-      if (slot < static_cast<uint32_t>(k)) {
-        ov[slot] = src[f];
-        oi[slot] = f;
-      }
-    }
-    gt_before += gt ? 1u : 0u;
-  }
-  // fewer than k valid candidates (NaN rows): pad with (-inf, -1) like the fused epilogue
-  if (!prefix_mask) {
-    __syncthreads();
-    uint32_t total_valid = 0;
-    for (int w = 0; w < kRowTopkThreads / 32; ++w) total_valid += s_scan[w] & 0xFFFFu;
-    for (int sidx = static_cast<int>(total_valid) + tid; sidx < k; sidx += kRowTopkThreads) {
-      ov[sidx] = __uint_as_float(0xff800000u);
-      oi[sidx] = -1;
-    }
-  }
+  block_row_topk(pre + static_cast<size_t>(row) * F, F, k, s_key, sm, out_val + static_cast<size_t>(row) * k,
+                 out_idx + static_cast<size_t>(row) * k);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2270,18 +2137,14 @@ extern "C" int wsae_encode_topk(const void* a_packed, const void* w_packed, int 
 }
 
 
-// Small-batch form of wsae_encode_topk (see encode_dense_kernel): `pre_ws` is B * F floats of scratch.
-// Same results as wsae_encode_topk (values bit-identical: the same MMA sequence; ties to the lowest
-// feature index), output in ascending feature index.  F * 4 bytes of shared memory per row block:
-// F <= 49152.
-extern "C" int wsae_encode_topk_dense(const void* a_packed, const void* w_packed, int B, int Bp, int F,
-                                      int Fp, int Kp, int k_used_cols, int k, float* pre_ws,
-                                      float* out_val, int32_t* out_idx, cudaStream_t stream) {
-  if (!a_packed || !w_packed || !pre_ws || !out_val || !out_idx) return kBadArg;
-  if (B <= 0 || F <= 0 || k <= 0 || k > F) return kBadArg;
+// The GEMM half of the small-batch form: pre_ws[B, F] = A' x W'^T (bias included), nothing else.
+extern "C" int wsae_encode_dense(const void* a_packed, const void* w_packed, int B, int Bp, int F, int Fp,
+                                 int Kp, int k_used_cols, float* pre_ws, cudaStream_t stream) {
+  if (!a_packed || !w_packed || !pre_ws) return kBadArg;
+  if (B <= 0 || F <= 0) return kBadArg;
   if (Bp % kBM != 0 || Fp % kBN != 0 || Kp % kBK != 0 || Bp < B || Fp < F) return kBadArg;
   if (k_used_cols <= 0 || k_used_cols % 16 != 0 || k_used_cols > Kp) return kBadArg;
-  if (F > 49152 || k > 0xFFFF || F % 4 != 0) return kUnsupported;
+  if (F % 4 != 0) return kUnsupported;
   CUtensorMap ta, tw;
   int rc = make_tmap_bf16(&ta, a_packed, static_cast<uint64_t>(Bp), static_cast<uint64_t>(Kp), kBM);
   if (rc) return rc;
@@ -2292,13 +2155,10 @@ extern "C" int wsae_encode_topk_dense(const void* a_packed, const void* w_packed
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   constexpr int kStages = 3;
   constexpr int smem_g = kStages * (kAStage + kBStage) + 256 + 1024;
-  const size_t smem_t = static_cast<size_t>(F) * 4;
   static bool attr_set[64] = {};
   if (dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(encode_dense_kernel<kStages>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(rowwise_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     if (dev < 64) attr_set[dev] = true;
   }
@@ -2308,9 +2168,32 @@ extern "C" int wsae_encode_topk_dense(const void* a_packed, const void* w_packed
   const int grid = total < num_sms ? total : num_sms;
   cudaError_t e = launch_pdl(encode_dense_kernel<kStages>, grid, 256, smem_g, stream, ta, tw, B, F,
                              k_used_cols / 16, num_m_blocks, num_n_tiles, pre_ws);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  e = launch_pdl(rowwise_topk_kernel, B, kRowTopkThreads, smem_t, stream, static_cast<const float*>(pre_ws), B, F,
-                 k, out_val, out_idx);
+  return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
+}
+
+// Small-batch form of wsae_encode_topk (see encode_dense_kernel): `pre_ws` is B * F floats of scratch.
+// Same results as wsae_encode_topk (values bit-identical: the same MMA sequence; ties to the lowest
+// feature index), output in ascending feature index.  F * 4 bytes of shared memory per row block:
+// F <= 49152.
+extern "C" int wsae_encode_topk_dense(const void* a_packed, const void* w_packed, int B, int Bp, int F,
+                                      int Fp, int Kp, int k_used_cols, int k, float* pre_ws,
+                                      float* out_val, int32_t* out_idx, cudaStream_t stream) {
+  if (!out_val || !out_idx) return kBadArg;
+  if (k <= 0 || k > F) return kBadArg;
+  if (F > 49152 || k > 0xFFFF) return kUnsupported;
+  int rc = wsae_encode_dense(a_packed, w_packed, B, Bp, F, Fp, Kp, k_used_cols, pre_ws, stream);
+  if (rc) return rc;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t smem_t = static_cast<size_t>(F) * 4;
+  static bool attr_set[64] = {};
+  if (dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(rowwise_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (dev < 64) attr_set[dev] = true;
+  }
+  cudaError_t e = launch_pdl(rowwise_topk_kernel, B, kRowTopkThreads, smem_t, stream, static_cast<const float*>(pre_ws), B, F,
+                             k, out_val, out_idx);
   return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
 }
 

@@ -19,7 +19,14 @@ from . import _lib
 GPU_LAUNCHES = 0  # kernels launched through this module (bench.py reports it)
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw C getter: the Python
+    `torch.cuda.current_stream()` wrapper costs ~8 us per call, which the 60 us YAML-batch step notices)."""
+    if _RAW_STREAM is not None:
+        return _RAW_STREAM(torch._C._cuda_getDevice())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -271,6 +278,65 @@ def backward_sparse(resid: Tensor, x: Tensor | None, b_pre: Tensor | None, w_dec
         raise RuntimeError("input_dim must be a multiple of 4 for the sparse backward kernels")
     lib = _lib.load()
     _run("wsae_backward_sparse", lib.wsae_backward_sparse, _ptr(resid), _ptr(x), _ptr(b_pre), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(d_w_enc), _ptr(d_w_decT), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _ptr(resid_bf16), _stream())
+
+
+def graph_launch(graph_exec: int) -> None:
+    """cudaGraphLaunch(graph_exec, current stream) through the library (see SAETrainer's graphed step)."""
+    lib = _lib.load()
+    _lib.check(lib.wsae_graph_launch(graph_exec, _stream()), "wsae_graph_launch")
+
+
+def row_step_supported(B: int, d: int, F: int, k: int, bf16: bool) -> bool:
+    """Shapes the one-block-per-row small-batch step covers (else: K1 selection + K23 + bucket + K4)."""
+    return (bf16 and B <= int(os.environ.get("WSAE_ROW_STEP_ROWS", "512")) and k <= 32 and d % 8 == 0
+            and F % 4 == 0 and (F + 2 * d) * 4 <= 200 * 1024)
+
+
+def encode_dense(a_packed: Tensor, w_packed: Tensor, B: int, F: int, d: int, terms: int,
+                 out: Tensor | None = None) -> Tensor:
+    """The GEMM of K1 alone: dense pre-activations [B, F] fp32 (small batches: L2-sized scratch)."""
+    _need_cuda(a_packed, w_packed)
+    ps = packed_shape(d, terms)
+    if a_packed.dtype != torch.bfloat16 or a_packed.shape[1] != ps.kp or w_packed.shape[1] != ps.kp:
+        raise RuntimeError("packed operands do not match (d, terms)")
+    if out is None:
+        out = torch.empty((B, F), dtype=torch.float32, device=a_packed.device)
+    lib = _lib.load()
+    _run("wsae_encode_topk", lib.wsae_encode_dense, _ptr(a_packed), _ptr(w_packed), B, a_packed.shape[0], F,
+         w_packed.shape[0], ps.kp, ps.used_cols, _ptr(out), _stream())
+    return out
+
+
+def row_step(pre: Tensor, target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: Tensor | None,
+             grad_out: Tensor | None, coef: float, k: int, *, stats: Tensor | None,
+             last_activated: Tensor | None, step_count: Tensor | None, d_b_enc: Tensor | None,
+             d_b_dec: Tensor | None, d_w_enc: Tensor | None, d_w_decT: Tensor | None,
+             resid: Tensor | None = None, dpre_val: Tensor | None = None, target_is_slot: bool = False,
+             rows_at: Tensor | None = None, w_enc: Tensor | None = None,
+             d_b_pre: Tensor | None = None) -> tuple[Tensor, Tensor]:
+    """Small-batch step, one block per row: TopK of ``pre`` + sparse decode + MSE + stamps + dv + bias
+    gradients + both weight-gradient rows (fp32 atomics).  Returns (idx int32 [B,k], val fp32 [B,k])."""
+    _need_cuda(pre, target, w_decT, b_dec, b_pre, grad_out)
+    _f32c(pre, "pre")
+    B, F = pre.shape
+    d = w_decT.shape[1]
+    if w_decT.dtype != torch.bfloat16 or not w_decT.is_contiguous() or w_decT.shape[0] != F:
+        raise RuntimeError("w_decT must be contiguous [F, d] bfloat16")
+    if target_is_slot:
+        if target.dtype != torch.int64 or target.numel() != 1:
+            raise RuntimeError("target slot must be a one-element int64 CUDA tensor")
+        tgt, tgt_at = None, target
+    else:
+        _f32c(target, "target")
+        tgt, tgt_at = target, None
+    idx = torch.empty((B, k), dtype=torch.int32, device=pre.device)
+    val = torch.empty((B, k), dtype=torch.float32, device=pre.device)
+    lib = _lib.load()
+    _run("wsae_row_step", lib.wsae_row_step, _ptr(pre), _ptr(tgt), _ptr(tgt_at), _ptr(rows_at), _ptr(w_decT),
+         _ptr(b_dec), _ptr(b_pre), _ptr(grad_out), float(coef), B, d, F, k, _ptr(val), _ptr(idx), _ptr(stats),
+         _ptr(last_activated), _ptr(step_count), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(d_w_enc), _ptr(d_w_decT),
+         _ptr(resid), _ptr(dpre_val), _ptr(w_enc), _ptr(d_b_pre), _stream())
+    return idx, val
 
 
 def decode_backward_supported(d: int, k: int, bf16: bool) -> bool:

@@ -144,6 +144,11 @@ class _GraphedStep:
         # YAML batch) leave most SMs idle, so dW_dec runs beside dW_enc on a second branch of the graph
         # (96.9 -> 92.7 us per step at 128 rows; no gain from 1024 rows on: profiles/r2c_k4_fork_ab.txt)
         self.fork_k4 = self.fork and rows <= int(os.environ.get("WSAE_FORK_K4_ROWS", "512"))
+        # batches of a few hundred rows (the shipped YAML batch is 128): one block per row does the TopK
+        # selection, K23 and both weight-gradient rows in ONE launch (wsae_row_step.cu) instead of the
+        # five dependent launches rowwise top-k -> K23 -> bucketing -> 2 x K4
+        self.row_step = (self.in_place and not trainer.data_parallel and not trainer.deterministic
+                         and ops.row_step_supported(rows, d_in, m.hidden_dim, k_sel, True))
         self._side2 = torch.cuda.Stream(device=dev) if self.fork_k4 else None
         self._k4_forked = False
         self._w_packed_buf: Tensor | None = None
@@ -208,6 +213,7 @@ class _GraphedStep:
             self.det_sumsq = torch.empty(1024, dtype=torch.float64, device=dev)
             self.det_bpre = torch.empty((F + 255) // 256 * d, dtype=torch.float32, device=dev)
         self.graph: torch.cuda.CUDAGraph | list | None = None
+        self._exec: int | None = None     # cudaGraphExec_t of `graph` (raw launch, see _launch_graph)
         self._mid: dict = {}
         self.kernels_per_replay = 0
         self.calls = 0
@@ -338,22 +344,50 @@ class _GraphedStep:
             with torch.cuda.stream(self._side):
                 w_packed = self._w_packed_buf = ops.pack_encoder(
                     m.encoder.weight.data, m.encoder.bias.data, terms, out=self._w_packed_buf)
-                w_used = ops.cast_bf16(w_decT, out=self._w_used_buf)
+                if self._side2 is None:
+                    w_used = ops.cast_bf16(w_decT, out=self._w_used_buf)
+            if self._side2 is not None:      # small batches: the two weight-side kernels side by side
+                self._side2.wait_stream(main)
+                with torch.cuda.stream(self._side2):
+                    w_used = ops.cast_bf16(w_decT, out=self._w_used_buf)
         if self.in_place:
             a_packed = ops.pack_activations_at(self.x_slot, B, d, m.b_pre.data, rows_at=self.rows_slot)
         else:
             a_packed = ops.pack_activations(x, m.b_pre.data, terms)
         if self.fork:
             main.wait_stream(self._side)
+            if self._side2 is not None:
+                main.wait_stream(self._side2)
         elif self.zero:
             w_packed, w_used = self._operands()      # gathered at the end of the previous step
         else:
             w_packed = ops.pack_encoder(m.encoder.weight.data, m.encoder.bias.data, terms)
+        rows_total = m._global_rows or B
+        coef = 2.0 / (float(rows_total) * d)
+        if self.row_step:
+            if not self.fork:
+                w_used = ops.cast_bf16(w_decT)
+            pre = ops.encode_dense(a_packed, w_packed, B, F, d, terms)
+            idx, val = ops.row_step(pre, self.x_slot, w_used, m.decoder.bias.data, m.b_pre.data, self.one, coef, k,
+                                    stats=self.stats, last_activated=m.feature_last_activated,
+                                    step_count=m.step_count, d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec,
+                                    d_w_enc=self.g_w_enc, d_w_decT=self.g_w_decT, target_is_slot=True,
+                                    rows_at=self.rows_slot, w_enc=m.encoder.weight.data, d_b_pre=self.g_b_pre)
+            if self.fork:
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):      # joined in _update_pre, before the gradient norm
+                    self._counters()
+            else:
+                self._counters()
+            self._k4_forked = False
+            self._mid = dict(use_gemm=False, buckets=None, resid_bf=None, B=B, d=d, coef=coef)
+            st = self.state
+            st.idx, st.val, st.resid, st.stats, st.w_dec_used, st.rows_total = idx, val, None, self.stats, w_used, rows_total
+            st.d_out = d
+            return
         idx, val = ops.encode_topk(a_packed, w_packed, B, F, d, terms, k)
         if not self.fork and not self.zero:
             w_used = ops.cast_bf16(w_decT) if self.bf16 else w_decT
-        rows_total = m._global_rows or B
-        coef = 2.0 / (float(rows_total) * d)
         dpre = torch.empty((B, k), dtype=torch.float32, device=dev)
         use_gemm = self.bf16 and ops.wgrad_gemm_supported(d)
         if use_gemm and ops.decode_backward_supported(d, k, True):
@@ -416,7 +450,7 @@ class _GraphedStep:
             ops.wgrad_gemm_(self.g_w_decT, mid["resid_bf"], mid["B"], mid["d"], mid["buckets"],
                             mid["buckets"].act, self.one, mid["coef"],
                             det_ws=self.det_k4 if self.det else None)
-        if not self.fork and not self.zero:      # operand-gather mode: after the exchange (_exchange)
+        if not self.fork and not self.zero and not self.row_step:   # operand-gather mode: after the exchange
             ops.bpre_grad(self.g_b_dec, self.g_b_enc, m.encoder.weight.data, out=self.g_b_pre,
                           det_ws=self.det_bpre)
 
@@ -460,6 +494,23 @@ class _GraphedStep:
         ops.counters_update(m.feature_last_activated, m.step_count, m.dead_feature_threshold, True,
                             self.stats[2:], post=(self.stats[:2], self.seq_dev, self.mailbox))
 
+    def _launch_graph(self) -> None:
+        """cudaGraphLaunch of the captured step on the current stream.  torch's CUDAGraph.replay() costs
+        ~25 us of host time per call (generator bookkeeping, guards); the YAML-batch step's GPU floor is
+        ~60 us, so the raw launch through the library (wsae_graph_launch) keeps the loop GPU-bound."""
+        if self._exec is None:
+            raw = getattr(self.graph, "raw_cuda_graph_exec", None)
+            self._exec = 0
+            if raw is not None and os.environ.get("WSAE_RAW_LAUNCH", "1") != "0":
+                try:
+                    self._exec = int(raw())
+                except Exception:  # noqa: BLE001 - older torch / not instantiated: CUDAGraph.replay() it is
+                    self._exec = 0
+        if self._exec:
+            ops.graph_launch(self._exec)
+        else:
+            self.graph.replay()
+
     def wait_metrics(self) -> tuple[float, int, int]:
         """(sse, l0 count, dead count) of the step launched last: polls the mailbox's sequence word."""
         mb, seq = self.mailbox_np, self.seq
@@ -502,9 +553,17 @@ class _GraphedStep:
         self.seq += 1
         self.seq_np[0] = self.seq
         group = tr.optimizer.param_groups[0]
-        for p in self.params:
-            _ensure_adamw_state(tr.optimizer, p)
-        step_t = float(tr.optimizer.state[self.params[0]]["step"]) + 1.0
+        # AdamW state: created / re-laid-out on first use and whenever the optimizer's state objects were
+        # replaced (load_state_dict); otherwise the cached numpy views of the `step` tensors are current
+        opt_state = tr.optimizer.state
+        if len(self._step_views) != len(self.params) or any(
+                opt_state[p].get("step") is not tv[0] for p, tv in zip(self.params, self._step_views)):
+            self._step_views = []
+            for p in self.params:
+                t = _ensure_adamw_state(tr.optimizer, p)["step"]
+                self._step_views.append((t, None if t.is_cuda else t.numpy()))
+        t0, v0 = self._step_views[0]
+        step_t = float(v0 if v0 is not None else t0) + 1.0
         beta1, beta2 = group["betas"]
         h = self.hyper_np
         h[0], h[1], h[2], h[3], h[4] = group["lr"], beta1, beta2, group["eps"], group["weight_decay"]
@@ -513,10 +572,13 @@ class _GraphedStep:
         h[7] = tr.config.gradient_clip
         self.ctl.copy_(self.ctl_host, non_blocking=True)
         self.calls += 1
-        tr.model._w_decT()
+        wd = tr.model.decoder.weight
+        if wd.stride() != (1, wd.shape[0]):      # feature-major storage lost (.data assigned): re-point it
+            tr.model._w_decT()
         key = self._pointer_key()
         if key != self._ptrs:      # storage was swapped behind our back (.data = ..., load): re-capture
             self.graph = None
+            self._exec = None
             if self._ptrs:
                 tr._dp_operands_fresh = False      # new weights: the gathered bf16 operands are void
             self._ptrs = key
@@ -571,18 +633,12 @@ class _GraphedStep:
                 self.kernels_per_replay = ops.GPU_LAUNCHES - before   # captured, not yet executed
                 ops.GPU_LAUNCHES = before
                 self.graph = g
-            self.graph.replay()
+                self._exec = None
+            self._launch_graph()
             ops.GPU_LAUNCHES += self.kernels_per_replay
         # ---- host book-keeping, overlapping the kernels ----
         # torch.optim.AdamW keeps `step` as a CPU float32 tensor per parameter: bump them through
         # cached numpy views (re-made when a load_state_dict swapped the tensors)
-        opt_state = tr.optimizer.state
-        if len(self._step_views) != len(self.params) or any(
-                opt_state[p]["step"] is not tv[0] for p, tv in zip(self.params, self._step_views)):
-            self._step_views = []
-            for p in self.params:
-                t = opt_state[p]["step"]
-                self._step_views.append((t, None if t.is_cuda else t.numpy()))
         for t, view in self._step_views:
             if view is None:
                 t += 1
@@ -778,16 +834,18 @@ class SAETrainer:
     # ------------------------------------------------------------------ the hot loop
     def train_step(self, batch: Tensor | tuple | list) -> TrainingMetrics:
         """One optimisation step; same order of operations as training.py:161-217."""
-        self.model.train()
+        if not self.model.training:      # model.train() walks every submodule: 10+ us of the ~60 us YAML-batch step
+            self.model.train()
         if isinstance(batch, (tuple, list)):
             batch = batch[0]
-        if isinstance(batch, IndexedBatch) and not self._graph_ok(batch):
+        graph_ok = self._graph_ok(batch)
+        if isinstance(batch, IndexedBatch) and not graph_ok:
             batch = batch.materialize()      # only the graphed step gathers rows inside its kernels
         if self.data_parallel:
-            if not self._graph_ok(batch):
+            if not graph_ok:
                 raise RuntimeError("data_parallel=True supports the fused TopKSAE step only")
             self.model._global_rows = self.global_batch_rows or batch.shape[0] * self.dp_comm.world
-        if self._graph_ok(batch):
+        if graph_ok:
             gs = self._graphs.get(batch.shape[0])
             if gs is None:
                 gs = self._graphs[batch.shape[0]] = _GraphedStep(self, batch.shape[0])
@@ -833,10 +891,13 @@ class SAETrainer:
 
     def _graph_ok(self, batch: Tensor) -> bool:
         m = self.model
-        return (self.cuda_graph and isinstance(m, TopKSAE) and type(m).forward is TopKSAE.forward
+        if not (self.cuda_graph and isinstance(m, TopKSAE) and type(m).forward is TopKSAE.forward
                 and batch.dim() == 2 and batch.shape[1] == m.input_dim and m.input_dim % 4 == 0
-                and batch.dtype == torch.float32 and m.k <= 64 and m.precision is None
-                and all(p.requires_grad for p in m.parameters()))
+                and batch.dtype == torch.float32 and m.k <= 64 and m.precision is None):
+            return False
+        # the five parameters by attribute (Module.parameters() walks the module tree: ~10 us per call)
+        return (m.b_pre.requires_grad and m.encoder.weight.requires_grad and m.encoder.bias.requires_grad
+                and m.decoder.weight.requires_grad and m.decoder.bias.requires_grad)
 
     def _read_metrics(self, output: SAEOutput | None, rows: int) -> TrainingMetrics:
         lr = self.optimizer.param_groups[0]["lr"]
