@@ -213,7 +213,7 @@ class _GraphedStep:
             self.det_sumsq = torch.empty(1024, dtype=torch.float64, device=dev)
             self.det_bpre = torch.empty((F + 255) // 256 * d, dtype=torch.float32, device=dev)
         self.graph: torch.cuda.CUDAGraph | list | None = None
-        self._exec: int | None = None     # cudaGraphExec_t of `graph` (raw launch, see _launch_graph)
+        self._exec: int | list | None = None     # cudaGraphExec_t of `graph` / of its segments (raw launch, see _launch_graph)
         self._mid: dict = {}
         self.kernels_per_replay = 0
         self.calls = 0
@@ -499,17 +499,25 @@ class _GraphedStep:
         ~25 us of host time per call (generator bookkeeping, guards); the YAML-batch step's GPU floor is
         ~60 us, so the raw launch through the library (wsae_graph_launch) keeps the loop GPU-bound."""
         if self._exec is None:
-            raw = getattr(self.graph, "raw_cuda_graph_exec", None)
-            self._exec = 0
-            if raw is not None and os.environ.get("WSAE_RAW_LAUNCH", "1") != "0":
-                try:
-                    self._exec = int(raw())
-                except Exception:  # noqa: BLE001 - older torch / not instantiated: CUDAGraph.replay() it is
-                    self._exec = 0
-        if self._exec:
-            ops.graph_launch(self._exec)
+            self._exec = self._raw_exec(self.graph)
+        self._launch_one(self.graph, self._exec)
+
+    @staticmethod
+    def _raw_exec(graph: torch.cuda.CUDAGraph) -> int:
+        raw = getattr(graph, "raw_cuda_graph_exec", None)
+        if raw is not None and os.environ.get("WSAE_RAW_LAUNCH", "1") != "0":
+            try:
+                return int(raw())
+            except Exception:  # noqa: BLE001 - older torch / not instantiated: CUDAGraph.replay() it is
+                return 0
+        return 0
+
+    @staticmethod
+    def _launch_one(graph: torch.cuda.CUDAGraph, handle: int) -> None:
+        if handle:
+            ops.graph_launch(handle)
         else:
-            self.graph.replay()
+            graph.replay()
 
     def wait_metrics(self) -> tuple[float, int, int]:
         """(sse, l0 count, dead count) of the step launched last: polls the mailbox's sequence word."""
@@ -608,16 +616,19 @@ class _GraphedStep:
                 self.kernels_per_replay = ops.GPU_LAUNCHES - before
                 ops.GPU_LAUNCHES = before
                 self.graph = segs
-            ga, gb, gc, gd = self.graph
-            ga.replay()
+            if not self._exec:        # raw cudaGraphExec_t handles of the four segments (see _launch_graph)
+                self._exec = [self._raw_exec(g) for g in self.graph]
+            launch = self._launch_one
+            (ga, gb, gc, gd), (ea, eb, ec, ed) = self.graph, self._exec
+            launch(ga, ea)
             if self._mid["use_gemm"]:
                 self._start_early()
-            gb.replay()
+            launch(gb, eb)
             self._exchange()
-            gc.replay()
+            launch(gc, ec)
             if self.shard:
                 tr.dp_comm.all_reduce_sum(self.sumsq)
-            gd.replay()
+            launch(gd, ed)
             if self.shard:
                 self._gather_weights()
             ops.GPU_LAUNCHES += self.kernels_per_replay
