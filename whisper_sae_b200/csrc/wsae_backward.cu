@@ -43,14 +43,22 @@ backward_sparse_kernel(const float* __restrict__ resid, const float* __restrict_
   const int warp_stride = gridDim.x * warps_per_block;
   const float s = coef * (grad_out != nullptr ? *grad_out : 1.f);
 
-  float4 bp[NV];
-  float4 gsum[NV];
+  // Wide rows (NV > 8: d > 1024) cannot keep b_pre and the running db_dec sums in registers next to the
+  // row's gradient and centred input (4 x NV float4 = 256 registers at NV = 16: 504 bytes of spills in
+  // round 1): there b_pre is re-read (L1 resident) and db_dec accumulates in shared memory row by row.
+  constexpr bool kLean = NV > 8;
+  constexpr int NR = kLean ? 1 : NV;
+  extern __shared__ float s_g[];  // [d] db_dec of this block
+  for (int i = threadIdx.x; i < d; i += blockDim.x) s_g[i] = 0.f;
+  __syncthreads();
+  float4 bp[NR];
+  float4 gsum[NR];
 #pragma unroll
-  for (int c = 0; c < NV; ++c) {
+  for (int c = 0; c < NR; ++c) {
     const int col = c * 128 + lane * 4;
     bp[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     gsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col < d && b_pre != nullptr) bp[c] = *reinterpret_cast<const float4*>(b_pre + col);
+    if (!kLean && col < d && b_pre != nullptr) bp[c] = *reinterpret_cast<const float4*>(b_pre + col);
   }
 
   for (int row = warp_global; row < B; row += warp_stride) {
@@ -71,10 +79,19 @@ backward_sparse_kernel(const float* __restrict__ resid, const float* __restrict_
           o.y = *reinterpret_cast<uint32_t*>(&hi);
           *reinterpret_cast<uint2*>(resid_bf16 + static_cast<size_t>(row) * d + col) = o;
         }
-        gsum[c].x += g[c].x; gsum[c].y += g[c].y; gsum[c].z += g[c].z; gsum[c].w += g[c].w;
+        if (kLean) {
+          atomicAdd(&s_g[col + 0], g[c].x);
+          atomicAdd(&s_g[col + 1], g[c].y);
+          atomicAdd(&s_g[col + 2], g[c].z);
+          atomicAdd(&s_g[col + 3], g[c].w);
+        } else {
+          gsum[c].x += g[c].x; gsum[c].y += g[c].y; gsum[c].z += g[c].z; gsum[c].w += g[c].w;
+        }
         if (d_w_enc != nullptr) {
           const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d + col);
-          xc[c] = make_float4(xv.x - bp[c].x, xv.y - bp[c].y, xv.z - bp[c].z, xv.w - bp[c].w);
+          float4 b = kLean ? make_float4(0.f, 0.f, 0.f, 0.f) : bp[c];
+          if (kLean && b_pre != nullptr) b = __ldg(reinterpret_cast<const float4*>(b_pre + col));
+          xc[c] = make_float4(xv.x - b.x, xv.y - b.y, xv.z - b.z, xv.w - b.w);
         }
       }
     }
@@ -137,11 +154,8 @@ backward_sparse_kernel(const float* __restrict__ resid, const float* __restrict_
   }
 
   // db_dec: per-block shared reduction, then one atomic per column per block
-  extern __shared__ float s_g[];  // [d]
-  for (int i = threadIdx.x; i < d; i += blockDim.x) s_g[i] = 0.f;
-  __syncthreads();
 #pragma unroll
-  for (int c = 0; c < NV; ++c) {
+  for (int c = 0; c < (kLean ? 0 : NV); ++c) {
     const int col = c * 128 + lane * 4;
     if (col < d) {
       atomicAdd(&s_g[col + 0], gsum[c].x);
