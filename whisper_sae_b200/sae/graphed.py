@@ -85,6 +85,10 @@ class GraphedVariantStep:
         self._out = None
 
     def _body(self, inputs: tuple):
+        # grads set to None first: autograd then ASSIGNS the freshly computed gradient tensors instead of
+        # adding them into the old ones (one read-modify-write pass over every parameter less; inside the
+        # captured graph the assigned tensors live at fixed pool addresses, so replays stay valid)
+        self.optimizer.zero_grad(set_to_none=True)
         with torch.amp.autocast("cuda", enabled=self.use_amp, dtype=torch.bfloat16):
             out = self.model(*inputs)
         out.loss.backward()
@@ -112,13 +116,11 @@ class GraphedVariantStep:
             self._sig, self._graph, self.calls = sig, None, 0
         self.calls += 1
         if self.calls == 1:
-            self.optimizer.zero_grad(set_to_none=True)
             return self._result(self._body(inputs), rows)
         if self._graph is None:
             self._static = tuple(_static_like(v) for v in inputs)
             for dst, src in zip(self._static, inputs):
                 _fill(dst, src)
-            self.optimizer.zero_grad(set_to_none=True)   # backward allocates the grads inside the graph's pool
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with _quiet_gc(), torch.cuda.graph(g):
