@@ -75,8 +75,38 @@ def test_fullsize_train_step_invariants(tmp_path):
             fired[i[v > 0]] = True
             return ((recon - xb) ** 2).mean().item(), float((v > 0).sum()) / B, fired
 
+    def torch_grads(w, xb):
+        """Dense fp32 statement of the step's gradients (same bf16 operand roundings in the forward)."""
+        with torch.no_grad():
+            xc = xb - w["b_pre"]
+            pre = xc.to(torch.bfloat16).float() @ w["encoder.weight"].to(torch.bfloat16).float().t() + w["encoder.bias"]
+            v, i = torch.topk(pre, K, dim=1)
+            del pre
+            wd = w["decoder.weight"].t().to(torch.bfloat16).float()
+            hidden = torch.zeros(B, F, device="cuda").scatter_(1, i, torch.relu(v))
+            g = (hidden.to(torch.bfloat16).float() @ wd + w["decoder.bias"] + w["b_pre"] - xb) * (2.0 / (B * D))
+            dpre = torch.zeros(B, F, device="cuda").scatter_(1, i, (g @ wd.t()).gather(1, i) * (v > 0))
+            return {"encoder.weight": dpre.t() @ xc, "encoder.bias": dpre.sum(0), "decoder.bias": g.sum(0),
+                    "decoder.weight": (hidden.t() @ g).t()}
+
+    g_ref = torch_grads(w0, x[:B])
     loss_ref, l0_ref, fired_ref = torch_forward(w0, x[:B])
     m1 = tr.train_step(x[:B])
+    # the FIRST AdamW step moves every element by ~lr * sign(gradient): where the reference gradient is not
+    # tiny, the weights must have moved against it - a wrong row, a dropped or misplaced gradient tile at the
+    # benchmark's own shape shows up here (the digests above cannot see it)
+    for n in ("encoder.weight", "encoder.bias", "decoder.bias"):
+        delta = sae.state_dict()[n].detach() - w0[n]
+        gr = g_ref[n]
+        big = gr.abs() > 1e-2 * gr.abs().max()
+        agree = (torch.sign(delta[big]) == -torch.sign(gr[big])).double().mean().item()
+        assert big.sum() > 0.01 * gr.numel() and agree > 0.999, (n, agree, int(big.sum()))
+    # and the gradient the step left in .grad is the reference gradient (bf16 operands in K4: 2e-2)
+    for n in ("encoder.weight", "decoder.weight", "encoder.bias", "decoder.bias"):
+        got = dict(sae.named_parameters())[n].grad
+        rel = ((got - g_ref[n]).norm() / g_ref[n].norm()).item()
+        assert rel < 2e-2, (n, rel)
+    del g_ref
     assert m1.loss == pytest.approx(loss_ref, rel=1e-4)
     assert m1.l0 == pytest.approx(l0_ref, abs=1e-3)
     assert int(sae.step_count) == 1
