@@ -164,3 +164,45 @@ def test_deterministic_mode_is_bit_reproducible(shape, tmp_path):
     for n in ("encoder.weight", "decoder.weight"):
         rel = ((sa[n] - sc[n]).norm() / sc[n].norm()).item()
         assert rel < 1e-3, f"{n}: deterministic vs default rel-L2 {rel:.2e}"
+
+
+@pytest.mark.parametrize("rows,d,f", [(75776, 768, 6144), (37888, 1280, 40960)])
+def test_fullsize_step_gradients_small_and_large_v3(rows, d, f, tmp_path):
+    """BASELINE configs 3 / 4 at the bench's own batch sizes: loss, L0, fired set and the four gradient
+    tensors of ONE bf16 step against a dense fp32 statement with the same bf16 operand roundings in the
+    forward (the golden traces at these widths are 256-row batches)."""
+    from whisper_sae_b200.config import TrainingConfig
+    from whisper_sae_b200.sae import SAETrainer, TopKSAE
+
+    torch.manual_seed(42)
+    sae = TopKSAE(d, f, k=K, dead_feature_threshold=10_000)
+    tr = SAETrainer(sae, TrainingConfig(batch_size=rows, use_amp=True, num_workers=0), device="cuda", run_dir=tmp_path)
+    tr.setup_scheduler(1000)
+    x = O.synthetic_activations(rows, d, seed=17).cuda()
+    w = {n: p.detach().clone() for n, p in sae.named_parameters()}
+    with torch.no_grad():
+        xc = x - w["b_pre"]
+        pre = xc.to(torch.bfloat16).float() @ w["encoder.weight"].to(torch.bfloat16).float().t() + w["encoder.bias"]
+        v, i = torch.topk(pre, K, dim=1)
+        del pre
+        wd = w["decoder.weight"].t().to(torch.bfloat16).float()
+        hidden = torch.zeros(rows, f, device="cuda").scatter_(1, i, torch.relu(v))
+        resid = hidden.to(torch.bfloat16).float() @ wd + w["decoder.bias"] + w["b_pre"] - x
+        loss_ref = (resid ** 2).mean().item()
+        g = resid * (2.0 / (rows * d))
+        dpre = torch.zeros(rows, f, device="cuda").scatter_(1, i, (g @ wd.t()).gather(1, i) * (v > 0))
+        ref = {"encoder.weight": dpre.t() @ xc, "encoder.bias": dpre.sum(0), "decoder.bias": g.sum(0),
+               "decoder.weight": (hidden.t() @ g).t()}
+        ref["b_pre"] = ref["decoder.bias"] - ref["encoder.bias"] @ w["encoder.weight"]
+        fired = torch.zeros(f, dtype=torch.bool, device="cuda")
+        fired[i[v > 0]] = True
+        l0_ref = float((v > 0).sum()) / rows
+        del hidden, dpre, resid, g
+    m = tr.train_step(x)
+    assert m.loss == pytest.approx(loss_ref, rel=1e-4)
+    assert m.l0 == pytest.approx(l0_ref, abs=1e-3)
+    assert torch.equal(sae.feature_last_activated > 0, fired)
+    for n, p in sae.named_parameters():
+        rel = ((p.grad - ref[n]).norm() / ref[n].norm().clamp_min(1e-30)).item()
+        # db_pre = db_dec - db_enc . W_enc is a difference of nearly cancelling sums: looser
+        assert rel < (1e-1 if n == "b_pre" else 2e-2), (n, rel)
