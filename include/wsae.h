@@ -33,12 +33,15 @@ extern "C" {
 
 typedef void* wsae_stream_t; /* cudaStream_t */
 
-/* Library / build identification: returns 100 * major + minor of the ABI (currently 110: + wsae_encode_topk_dense, wsae_encode_dense, wsae_row_step). */
+/* Library / build identification: returns 100 * major + minor of the ABI (currently 111: + wsae_encode_topk_dense, wsae_encode_dense, wsae_row_step with the fused counters, wsae_graph_launch, wsae_memcpy_async). */
 int wsae_abi_version(void);
 
 /* cudaGraphLaunch(graph_exec, stream) for an instantiated CUDA graph of the calls below (the host mirror
  * captures one train step per batch shape; sae/training.py:161-217 is the step it replaces). */
 int wsae_graph_launch(void* graph_exec /* cudaGraphExec_t */, wsae_stream_t stream);
+
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream). */
+int wsae_memcpy_async(void* dst, const void* src, size_t bytes, wsae_stream_t stream);
 
 /* ---- K0: operand packing (sae/model.py:108 `x - b_pre`; bias of nn.Linear at :111) ------------
  * Packed row layout: `terms` blocks of dp = round_up(d, 8) bf16 columns (split-bf16 pieces), then
@@ -99,6 +102,9 @@ int wsae_encode_dense(const void* a_packed, const void* w_packed, int B, int Bp,
  * atomics): d_b_enc[F], d_b_dec[d], d_w_enc[F,d] += dv * (x - b_pre), d_w_decT[F,d] += coef*g*relu(v)*resid.
  * With w_enc (fp32 [F,d]) and d_b_pre both given, d_b_pre[d] += coef*g*resid - sum_j dv_j * w_enc[i_j, :]
  * (= db_dec - db_enc . W_enc summed over the rows, the job of wsae_bpre_grad).
+ * With ticket (a caller-zeroed uint32) given, the LAST block to finish also does wsae_counters_update_post's
+ * job: *step_count += 1, *dead_count = #{f: step - last_activated[f] > dead_threshold}, and {sse, l0, dead,
+ * *seq} posted to the pinned host `mailbox` (4 x int64) behind a system-scope fence.
  * resid / dpre_val / any gradient pointer may be NULL.  k <= 32, d even, (F + 2 d) * 4 <= 200 KB.
  * Replaces wsae_encode_topk_dense's selection + wsae_decode_backward + wsae_bucket_by_tile + 2 x
  * wsae_wgrad_gemm for batches of a few hundred rows (the shipped YAML batch is 128). */
@@ -106,9 +112,10 @@ int wsae_row_step(const float* pre, const float* target, const float* const* tar
                   const long long* const* rows_at, const void* w_decT_bf16, const float* b_dec,
                   const float* b_pre, const float* grad_out, float coef, int B, int d, int F, int k,
                   float* out_val, int32_t* out_idx, void* stats, long long* last_activated,
-                  const long long* step_count, float* d_b_enc, float* d_b_dec, float* d_w_enc,
+                  long long* step_count, float* d_b_enc, float* d_b_dec, float* d_w_enc,
                   float* d_w_decT, float* resid, float* dpre_val, const float* w_enc, float* d_b_pre,
-                  wsae_stream_t stream);
+                  unsigned int* ticket, long long dead_threshold, long long* dead_count,
+                  const long long* seq, long long* mailbox, wsae_stream_t stream);
 
 /* ---- K2: k-sparse decode + MSE + L0 + fired stamps (sae/model.py:116,129,145,148,174-181) -----
  * recon = sum_j relu(val_j) * W_decT[idx_j,:] + b_dec (+ b_pre);  resid = recon - target.

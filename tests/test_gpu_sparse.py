@@ -353,3 +353,27 @@ def test_row_step_small_batch_form(B, d, F, k):
     close(dwd, s * dense_h.t() @ resid_ref, "dW_decT", rtol=1e-4, arel=1e-5)
     # db_pre = db_dec - db_enc . W_enc (what wsae_bpre_grad computes from the finished sums)
     close(dbp, s * resid_ref.sum(0) - dense_dv.sum(0) @ state["encoder.weight"], "db_pre", rtol=1e-4, arel=2e-5)
+
+    # with a ticket the LAST block also does the counters kernel's job: step_count += 1, dead count against the
+    # new step (model.py:183-195), {sse, l0, dead, seq} posted to the pinned host mailbox
+    stats2 = torch.zeros(3, dtype=torch.int64, device=dev)
+    last2 = torch.zeros(F, dtype=torch.int64, device=dev)
+    last2[: F // 2] = -5                        # half the features: last fired long ago
+    step2 = torch.tensor(6, dtype=torch.int64, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int64, device=dev)
+    seq = torch.tensor([77], dtype=torch.int64, device=dev)
+    mailbox = torch.zeros(4, dtype=torch.int64).pin_memory()
+    ops.row_step(pre, x.cuda(), w_decT.cuda().to(torch.bfloat16), state["decoder.bias"].cuda(),
+                 state["b_pre"].cuda(), torch.tensor(grad_out, device=dev), coef, k, stats=stats2,
+                 last_activated=last2, step_count=step2, d_b_enc=None, d_b_dec=None, d_w_enc=None, d_w_decT=None,
+                 finish=(ticket, 3, stats2[2:], seq, mailbox))
+    torch.cuda.synchronize()
+    assert int(step2) == 7 and int(ticket) == B
+    want_last2 = torch.zeros(F, dtype=torch.int64)
+    want_last2[: F // 2] = -5
+    want_last2[idx_c[val_c > 0]] = 7
+    dead = int(((7 - want_last2) > 3).sum())
+    assert torch.equal(last2.cpu(), want_last2)
+    assert int(stats2[2]) == dead
+    assert mailbox[3].item() == 77 and mailbox[2].item() == dead and mailbox[1].item() == int((val_c > 0).sum())
+    assert mailbox[:1].view(torch.float64).item() == pytest.approx((resid_ref.double() ** 2).sum().item(), rel=1e-6)

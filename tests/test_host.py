@@ -68,7 +68,7 @@ def test_library_exports_every_declared_symbol():
     for sym in sorted(declared):
         assert hasattr(raw, sym), f"{sym} declared in wsae.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS), "ctypes signature table out of sync with wsae.h"
-    assert lib.wsae_abi_version() == 110
+    assert lib.wsae_abi_version() == 111
     # pure host helpers can be called without a GPU
     dp, used, kp = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     assert lib.wsae_packed_k(384, 1, ctypes.byref(dp), ctypes.byref(used), ctypes.byref(kp)) == 0

@@ -83,9 +83,11 @@ _SIGNATURES = {
     "wsae_row_step": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
          c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p,
+         c_void_p, c_void_p],
         c_int,
     ),
+    "wsae_memcpy_async": ([c_void_p, c_void_p, ctypes.c_size_t, c_void_p], c_int),
     "wsae_decode_mse": (
         [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

@@ -40,10 +40,12 @@ row_step_kernel(const float* __restrict__ pre, const float* __restrict__ target,
                 const float* __restrict__ b_pre, const float* __restrict__ grad_out, float coef, int B, int d,
                 int F, int k, float* __restrict__ out_val, int32_t* __restrict__ out_idx,
                 double* __restrict__ stats_sse, unsigned long long* __restrict__ stats_l0,
-                long long* __restrict__ last_activated, const long long* __restrict__ step_count,
+                long long* __restrict__ last_activated, long long* step_count,
                 float* __restrict__ d_b_enc, float* __restrict__ d_b_dec, float* __restrict__ d_w_enc,
                 float* __restrict__ d_w_decT, float* __restrict__ resid_out, float* __restrict__ dpre_val,
-                const float* __restrict__ w_enc, float* __restrict__ d_b_pre) {
+                const float* __restrict__ w_enc, float* __restrict__ d_b_pre, unsigned int* ticket,
+                long long dead_threshold, long long* dead_count, const long long* seq_src,
+                long long* mailbox) {
   extern __shared__ __align__(16) uint32_t s_dyn[];          // [F] keys | [d] residual | [d] x - b_pre
   __shared__ RowSelectSmem sel;
   __shared__ float s_val[kRowStepMaxK];                      // selected pre-activations, ascending feature index
@@ -208,6 +210,43 @@ row_step_kernel(const float* __restrict__ pre, const float* __restrict__ target,
       atomicAdd(d_b_pre + c + 1, g1);
     }
   }
+
+  // ---- the step's counters and metrics, by the LAST block to finish (ticket != NULL): what
+  //      counters_update_kernel does in a launch of its own - bump step_count (model.py:174), count the dead
+  //      features against the new step (model.py:183-195), post {sse, l0, dead, seq} to the host mailbox ----
+  if (ticket != nullptr) {
+    __shared__ int s_last;
+    __shared__ int s_part[kRowTopkThreads / 32];
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();                                       // this block's stamps / sums before its ticket
+      s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const long long sc = *step_count + 1;                  // every block read the old value long ago
+      int c = 0;
+      for (int f = tid; f < F; f += kRowTopkThreads) c += ((sc - __ldcg(last_activated + f)) > dead_threshold) ? 1 : 0;
+      c = static_cast<int>(warp_sum(static_cast<float>(c)));  // <= F / 8 per warp: exact in fp32
+      if (lane == 0) s_part[warp] = c;
+      __syncthreads();
+      if (tid == 0) {
+        long long t = 0;
+        for (int w = 0; w < kRowTopkThreads / 32; ++w) t += s_part[w];
+        *step_count = sc;
+        if (dead_count != nullptr) *dead_count = t;
+        if (mailbox != nullptr) {
+          volatile long long* mb = mailbox;
+          mb[0] = stats_sse != nullptr ? __ldcg(reinterpret_cast<const long long*>(stats_sse)) : 0;
+          mb[1] = stats_l0 != nullptr ? static_cast<long long>(__ldcg(stats_l0)) : 0;
+          mb[2] = t;
+          __threadfence_system();
+          mb[3] = *seq_src;
+        }
+      }
+    }
+  }
 }
 
 }  // namespace wsae
@@ -219,12 +258,14 @@ extern "C" int wsae_row_step(const float* pre, const float* target, const float*
                              const long long* const* rows_at, const void* w_decT_bf16, const float* b_dec,
                              const float* b_pre, const float* grad_out, float coef, int B, int d, int F, int k,
                              float* out_val, int32_t* out_idx, void* stats, long long* last_activated,
-                             const long long* step_count, float* d_b_enc, float* d_b_dec, float* d_w_enc,
+                             long long* step_count, float* d_b_enc, float* d_b_dec, float* d_w_enc,
                              float* d_w_decT, float* resid, float* dpre_val, const float* w_enc, float* d_b_pre,
-                             cudaStream_t stream) {
+                             unsigned int* ticket, long long dead_threshold, long long* dead_count,
+                             const long long* seq, long long* mailbox, cudaStream_t stream) {
   if (!pre || (!target && !target_at) || !w_decT_bf16 || !b_dec || !out_val || !out_idx) return kBadArg;
   if (B <= 0 || d <= 0 || F <= 0 || k <= 0 || k > F) return kBadArg;
   if (k > kRowStepMaxK || d % 2 != 0) return kUnsupported;
+  if (ticket != nullptr && (!step_count || !last_activated || (mailbox != nullptr && !seq))) return kBadArg;
   const size_t smem = (static_cast<size_t>(F) + 2 * static_cast<size_t>(d)) * 4;
   if (smem > 200 * 1024) return kUnsupported;
   int dev = 0;
@@ -240,6 +281,6 @@ extern "C" int wsae_row_step(const float* pre, const float* target, const float*
   cudaError_t e = launch_pdl(row_step_kernel, B, kRowTopkThreads, smem, stream, pre, target, target_at, rows_at,
                              static_cast<const __nv_bfloat16*>(w_decT_bf16), b_dec, b_pre, grad_out, coef, B, d, F,
                              k, out_val, out_idx, sse, l0, last_activated, step_count, d_b_enc, d_b_dec, d_w_enc,
-                             d_w_decT, resid, dpre_val, w_enc, d_b_pre);
+                             d_w_decT, resid, dpre_val, w_enc, d_b_pre, ticket, dead_threshold, dead_count, seq, mailbox);
   return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
 }

@@ -280,6 +280,15 @@ def backward_sparse(resid: Tensor, x: Tensor | None, b_pre: Tensor | None, w_dec
     _run("wsae_backward_sparse", lib.wsae_backward_sparse, _ptr(resid), _ptr(x), _ptr(b_pre), _ptr(w_decT), int(w_decT.dtype == torch.bfloat16), _ptr(idx), _ptr(val), _ptr(grad_out), float(coef), B, d, F, k, _ptr(d_w_enc), _ptr(d_w_decT), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(dpre_val), _ptr(resid_bf16), _stream())
 
 
+def memcpy_async(dst: Tensor, src: Tensor) -> None:
+    """cudaMemcpyAsync of ``src`` (pinned host or device, contiguous) into ``dst`` on the current stream."""
+    n = src.numel() * src.element_size()
+    if n != dst.numel() * dst.element_size():
+        raise RuntimeError("memcpy_async: size mismatch")
+    lib = _lib.load()
+    _lib.check(lib.wsae_memcpy_async(dst.data_ptr(), src.data_ptr(), n, _stream()), "wsae_memcpy_async")
+
+
 def graph_launch(graph_exec: int) -> None:
     """cudaGraphLaunch(graph_exec, current stream) through the library (see SAETrainer's graphed step)."""
     lib = _lib.load()
@@ -313,7 +322,8 @@ def row_step(pre: Tensor, target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: 
              d_b_dec: Tensor | None, d_w_enc: Tensor | None, d_w_decT: Tensor | None,
              resid: Tensor | None = None, dpre_val: Tensor | None = None, target_is_slot: bool = False,
              rows_at: Tensor | None = None, w_enc: Tensor | None = None,
-             d_b_pre: Tensor | None = None) -> tuple[Tensor, Tensor]:
+             d_b_pre: Tensor | None = None,
+             finish: tuple[Tensor, int, Tensor | None, Tensor, Tensor] | None = None) -> tuple[Tensor, Tensor]:
     """Small-batch step, one block per row: TopK of ``pre`` + sparse decode + MSE + stamps + dv + bias
     gradients + both weight-gradient rows (fp32 atomics).  Returns (idx int32 [B,k], val fp32 [B,k])."""
     _need_cuda(pre, target, w_decT, b_dec, b_pre, grad_out)
@@ -332,10 +342,16 @@ def row_step(pre: Tensor, target: Tensor, w_decT: Tensor, b_dec: Tensor, b_pre: 
     idx = torch.empty((B, k), dtype=torch.int32, device=pre.device)
     val = torch.empty((B, k), dtype=torch.float32, device=pre.device)
     lib = _lib.load()
+    # finish = (ticket: zeroed 4+ bytes on the device, dead threshold, dead_count int64[1] | None, seq int64[1]
+    # on the device, mailbox: 4 x int64 pinned host): the last block also bumps step_count and posts the metrics
+    fin = (None, 0, None, None, None)
+    if finish is not None:
+        ticket, thr, dead, seq, mailbox = finish
+        fin = (_ptr(ticket), int(thr), _ptr(dead), _ptr(seq), _ptr(mailbox))
     _run("wsae_row_step", lib.wsae_row_step, _ptr(pre), _ptr(tgt), _ptr(tgt_at), _ptr(rows_at), _ptr(w_decT),
          _ptr(b_dec), _ptr(b_pre), _ptr(grad_out), float(coef), B, d, F, k, _ptr(val), _ptr(idx), _ptr(stats),
          _ptr(last_activated), _ptr(step_count), _ptr(d_b_enc), _ptr(d_b_dec), _ptr(d_w_enc), _ptr(d_w_decT),
-         _ptr(resid), _ptr(dpre_val), _ptr(w_enc), _ptr(d_b_pre), _stream())
+         _ptr(resid), _ptr(dpre_val), _ptr(w_enc), _ptr(d_b_pre), *fin, _stream())
     return idx, val
 
 

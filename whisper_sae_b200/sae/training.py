@@ -171,9 +171,10 @@ class _GraphedStep:
         # [gradient bucket | stats int64[3] | grad sum-of-squares f64] (tail 64-byte aligned)
         self.zeroed = torch.zeros(off + 16, dtype=torch.float32, device=dev)
         self.g_flat = self.zeroed[:off]
-        tail = self.zeroed[off:off + 8].view(torch.int64)
+        tail = self.zeroed[off:off + 16].view(torch.int64)
         self.stats = tail[0:3]
         self.sumsq = tail[3:4].view(torch.float64)
+        self.ticket = tail[4:5]           # block-completion ticket of the row step (zeroed with the rest)
         seg = [self.g_flat[s0:s0 + n] for s0, n in zip(starts, sizes)]
         self.g_b_pre, self.g_b_enc, self.g_b_dec = seg[0], seg[1], seg[2]
         self.g_w_enc, self.g_w_decT = seg[3].view(F, d), seg[4].view(F, d)
@@ -231,10 +232,10 @@ class _GraphedStep:
     def _pointer_key(self) -> tuple[int, ...]:
         m = self.trainer.model
         opt_state = self.trainer.optimizer.state
+        # the AdamW moments are not in the per-step key: optimizer.load_state_dict replaces them together with
+        # the `step` tensors, which run() notices (and then drops the graph) when it validates its step views
         ptrs = [p.data_ptr() for p in self.params]
         ptrs += [m.feature_last_activated.data_ptr(), m.step_count.data_ptr()]
-        for p in self.params:
-            ptrs += [opt_state[p]["exp_avg"].data_ptr(), opt_state[p]["exp_avg_sq"].data_ptr()]
         return tuple(ptrs)
 
     def _body(self) -> None:
@@ -372,13 +373,9 @@ class _GraphedStep:
                                     stats=self.stats, last_activated=m.feature_last_activated,
                                     step_count=m.step_count, d_b_enc=self.g_b_enc, d_b_dec=self.g_b_dec,
                                     d_w_enc=self.g_w_enc, d_w_decT=self.g_w_decT, target_is_slot=True,
-                                    rows_at=self.rows_slot, w_enc=m.encoder.weight.data, d_b_pre=self.g_b_pre)
-            if self.fork:
-                self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):      # joined in _update_pre, before the gradient norm
-                    self._counters()
-            else:
-                self._counters()
+                                    rows_at=self.rows_slot, w_enc=m.encoder.weight.data, d_b_pre=self.g_b_pre,
+                                    finish=(self.ticket, m.dead_feature_threshold, self.stats[2:], self.seq_dev,
+                                            self.mailbox))      # counters + metrics mailbox by the last block
             self._k4_forked = False
             self._mid = dict(use_gemm=False, buckets=None, resid_bf=None, B=B, d=d, coef=coef)
             st = self.state
@@ -570,6 +567,8 @@ class _GraphedStep:
             for p in self.params:
                 t = _ensure_adamw_state(tr.optimizer, p)["step"]
                 self._step_views.append((t, None if t.is_cuda else t.numpy()))
+            self.graph = None             # new state tensors: the captured moment pointers are void
+            self._exec = None
         t0, v0 = self._step_views[0]
         step_t = float(v0 if v0 is not None else t0) + 1.0
         beta1, beta2 = group["betas"]
@@ -578,7 +577,7 @@ class _GraphedStep:
         h[5] = 1.0 - beta1 ** step_t
         h[6] = math.sqrt(1.0 - beta2 ** step_t)
         h[7] = tr.config.gradient_clip
-        self.ctl.copy_(self.ctl_host, non_blocking=True)
+        ops.memcpy_async(self.ctl, self.ctl_host)      # 64 bytes, pinned -> device (raw cudaMemcpyAsync)
         self.calls += 1
         wd = tr.model.decoder.weight
         if wd.stride() != (1, wd.shape[0]):      # feature-major storage lost (.data assigned): re-point it
