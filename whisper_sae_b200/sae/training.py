@@ -638,7 +638,10 @@ class _GraphedStep:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 before = ops.GPU_LAUNCHES
-                with _quiet_gc(), torch.cuda.graph(g):
+                # data parallel (WSAE_DP_GRAPH=1): the NCCL watchdog thread queries events while this thread
+                # captures - under the default "global" mode that alone invalidates the capture
+                mode = "thread_local" if tr.data_parallel else "global"
+                with _quiet_gc(), torch.cuda.graph(g, capture_error_mode=mode):
                     self._body()
                 self.kernels_per_replay = ops.GPU_LAUNCHES - before   # captured, not yet executed
                 ops.GPU_LAUNCHES = before
