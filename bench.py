@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import argparse
 import contextlib
+import gc
 import json
 import os
 import statistics
@@ -691,8 +692,9 @@ def side_workload(name: str, batch: int, dev: str, rank: int, world: int, steps:
            "ms_per_step": 1e3 * blk["median"] / steps,
            "ms_per_step_min_max": [1e3 * blk["min"] / steps, 1e3 * blk["max"] / steps],
            "gpu_launches": launches, "clocks": clocks.summary()}
+    tr.release_graphs()      # (captured graphs that hold NCCL kernels must not outlive the communicator)
+    del tr
     if profile:
-        del tr
         tr_e, _ = make_trainer(wl, batch, dev, layer_seed=0, cuda_graph="eager")
         with serial_kernels():
             for i in range(3):
@@ -702,6 +704,7 @@ def side_workload(name: str, batch: int, dev: str, rank: int, world: int, steps:
         out["kernels"] = {n: {kk: vv for kk, vv in e.items() if kk not in ("per_step",)} for n, e in table.items()}
         del tr_e
     del batches, rows
+    gc.collect()
     torch.cuda.empty_cache()
     return out
 
@@ -774,6 +777,9 @@ def main() -> None:
                               "ms_per_step": 1e3 * sec / args.steps, "gpu_launches": launches,
                               "note": "value-only leg (not a bench line)"}))
         if dist_on:
+            tr.release_graphs()
+            del tr
+            gc.collect()
             torch.distributed.destroy_process_group()
         return
 
@@ -838,7 +844,9 @@ def main() -> None:
             "deterministic_mode": det_info,
             "resident_loader": resident,
         }
+    tr.release_graphs()
     del tr, dev_batches, host_batches, rows
+    gc.collect()
     torch.cuda.empty_cache()
 
     # ---- `workloads` block: BASELINE configs[2] / [3] ----
@@ -872,11 +880,13 @@ def main() -> None:
                 line["cpu_baseline_port"] = port
             else:
                 line["cpu_baseline"] = port
+    if line is not None:
+        print(json.dumps(line), flush=True)
     if dist_on:
         torch.distributed.barrier()
+        gc.collect()                 # captured graphs that hold NCCL kernels must be gone before the communicator
+        torch.cuda.synchronize()
         torch.distributed.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -23,6 +23,7 @@ import gc
 import json
 import math
 import os
+import weakref
 from dataclasses import asdict, dataclass
 from pathlib import Path
 
@@ -82,6 +83,36 @@ def _quiet_gc():
     finally:
         if was_on:
             gc.enable()
+
+
+_DP_GRAPH_TRAINERS: "weakref.WeakSet[SAETrainer]" = weakref.WeakSet()
+
+
+def _guard_process_group_teardown(trainer: "SAETrainer") -> None:
+    """Whole-step capture with the NCCL collectives inside (WSAE_DP_GRAPH=1): destroying the communicator
+    while a captured graph still holds its kernels blocks forever (what looked like a capture hang in
+    round 1 was exactly this, at the end of the run).  Live trainers therefore drop their graphs right
+    before ``torch.distributed.destroy_process_group`` and at interpreter exit."""
+    import atexit
+
+    import torch.distributed as dist
+
+    _DP_GRAPH_TRAINERS.add(trainer)
+
+    def release_all() -> None:
+        for tr in list(_DP_GRAPH_TRAINERS):
+            tr.release_graphs()
+
+    if not getattr(dist.destroy_process_group, "_wsae_guard", False):
+        original = dist.destroy_process_group
+
+        def destroy_process_group(*args, **kwargs):
+            release_all()
+            return original(*args, **kwargs)
+
+        destroy_process_group._wsae_guard = True
+        dist.destroy_process_group = destroy_process_group
+        atexit.register(release_all)
 
 
 class _GraphedStep:
@@ -750,15 +781,18 @@ class SAETrainer:
             self.dp_comm = dp_comm if dp_comm is not None else TorchDistCommunicator()
             if not (is_cuda and self.fused_optimizer) or self.scaler.is_enabled():
                 raise RuntimeError("data_parallel=True needs the fused CUDA step (no GradScaler)")
-            # collectives between the kernels: the step is launched kernel by kernel.  Capturing the
-            # NCCL calls into the step's CUDA graph (WSAE_DP_GRAPH=1, experimental) hung on the
-            # 2-GPU box in round 1 and stays off by default.
+            # collectives between the kernels: four graph segments with eager NCCL calls between them (default).
+            # WSAE_DP_GRAPH=1 captures the NCCL calls into ONE graph per step (measured on 2 GPUs: small
+            # 2.38 -> 2.31 ms weak, 1.37 -> 1.33 ms strong; opt-in: the communicator must not be destroyed
+            # while such a graph is alive - see _guard_process_group_teardown).
             graph_ok = getattr(self.dp_comm, "graph_safe", False) and \
                 os.environ.get("WSAE_DP_GRAPH", "0") == "1" and self.cuda_graph is not False
             # default for real process groups: graph the kernel segments, keep the collectives eager
             seg_ok = getattr(self.dp_comm, "graph_safe", False) and self.cuda_graph is not False and \
                 os.environ.get("WSAE_DP_SEGMENTS", "1") != "0"
             self.cuda_graph = True if graph_ok else ("segments" if seg_ok else "eager")
+            if graph_ok:
+                _guard_process_group_teardown(self)
 
     # ------------------------------------------------------------------ resampling plumbing
     def set_resample_dataset(self, dataset: torch.utils.data.Dataset) -> None:
@@ -1038,6 +1072,19 @@ class SAETrainer:
         }
         torch.save(payload, path)
         return path
+
+    def release_graphs(self) -> None:
+        """Drop the captured CUDA graphs (they are re-captured on the next step).  Call it before
+        ``torch.distributed.destroy_process_group()`` when the step's NCCL collectives are captured into
+        the graph (``WSAE_DP_GRAPH=1``): destroying the communicator while graphs that hold its kernels
+        are alive blocks forever."""
+        for gs in self._graphs.values():
+            gs.graph = None
+            gs._exec = None
+        self._graphs.clear()
+        gc.collect()
+        if str(self.device).startswith("cuda"):
+            torch.cuda.synchronize(self.device)
 
     def consolidate_weights(self) -> None:
         """Data parallel with the bf16 operand gather: a replica keeps only ITS feature rows of the fp32
