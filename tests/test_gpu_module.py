@@ -590,3 +590,30 @@ def test_dense_model_trains_under_bf16_autocast(tmp_path):
         for _ in range(20):
             last = tr.train_step(x).loss
         assert seen[0] == want and last < first
+
+
+def test_release_graphs_recaptures_without_changing_the_trajectory(tmp_path):
+    """SAETrainer.release_graphs() (needed before a process group is destroyed when the step's NCCL calls are
+    captured) drops the captured step; the next call runs eagerly, the one after re-captures, and the losses
+    are those of an uninterrupted run."""
+    _, TrainingConfig, _, SAETrainer, TopKSAE, _ = _mods()
+    d, F, k, B = 384, 3072, 32, 1024
+    x = O.synthetic_activations(6 * B, d, 77).cuda()
+
+    def run(release_at):
+        torch.manual_seed(9)
+        tr = SAETrainer(TopKSAE(d, F, k=k), TrainingConfig(batch_size=B, use_amp=True, num_workers=0),
+                        device="cuda", run_dir=tmp_path / f"r{release_at}")
+        tr.setup_scheduler(100)
+        out = []
+        for s in range(6):
+            if s == release_at:
+                assert tr._graphs[B].graph is not None
+                tr.release_graphs()
+                assert not tr._graphs
+            out.append(tr.train_step(x[s * B:(s + 1) * B]).loss)
+        return out
+
+    a, b = run(None), run(3)
+    for p, q in zip(a, b):
+        assert p == pytest.approx(q, rel=1e-5)
