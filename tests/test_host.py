@@ -257,3 +257,49 @@ def test_choose_nsplit():
     assert choose_nsplit(65536, 3072, 32, 148) == 1        # per-item start-up cost beats tail filling
     assert choose_nsplit(8, 128, 4, 148) == 1              # a single tile cannot be split
     assert choose_nsplit(64, 40960, 64, 148) <= 32         # merge kernel limit: nsplit*k <= 2048
+
+
+def test_row_step_shape_rule(monkeypatch):
+    """Which batches take the one-block-per-row small-batch step (wsae_row_step)."""
+    from whisper_sae_b200.ops import row_step_supported
+
+    assert row_step_supported(128, 384, 3072, 32, True)             # the shipped YAML batch
+    assert row_step_supported(512, 768, 6144, 32, True)
+    assert not row_step_supported(1024, 384, 3072, 32, True)        # large-batch chain (K23 + K4) from here on
+    assert not row_step_supported(128, 384, 3072, 64, True)         # k > 32
+    assert not row_step_supported(128, 384, 3072, 32, False)        # fp32-grade mode keeps K2 + K3
+    assert not row_step_supported(128, 1280, 65536, 32, True)       # keys + row do not fit shared memory
+    monkeypatch.setenv("WSAE_ROW_STEP_ROWS", "0")
+    assert not row_step_supported(128, 384, 3072, 32, True)
+
+
+def test_graphed_variant_step_refuses_cpu_and_plain_optimizers():
+    from whisper_sae_b200.sae import GraphedVariantStep, make_optimizer
+    from whisper_sae_b200.sae.transcoder import TopKTranscoder
+
+    m = TopKTranscoder(16, 16, 32, k=4)
+    opt = make_optimizer(m, lr=1e-3)
+    assert all(g["capturable"] for g in opt.param_groups)
+    with pytest.raises(RuntimeError):
+        GraphedVariantStep(m, opt)                                   # CPU module: no fallback
+
+
+def test_process_group_teardown_guard_releases_graphs_first(monkeypatch):
+    """WSAE_DP_GRAPH=1 mode: live trainers drop their captured graphs before the communicator goes away."""
+    import torch.distributed as dist
+
+    from whisper_sae_b200.sae import training
+
+    calls = []
+
+    class FakeTrainer:
+        def release_graphs(self):
+            calls.append("release")
+
+    monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: calls.append("destroy"))
+    monkeypatch.setattr(training, "_DP_GRAPH_TRAINERS", __import__("weakref").WeakSet())
+    t = FakeTrainer()
+    training._guard_process_group_teardown(t)
+    training._guard_process_group_teardown(t)                        # installs the wrapper once
+    dist.destroy_process_group()
+    assert calls == ["release", "destroy"]
