@@ -439,13 +439,14 @@ def kernel_profile(tr, batches, steps: int) -> dict:
 
 # dram__bytes_read.sum + dram__bytes_write.sum and lts__t_sectors.sum x 32 B per launch from `ncu --set
 # full` of each workload's default batch (bf16): profiles/r2c_{tiny,small-dp,large-dp}_top3_ncu_full.txt
-# (K1 = CTA-pair kernel, K23 = tensor form, K4 averaged over its two launches)
+# (K1 = CTA-pair kernel, K4 averaged over its two launches); K23 = tensor form with the L2 eviction hints:
+# profiles/r2d_{tiny,small-dp,large-dp}_k23_ncu_full.txt
 NCU_TRAFFIC = {
-    "tiny": {"wsae_encode_topk": (74.56e6, 1704.9e6), "wsae_decode_backward": (246.43e6, 2285.5e6),
+    "tiny": {"wsae_encode_topk": (74.56e6, 1704.9e6), "wsae_decode_backward": (155.07e6, 2248.7e6),
              "wsae_wgrad_gemm": (88.89e6, 925.6e6)},
-    "small-dp": {"wsae_encode_topk": (155.82e6, 6022.0e6), "wsae_decode_backward": (896.37e6, 4655.6e6),
+    "small-dp": {"wsae_encode_topk": (155.82e6, 6022.0e6), "wsae_decode_backward": (337.65e6, 4410.4e6),
                  "wsae_wgrad_gemm": (289.79e6, 3436.5e6)},
-    "large-dp": {"wsae_encode_topk": (334.74e6, 23662.3e6), "wsae_decode_backward": (1541.80e6, 8688.1e6),
+    "large-dp": {"wsae_encode_topk": (334.74e6, 23662.3e6), "wsae_decode_backward": (1421.41e6, 8744.3e6),
                  "wsae_wgrad_gemm": (1094.70e6, 17442.1e6)},
 }
 NCU_SOURCE = "profiles/r2c_{wl}_top3_ncu_full.txt"
